@@ -1,0 +1,147 @@
+/* b200rl -- C-ABI of the B200-native learner-update path.
+ *
+ * The reference (ymg1114/pytorch-distributed-reinforcement-learning) is pure Python
+ * and has no FFI of its own: its seams are Python call
+ * boundaries.  This header declares the native entry points that the Python shims
+ * in `pytorch-distributed-reinforcement-learning_b200/b200rl/` bind with ctypes; each
+ * entry point cites the reference code it replaces (paths relative to the reference
+ * root).  INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous fp32 unless stated otherwise
+ *     (the reference stores every rollout field as fp32,
+ *     agents/storage_module/shared_batch.py:15,28-46);
+ *   - batch-major layout (B, T, width), exactly what
+ *     agents/learner.py:197-233 hands to `learning()`;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - return 0 on success, non-zero on error; `b200rl_last_error()` gives the text.
+ *     Nothing aborts the process (SURVEY.md 8b "Errors").
+ *   - H (LSTM width) is 64, the reference's `hidden_size` (utils/parameters.json:10).
+ */
+#ifndef B200RL_H_
+#define B200RL_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200RL_H 64
+#define B200RL_MAX_HEADS 32   /* NH <= 32 head outputs per net */
+#define B200RL_MAX_ACT 8      /* discrete A / continuous act_dim <= 8 */
+
+int b200rl_version(void);
+const char* b200rl_last_error(void);
+
+/* ---- per-timestep recurrences --------------------------------------------------
+ * compute_gae(deltas, gamma, lambda_)          agents/learner_module/compute_loss.py:7-19
+ *   deltas (B, n, 1) -> gae (B, n, 1);  g[t] = d[t] + gamma*lambda*g[t+1]           */
+int b200rl_compute_gae(const float* deltas, float* gae, int B, int n,
+                       float gamma, float lambda_, void* stream);
+
+/* td target + delta + GAE fused           agents/learner_module/ppo/learning.py:48-57
+ *   rew, is_fir, value (B, T, 1) -> td_target (B, T-1, 1), gae (B, T-1, 1)           */
+int b200rl_td_gae(const float* rew, const float* is_fir, const float* value,
+                  float* td_target, float* gae, int B, int T,
+                  float gamma, float lambda_, void* stream);
+
+/* compute_v_trace(...)                        agents/learner_module/compute_loss.py:22-66
+ *   5 inputs (B, T, 1) -> rho (B,T-1,1), advantages (B,T-1,1), values_target (B,T,1) */
+int b200rl_compute_v_trace(const float* behav_logp, const float* target_logp,
+                           const float* is_fir, const float* rew, const float* values,
+                           float* rho, float* adv, float* vs, int B, int T,
+                           float gamma, float rho_bar, float c_bar, void* stream);
+
+/* kldivergence(logits_p, logits_q)            agents/learner_module/compute_loss.py:74-77
+ *   (rows, A) x2 -> (rows)                                                            */
+int b200rl_kldivergence(const float* logits_p, const float* logits_q, float* kl,
+                        long long rows, int A, void* stream);
+
+/* soft_update(critic, target, tau)            agents/learner_module/compute_loss.py:69-71
+ *   target <- (1-tau) target + tau src over n flat floats (src may alias target)      */
+int b200rl_soft_update(const float* src, float* target, long long n, float tau, void* stream);
+
+/* ---- torso + LSTMCell-over-T + linear heads -------------------------------------
+ * Replaces MlpLSTMBase.forward / MlpLSTMActor* / MlpLSTMCritic* forward and its
+ * autograd backward                                  networks/models.py:63-100,135-322
+ *
+ * u      (B, T, Fin)  torso input (obs, or [obs|act] for the continuous critic)
+ * hx0/cx0 (B, H)      LSTM state before step 0 (`hx[:,0]`, ppo/learning.py:37-40)
+ * Wt (H, Fin), bt (H) torso Linear;  W_ih/W_hh (4H, H), b_ih/b_hh (4H) PyTorch layout
+ * saved activations (private layout, only lstm_bwd / lstm_wgrad read them):
+ *   gates (B, T, H, 4) post-activation i,f,g,o ; c (B, T, H) ; h (B, T, H)
+ * `variant`: 0 = default kernel.                                                     */
+int b200rl_lstm_fwd(const float* u, const float* hx0, const float* cx0,
+                    const float* Wt, const float* bt,
+                    const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh,
+                    float* gates, float* c, float* h,
+                    int B, int T, int Fin, int variant, void* stream);
+
+/* head_out (rows, NH) = h (rows, H) . W_head^T (NH, H) + b_head                      */
+int b200rl_head_fwd(const float* h, const float* W_head, const float* b_head,
+                    float* head_out, long long rows, int NH, void* stream);
+
+/* BPTT, serial part: consumes dhead (B,T,NH) = dLoss/dhead_out and OVERWRITES `gates`
+ * in place with dLoss/d(gate pre-activations) (same (B,T,H,4) layout).               */
+int b200rl_lstm_bwd(const float* dhead, const float* W_head, const float* W_hh,
+                    float* gates, const float* c, const float* cx0,
+                    int B, int T, int NH, int variant, void* stream);
+
+/* BPTT, parallel part: weight gradients as `nparts` partial slabs of `P` floats each
+ * (partials[part*P + off_*]); also the torso-input gradient du (B,T,Fin) if non-NULL. */
+int b200rl_lstm_wgrad(const float* dpre, const float* h, const float* hx0, const float* u,
+                      const float* dhead, const float* Wt, const float* bt, const float* W_ih,
+                      float* partials, int nparts, long long P,
+                      long long off_Wt, long long off_bt, long long off_Wih, long long off_Whh,
+                      long long off_bih, long long off_bhh, long long off_Whead, long long off_bhead,
+                      float* du, int B, int T, int Fin, int NH, int variant, void* stream);
+
+/* grad[i] = sum_part partials[part*P + i]                                             */
+int b200rl_reduce_partials(const float* partials, float* grad, int nparts, long long P, void* stream);
+
+/* ---- loss heads (scan + loss + dLoss/dhead_out in one pass) ----------------------
+ * scalars: device array of 8 doubles, ACCUMULATED into (caller zeroes):
+ *   [0] sum policy term  [1] sum value term  [2] sum entropy  [3] sum ratio
+ *   [4] min ratio (as +value) [5] max ratio  [6],[7] algorithm specific
+ * PPO head                                    agents/learner_module/ppo/learning.py:43-81
+ *   head_out (B,T,NH): discrete NH=1+A -> [value, z_0..z_{A-1}];
+ *                      continuous NH=1+2A (A==1) -> [value, z_mu, z_std]
+ *   optional outputs (may be NULL): logits_norm (B,T,A), logp (B,T), entropy (B,T),
+ *   td_target (B,T-1), gae (B,T-1), ratio (B,T-1)                                     */
+int b200rl_ppo_head(const float* head_out, const float* act, const float* rew,
+                    const float* is_fir, const float* behav_logp,
+                    float* dhead, double* scalars,
+                    float* logits_norm, float* logp, float* entropy,
+                    float* td_target, float* gae, float* ratio,
+                    int B, int T, int A, int continuous,
+                    float gamma, float lambda_, float eps_clip,
+                    float c_policy, float c_value, float c_entropy, void* stream);
+
+/* IMPALA head                              agents/learner_module/impala/learning.py:43-69
+ *   optional outputs: logits_norm, logp, entropy, rho (B,T-1), adv (B,T-1), vs (B,T)  */
+int b200rl_impala_head(const float* head_out, const float* act, const float* rew,
+                       const float* is_fir, const float* behav_logp,
+                       float* dhead, double* scalars,
+                       float* logits_norm, float* logp, float* entropy,
+                       float* rho, float* adv, float* vs,
+                       int B, int T, int A,
+                       float gamma, float rho_bar, float c_bar,
+                       float c_policy, float c_value, float c_entropy, void* stream);
+
+/* ---- optimizer step ---------------------------------------------------------------
+ * clip_grad_norm_(max_norm) + RMSprop(lr, alpha, eps)
+ *                    agents/learner_module/ppo/learning.py:93-106, agents/learner.py:70
+ * grad is scaled in place by `grad_scale` first (1/world_size after an allreduce-sum),
+ * then clipped; norm_out (1 float, may be NULL) receives the pre-clip L2 norm.        */
+int b200rl_clip_rmsprop(float* param, float* grad, float* sq_avg, long long n,
+                        float grad_scale, float max_norm, float lr, float alpha, float eps,
+                        float* norm_out, void* stream);
+
+/* clip_grad_norm_ + Adam (bias-corrected, step = 1-based)   agents/learner.py:360-367 */
+int b200rl_clip_adam(float* param, float* grad, float* m, float* v, long long n,
+                     float grad_scale, float max_norm, float lr, float beta1, float beta2,
+                     float eps, int step, float* norm_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RL_H_ */

@@ -1,0 +1,136 @@
+"""The learner update as a fixed sequence of native kernel launches.
+
+One `OnPolicyEngine.update(batch)` is what one epoch of the reference's `learning()`
+body does (`agents/learner_module/{ppo,impala}/learning.py:36-106`): forward over the
+(B, T) window, GAE / V-trace, loss, backward, clip_grad_norm_, RMSprop step -- with no
+Python loop over T, no autograd graph and no host sync:
+
+    lstm_fwd -> head_fwd -> {ppo,impala}_head -> lstm_bwd -> lstm_wgrad
+             -> reduce_partials -> [NCCL all-reduce of the flat gradient] -> clip_rmsprop
+
+Multi-GPU: sequences are independent, every loss is a mean over
+B*(T-1) elements, so B shards evenly across ranks; each rank computes the gradient of
+its shard mean, ONE all-reduce(sum) of the flat gradient (+ the 8 loss scalars riding
+in a second tiny buffer) and a 1/world scale inside the optimizer kernel reproduce the
+full-batch gradient; the global-norm clip comes after the reduction.
+"""
+import math
+
+import torch
+
+from . import ops as _ops
+
+H = _ops.H
+
+_SCALAR_INIT = [0.0, 0.0, 0.0, 0.0, float("inf"), float("-inf"), 0.0, 0.0]
+
+
+def _sm_count(device, ops):
+    if ops.lib.emulated or device.type != "cuda":
+        return 4
+    return torch.cuda.get_device_properties(device).multi_processor_count
+
+
+class OnPolicyEngine:
+    """PPO / PPO-Continuous / IMPALA update for one `_FlatNet` actor-critic."""
+
+    def __init__(self, net, algo, hyper, ops=None, process_group=None):
+        self.net, self.algo, self.hp = net, algo, dict(hyper)
+        self.ops = ops or _ops.default()
+        self.pg = process_group
+        self.world = 1 if process_group is None else torch.distributed.get_world_size(process_group)
+        self.flat = net.flat_parameters()
+        self.L = net._layout
+        dev = self.flat.device
+        self.device = dev
+        self.grad = torch.zeros_like(self.flat)
+        self.sq_avg = torch.zeros_like(self.flat)            # RMSprop state (learner.py:70)
+        self.scalars = torch.zeros(8, dtype=torch.float64, device=dev)
+        self._scalar_init = torch.tensor(_SCALAR_INIT, dtype=torch.float64, device=dev)
+        self.grad_norm = torch.zeros(1, device=dev)
+        self._shape = None
+        self.n_launches = 0
+        self.debug_outs = None                                # set to {} to capture intermediates
+
+    # ------------------------------------------------------------------ workspace
+    def _workspace(self, B, T):
+        if self._shape == (B, T):
+            return
+        dev, L = self.device, self.L
+        self.ws = dict(gates=torch.empty(B, T, H, 4, device=dev), c=torch.empty(B, T, H, device=dev),
+                       h=torch.empty(B, T, H, device=dev))
+        self.head_out = torch.empty(B, T, L.NH, device=dev)
+        self.dhead = torch.empty(B, T, L.NH, device=dev)
+        nchunks = (B * T + 31) // 32
+        self.nparts = max(1, min(_sm_count(dev, self.ops), nchunks))
+        self.partials = torch.zeros(self.nparts, L.P, device=dev)   # pad slots stay zero
+        self._shape = (B, T)
+
+    def _alloc_outs(self, B, T):
+        d, A, dev = self.debug_outs, self.net.n_outputs, self.device
+        names = {"PPO": ("td_target", "gae", "ratio"), "IMPALA": ("ratio", "advantages")}["IMPALA" if self.algo == "IMPALA" else "PPO"]
+        d.clear()
+        d["log_probs"] = torch.empty(B, T, 1, device=dev)
+        d["entropy"] = torch.empty(B, T, 1, device=dev)
+        if not self.net.continuous:
+            d["logits"] = torch.empty(B, T, A, device=dev)
+        for n in names:
+            d[n] = torch.empty(B, T - 1, 1, device=dev)
+        if self.algo == "IMPALA":
+            d["values_target"] = torch.empty(B, T, 1, device=dev)
+        return d
+
+    # --------------------------------------------------------------------- update
+    def update(self, batch):
+        """batch: dict of device tensors obs (B,T,f), act (B,T,1), rew, log_prob, is_fir (B,T,1),
+        hx, cx (B,H).  Asynchronous: enqueues kernels on the current stream."""
+        ops, L, hp = self.ops, self.L, self.hp
+        obs = batch["obs"]
+        B, T = obs.shape[0], obs.shape[1]
+        self._workspace(B, T)
+        u = obs.reshape(B, T, -1)
+        outs = self._alloc_outs(B, T) if self.debug_outs is not None else None
+
+        ops.lstm_fwd(L, self.flat, u, batch["hx"], batch["cx"], self.ws)
+        ops.head_fwd(L, self.flat, self.ws["h"], self.head_out)
+        self.scalars.copy_(self._scalar_init)
+        if self.algo == "IMPALA":
+            ops.impala_head(self.head_out, batch, self.dhead, self.scalars, hp, self.net.n_outputs, outs)
+        else:
+            ops.ppo_head(self.head_out, batch, self.dhead, self.scalars, hp, self.net.n_outputs,
+                         self.net.continuous, outs)
+        ops.lstm_bwd(L, self.flat, self.dhead, self.ws, batch["cx"])
+        ops.lstm_wgrad(L, self.flat, self.ws, batch["hx"], u, self.dhead, self.partials)
+        ops.reduce_partials(self.partials, self.grad)
+        scale = 1.0
+        if self.world > 1:
+            torch.distributed.all_reduce(self.grad, group=self.pg)          # the ONE gradient collective
+            scale = 1.0 / self.world
+        ops.clip_rmsprop(self.flat, self.grad, self.sq_avg, L.P, scale, hp["max_grad_norm"], hp["lr"],
+                         0.99, 1e-5, self.grad_norm)
+        self.n_launches += 8
+
+    # -------------------------------------------------------------------- scalars
+    def losses(self):
+        """Host copy of the loss scalars of the LAST update (synchronises).  Keys follow
+        the reference's `detached_losses` (ppo/learning.py:83-88); `ratio` is reduced to
+        (min, max, mean) instead of shipping the (B,T-1,1) tensor to the host."""
+        B, T = self._shape
+        s = self.scalars
+        if self.world > 1:
+            s = s.clone()
+            mm = torch.stack([-s[4], s[5]])
+            torch.distributed.all_reduce(mm, op=torch.distributed.ReduceOp.MAX, group=self.pg)
+            sums = s[:4].clone()
+            torch.distributed.all_reduce(sums, group=self.pg)
+            s = torch.cat([sums, torch.stack([-mm[0], mm[1]]), s[6:]])
+        v = s.cpu().tolist()
+        N = float(B * (T - 1) * self.world)
+        hp = self.hp
+        pol, val, ent = v[0] / N, v[1] / N, v[2] / N
+        return {
+            "policy-loss": pol, "value-loss": val, "policy-entropy": ent,
+            "loss": hp["policy_loss_coef"] * pol + hp["value_loss_coef"] * val - hp["entropy_coef"] * ent,
+            "ratio-min": v[4], "ratio-max": v[5], "ratio-avg": v[3] / N,
+            "grad-norm": float(self.grad_norm.item()),
+        }

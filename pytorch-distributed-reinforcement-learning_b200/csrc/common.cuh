@@ -1,0 +1,76 @@
+// Common device helpers for the b200rl kernels (sm_100a).
+//
+// B200RL_EMUL: a TEST-ONLY build mode (tests/emul/) that compiles these same kernel
+// sources with g++ and runs every CUDA thread as a host thread, so kernel indexing
+// can be debugged in the GPU-less build container.  It is never built, loaded or
+// shipped by the product (`__graft_entry__.build()` compiles with nvcc only).
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <stddef.h>
+#include "b200rl.h"
+
+#ifdef B200RL_EMUL
+#include "../../tests/emul/cuda_emul.h"
+#else
+#include <cuda_runtime.h>
+#define B200RL_DYN_SMEM(T, name) extern __shared__ __align__(128) unsigned char name##_raw_[]; T* name = reinterpret_cast<T*>(name##_raw_)
+#define B200RL_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#endif
+
+namespace b200rl {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+
+// Block-wide sum of doubles into lane 0 of warp 0 (valid for thread 0 only).
+// `scratch` must hold >= 32 doubles of shared memory.  Contains __syncthreads().
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (warp == 0) {
+        r = lane < nw ? scratch[lane] : 0.0;
+        r = warp_sum(r);
+    }
+    return r;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// F.smooth_l1_loss(beta=1) value and derivative wrt d = x - y.
+__device__ __forceinline__ float smooth_l1(float d) { float a = fabsf(d); return a < 1.0f ? 0.5f * d * d : a - 0.5f; }
+__device__ __forceinline__ float smooth_l1_grad(float d) { return fabsf(d) < 1.0f ? d : (d > 0.0f ? 1.0f : -1.0f); }
+
+}  // namespace b200rl
+
+// Error plumbing shared by the C-ABI entry points.
+namespace b200rl {
+int set_error(const char* fmt, ...);
+int check_launch(const char* what);
+}  // namespace b200rl
+#define B200RL_REQUIRE(cond, ...) do { if (!(cond)) return ::b200rl::set_error(__VA_ARGS__); } while (0)

@@ -1,0 +1,89 @@
+// Fused optimizer step on the flat parameter vector (sm_100a).
+//
+//   clip_grad_norm_(params, max_norm) + RMSprop.step()
+//        agents/learner_module/ppo/learning.py:93-106 ; optimizer built at agents/learner.py:70
+//   clip_grad_norm_ + Adam.step()       agents/learner.py:360-367 (SAC actor / twin critic)
+//
+// The model is tiny (33 795 fp32 parameters for the CartPole actor-critic), so the whole
+// step -- optional 1/world scaling after a gradient all-reduce, global L2 norm, clip
+// coefficient min(1, max_norm/(norm+1e-6)), moment update, parameter update -- is ONE
+// single-CTA launch: grid-wide sync for the norm would cost more than the 135 KB pass.
+#include "common.cuh"
+
+namespace b200rl {
+
+constexpr int kOptThreads = 1024;
+
+__device__ __forceinline__ float grad_norm_and_coef(const float* grad, long long n, float grad_scale,
+                                                    float max_norm, float* norm_out) {
+    __shared__ double scratch[32];
+    __shared__ float coef_s;
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < n; i += kOptThreads) {
+        const double g = (double)(grad[i] * grad_scale);
+        s += g * g;
+    }
+    const double tot = block_sum(s, scratch);
+    if (threadIdx.x == 0) {
+        const float norm = (float)sqrt(tot);
+        float coef = 1.0f;
+        if (max_norm > 0.0f) coef = fminf(max_norm / (norm + 1e-6f), 1.0f);
+        coef_s = coef;
+        if (norm_out) *norm_out = norm;
+    }
+    __syncthreads();
+    return coef_s;
+}
+
+__global__ void __launch_bounds__(kOptThreads)
+clip_rmsprop_kernel(float* __restrict__ param, float* __restrict__ grad, float* __restrict__ sq,
+                    long long n, float grad_scale, float max_norm, float lr, float alpha, float eps,
+                    float* norm_out) {
+    const float coef = grad_norm_and_coef(grad, n, grad_scale, max_norm, norm_out);
+    for (long long i = threadIdx.x; i < n; i += kOptThreads) {
+        const float g = grad[i] * grad_scale * coef;
+        grad[i] = g;                                        // .grad is left clipped, as in torch
+        const float v = sq[i] * alpha + (1.0f - alpha) * g * g;
+        sq[i] = v;
+        param[i] = param[i] - lr * (g / (sqrtf(v) + eps));
+    }
+}
+
+__global__ void __launch_bounds__(kOptThreads)
+clip_adam_kernel(float* __restrict__ param, float* __restrict__ grad, float* __restrict__ m,
+                 float* __restrict__ v, long long n, float grad_scale, float max_norm, float lr,
+                 float beta1, float beta2, float eps, int step, float* norm_out) {
+    const float coef = grad_norm_and_coef(grad, n, grad_scale, max_norm, norm_out);
+    const double bc1 = 1.0 - pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    const float step_size = (float)((double)lr / bc1);
+    const float rsq_bc2 = (float)(1.0 / sqrt(bc2));
+    for (long long i = threadIdx.x; i < n; i += kOptThreads) {
+        const float g = grad[i] * grad_scale * coef;
+        grad[i] = g;
+        const float mi = m[i] * beta1 + (1.0f - beta1) * g;
+        const float vi = v[i] * beta2 + (1.0f - beta2) * g * g;
+        m[i] = mi; v[i] = vi;
+        param[i] = param[i] - step_size * (mi / (sqrtf(vi) * rsq_bc2 + eps));
+    }
+}
+
+}  // namespace b200rl
+
+using namespace b200rl;
+
+extern "C" int b200rl_clip_rmsprop(float* param, float* grad, float* sq_avg, long long n,
+                                   float grad_scale, float max_norm, float lr, float alpha, float eps,
+                                   float* norm_out, void* stream) {
+    B200RL_REQUIRE(n >= 1, "clip_rmsprop: n=%lld", n);
+    B200RL_LAUNCH(clip_rmsprop_kernel, 1, kOptThreads, 0, stream, param, grad, sq_avg, n, grad_scale, max_norm, lr, alpha, eps, norm_out);
+    return check_launch("clip_rmsprop");
+}
+
+extern "C" int b200rl_clip_adam(float* param, float* grad, float* m, float* v, long long n,
+                                float grad_scale, float max_norm, float lr, float beta1, float beta2,
+                                float eps, int step, float* norm_out, void* stream) {
+    B200RL_REQUIRE(n >= 1 && step >= 1, "clip_adam: n=%lld step=%d", n, step);
+    B200RL_LAUNCH(clip_adam_kernel, 1, kOptThreads, 0, stream, param, grad, m, v, n, grad_scale, max_norm, lr, beta1, beta2, eps, step, norm_out);
+    return check_launch("clip_adam");
+}

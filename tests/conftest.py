@@ -41,3 +41,37 @@ def golden_sd(g, prefix):
     from collections import OrderedDict
     n = len(prefix) + 1
     return OrderedDict((k[n:], torch.from_numpy(v)) for k, v in g.items() if k.startswith(prefix + "/"))
+
+
+# ---------------------------------------------------------------- kernel back-ends
+# "cuda": the product library on a real GPU (marked gpu).
+# "emul": the SAME kernel sources compiled for the test-only host emulator
+#         (tests/emul) -- a debugging aid for the GPU-less build container; it is not
+#         a product path and is skipped automatically if g++ cannot build it.
+_EMUL = {}
+
+
+def _emul_ops():
+    if "ops" not in _EMUL:
+        import subprocess
+        from b200rl import native, ops
+        script = os.path.join(ROOT, "tests", "emul", "build_emul.sh")
+        r = subprocess.run(["bash", script], capture_output=True, text=True)
+        if r.returncode != 0:
+            _EMUL["ops"] = None
+            _EMUL["err"] = r.stderr[-2000:]
+        else:
+            lib = native.Lib(os.path.join(ROOT, "tests", "emul", "_build", "libb200rl_emul.so"), emulated=True)
+            _EMUL["ops"] = ops.Ops(lib, allow_cpu=True)
+    if _EMUL["ops"] is None:
+        pytest.skip("emulator build failed: " + _EMUL.get("err", ""))
+    return _EMUL["ops"]
+
+
+@pytest.fixture(params=["emul", pytest.param("cuda", marks=pytest.mark.gpu)])
+def backend(request):
+    """(ops, device) for each kernel back-end."""
+    if request.param == "emul":
+        return _emul_ops(), torch.device("cpu")
+    from b200rl import ops
+    return ops.default(), torch.device("cuda:0")
