@@ -1,0 +1,25 @@
+"""Binds each algorithm's `learning()` coroutine onto `LearnerBase.learning_<algo>` with
+the same decorator-factory names the reference exports (`agents/__init__.py:8-55`)."""
+from .learner_module.ppo.learning import learning as alearning_ppo
+from .learner_module.impala.learning import learning as alearning_impala
+
+
+def _awrapper(alearning):
+    def factory(timer):
+        def outer(func):
+            async def inner(self, *args, **kwargs):
+                return await alearning(self, timer, *args, **kwargs)
+            return inner
+        return outer
+    return factory
+
+
+async def _not_native_yet(parent, timer, *a, **k):
+    raise NotImplementedError("this algorithm has no B200-native learner path yet (see DESIGN.md, scope table)")
+
+
+ppo_awrapper = _awrapper(alearning_ppo)
+impala_awrapper = _awrapper(alearning_impala)
+v_mpo_awrapper = _awrapper(_not_native_yet)
+sac_awrapper = _awrapper(_not_native_yet)
+sac_continuous_awrapper = _awrapper(_not_native_yet)

@@ -1,0 +1,192 @@
+"""Learner classes -- host-side mirror of the reference's `agents/learner.py`.
+
+Kept from the reference: class names (`LearnerBase`,
+`LearnerSinglePPO`, `LearnerSingleIMPALA`, `LearnerSingleVMPO`, `LearnerSeperate` (sic)),
+the constructor signature (`learner.py:40-52`), `sample_batch_from_sh_memory`,
+`put_batch_to_batch_q`, `learning_chain_<algo>`, `pub_model`, `log_loss_tensorboard`,
+the shared-memory reader interface and the module-level `timer`.
+
+Replaced: `self.optimizer` (torch RMSprop) and the autograd step become `self.engine`
+(`b200rl.engine.OnPolicyEngine`: native kernels + fused clip/RMSprop on the flat
+parameter vector); `self.to_gpu` ships only the fields the update reads, from pinned
+memory.  ZeroMQ / tensorboardX are imported lazily and only if a socket / log dir is asked
+for, so the learner update can be driven without them (the benchmark isolates the learner
+from workers, as BASELINE.json's north_star asks).
+"""
+import asyncio
+import pickle
+
+import numpy as np
+import torch
+
+from ..engine import OnPolicyEngine
+from ..utils.utils import ExecutionTimer, HostStager, Params, Protocol, hyper_from_args, to_torch
+from .storage_module.shared_batch import SMInterFace
+from . import ppo_awrapper, v_mpo_awrapper, impala_awrapper, sac_awrapper, sac_continuous_awrapper
+
+timer = ExecutionTimer(num_transition=Params.seq_len * Params.batch_size * 1)
+
+
+def encode(protocol, data):
+    """Wire frame of the reference (`utils/utils.py:244-245`): pickle + blosc2(clevel=1)."""
+    import blosc2
+    return pickle.dumps(protocol), blosc2.compress(pickle.dumps(data), clevel=1)
+
+
+class LearnerBase(SMInterFace):
+    def __init__(self, args, mutex, model, shm_ref, stop_event, learner_ip, learner_port, obs_shape,
+                 shared_stat_array=None, heartbeat=None, process_group=None, ops=None):
+        super().__init__(shm_ref=shm_ref)
+        self.args = args
+        self.mutex = mutex
+        self.stop_event = stop_event
+        self.obs_shape = obs_shape
+        self.np_shared_stat_array = None
+        if shared_stat_array is not None:
+            self.np_shared_stat_array = np.frombuffer(buffer=shared_stat_array.get_obj(), dtype=np.float32, count=-1)
+        self.heartbeat = heartbeat
+        self.device = torch.device(self.args.device)
+        self.model = model.to(self.device)
+        self.process_group = process_group
+        self._ops = ops                      # test hook (host-emulated library); None -> product library
+        self.to_gpu = HostStager(self.device)
+        self.pub_socket = None
+        if learner_ip is not None:
+            self.zeromq_set(learner_ip, learner_port)
+        if shm_ref is not None:
+            self.get_shared_memory_interface()
+        self.writer = None
+        if getattr(args, "result_dir", None) is not None:
+            from tensorboardX import SummaryWriter
+            self.writer = SummaryWriter(log_dir=args.result_dir)
+        self.idx = 0
+
+    def __del__(self):
+        if getattr(self, "pub_socket", None) is not None:
+            self.pub_socket.close()
+
+    # ------------------------------------------------------------------ transport
+    def zeromq_set(self, learner_ip, learner_port):
+        import zmq
+        context = zmq.Context()
+        self.pub_socket = context.socket(zmq.PUB)
+        self.pub_socket.bind(f"tcp://{learner_ip}:{int(learner_port) + 1}")
+
+    def pub_model(self, model_state_dict):
+        if self.pub_socket is not None:
+            self.pub_socket.send_multipart([*encode(Protocol.Model, model_state_dict)])
+
+    # -------------------------------------------------------------------- logging
+    def log_loss_tensorboard(self, timer, loss, detached_losses):
+        w = self.writer
+        if w is None:
+            return
+        w.add_scalar("total-loss", float(loss.item()), self.idx)
+        for key, tag in (("value-loss", "original-value-loss"), ("policy-loss", "original-policy-loss"),
+                         ("policy-entropy", "original-policy-entropy")):
+            if key in detached_losses:
+                w.add_scalar(tag, float(detached_losses[key]), self.idx)
+        if "ratio" in detached_losses:
+            r = detached_losses["ratio"]
+            w.add_scalar("min-ratio", float(r.min()), self.idx)
+            w.add_scalar("max-ratio", float(r.max()), self.idx)
+            w.add_scalar("avg-ratio", float(r.mean()), self.idx)
+        for key in ("loss-temperature", "loss_alpha"):
+            if key in detached_losses:
+                w.add_scalar(key, float(detached_losses[key].mean()), self.idx)
+        if "alpha" in detached_losses:
+            w.add_scalar("alpha", float(detached_losses["alpha"]), self.idx)
+        st = self.np_shared_stat_array
+        if st is not None and st.size == 3 and bool(st[2]):
+            w.add_scalar("50-game-mean-stat-of-epi-rew", st[1], st[0])
+            st[2] = 0
+        if isinstance(timer, ExecutionTimer):
+            for k, v in timer.timer_dict.items():
+                w.add_scalar(f"{k}-elapsed-mean-sec", sum(v) / (len(v) + 1e-6), self.idx)
+            for k, v in timer.throughput_dict.items():
+                w.add_scalar(f"{k}-transition-per-secs", sum(v) / (len(v) + 1e-6), self.idx)
+
+    # ------------------------------------------------------ shared memory -> batch
+    def sample_batch_from_sh_memory(self, sampling_method):
+        """The 8-tuple (obs, act, rew, logits, log_prob, is_fir, hx, cx) of fresh host
+        tensors (reference learner.py:168-233).  `hx`/`cx` are returned as (B, H): only
+        `[:, 0]` of the stored (B, T, H) is ever read by the update."""
+        assert sampling_method in ("on-policy", "off-policy")
+        sq, bn, sha = self.args.seq_len, self.args.batch_size, self.obs_shape
+        hs, ac, buf = self.args.hidden_size, self.args.action_space, self.args.buffer_size
+        stored = int(self.sh_obs_batch.shape[0] / (sq * sha[0]))
+        if sampling_method == "off-policy":
+            assert buf == stored
+            idx, num = np.random.randint(0, buf, size=bn), buf
+        else:
+            assert bn == stored
+            idx, num = slice(None), bn
+        widths = (("obs", tuple(sha)), ("act", (1,)), ("rew", (1,)), ("logits", (ac,)), ("log_prob", (1,)),
+                  ("is_fir", (1,)), ("hx", (hs,)), ("cx", (hs,)))
+        out = []
+        for name, w in widths:
+            view = getattr(self, f"sh_{name}_batch").reshape((num, sq, *w))[idx]
+            if name in ("hx", "cx"):
+                view = view[:, 0]
+            out.append(to_torch(np.array(view, dtype=np.float32, copy=True)))
+        return tuple(out)
+
+    def is_sh_ready(self):
+        return self.sh_data_num.value >= self.args.batch_size
+
+    async def put_batch_to_batch_q(self):
+        while not self.stop_event.is_set():
+            if self.is_sh_ready():
+                await self.batch_queue.put(self.sample_batch_from_sh_memory(sampling_method="on-policy"))
+                self.reset_data_num()
+            await asyncio.sleep(0.001)
+
+    # ----------------------------------------------------------------- coroutines
+    @ppo_awrapper(timer=timer)
+    def learning_ppo(self): ...
+
+    @v_mpo_awrapper(timer=timer)
+    def learning_v_mpo(self): ...
+
+    @impala_awrapper(timer=timer)
+    def learning_impala(self): ...
+
+    @sac_awrapper(timer=timer)
+    def learning_sac(self): ...
+
+    @sac_continuous_awrapper(timer=timer)
+    def learning_sac_continuous(self): ...
+
+    async def _chain(self, queue_name, learn, feed):
+        setattr(self, queue_name, asyncio.Queue(1024))
+        await asyncio.gather(asyncio.create_task(learn()), asyncio.create_task(feed()))
+
+    async def learning_chain_ppo(self):
+        await self._chain("batch_queue", self.learning_ppo, self.put_batch_to_batch_q)
+
+    async def learning_chain_v_mpo(self):
+        await self._chain("batch_queue", self.learning_v_mpo, self.put_batch_to_batch_q)
+
+    async def learning_chain_impala(self):
+        await self._chain("batch_queue", self.learning_impala, self.put_batch_to_batch_q)
+
+
+class LearnerSinglePPO(LearnerBase):
+    """PPO / PPO-Continuous (reference learner.py:308-314)."""
+
+    engine_algo = None      # None -> args.algo
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        assert self.model.actor is self.model.critic
+        self.actor = self.model.actor
+        self.critic = self.model.critic
+        algo = self.engine_algo or self.args.algo
+        self.engine = OnPolicyEngine(self.actor, algo, hyper_from_args(self.args), ops=self._ops,
+                                     process_group=self.process_group)
+        self.to_gpu.skip = {"logits"}          # behaviour logits are read by V-MPO only
+
+
+class LearnerSingleIMPALA(LearnerSinglePPO):
+    """(reference learner.py:317)"""
+    engine_algo = "IMPALA"
