@@ -51,6 +51,30 @@ def hyper_args(device):
     return a
 
 
+def usable_cpus():
+    """Host threads we can really use: min(affinity mask, cgroup CPU quota).  The GPU boxes
+    expose 128 logical CPUs under a 16-CPU cgroup quota; 128 torch threads there run ~10x
+    slower than 16."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(per) + 0.999)))
+    except Exception:  # noqa: BLE001
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, (q + per - 1) // per))
+        except Exception:  # noqa: BLE001
+            pass
+    return max(1, n)
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
@@ -105,8 +129,8 @@ def reference_arm(steps, warmup, rank, world):
     import oracle
     from oracle import models as OM
     from b200rl.synth import make_rollouts
-    torch.set_num_threads(os.cpu_count() or 1)
-    budget_steps = 2.0e7                                    # ~2 min at the ~1.7e5 env-steps/s the survey probed
+    torch.set_num_threads(usable_cpus())
+    budget_steps = 4.0e7                                    # ~2 min at the ~3e5 env-steps/s a 16-thread host sustains
     rows = int(max(64, min(B, budget_steps / max(1, steps + warmup) / T)))
     rows = 1 << (rows.bit_length() - 1)
     torch.manual_seed(0)
@@ -136,14 +160,15 @@ def cpu_baseline():
     import oracle
     from oracle import models as OM
     from b200rl.synth import make_rollouts
-    nthreads = os.cpu_count() or 1
+    nthreads = usable_cpus()
     old = torch.get_num_threads()
     torch.set_num_threads(nthreads)
     torch.manual_seed(0)
     learner = oracle.OracleLearner("PPO", OM.init_params("single", F, A), fused_cell=True)
     batch = make_rollouts(B, T, F, A)
+    t0 = time.perf_counter()
     learner.update(batch)
-    n = 3
+    n = 3 if time.perf_counter() - t0 < 10 else 1
     t0 = time.perf_counter()
     for _ in range(n):
         learner.update(batch)
@@ -257,6 +282,8 @@ def main():
     launches = eng.n_launches - launches0
     value = world * B * T * a.steps / (total_ms * 1e-3)
     losses = eng.losses()
+    if rank == 0:
+        log(f"value leg done: {total_ms / a.steps:.3f} ms/step")
 
     # ---- e2e: the reference-facing learning() coroutine fed with pinned HOST batches
     n_e2e = min(a.steps, 50)
@@ -288,6 +315,8 @@ def main():
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_value = world * B * T * n_e2e / (float(ms2.item()) * 1e-3)
     h2d = learner.to_gpu.bytes_last
+    if rank == 0:
+        log(f"e2e leg done: {float(ms2.item()) / n_e2e:.3f} ms/step")
     d2h = 8 * 8 + 4
 
     out = {
@@ -349,6 +378,7 @@ def main():
         out["kernels_hbm_gbs"] = {k: algo_bytes[k] / (v * 1e-3) / 1e9 for k, v in kms.items()}
         out["step_share"] = {k: v / sum(kms.values()) for k, v in kms.items()}
         if world == 1 and not a.no_cpu_baseline:
+            log("timing the CPU port ...")
             out["cpu_baseline"] = cpu_baseline()
         print(json.dumps(out))
     if world > 1:
