@@ -342,7 +342,7 @@ def main():
             "head_fwd": lambda i: ops.head_fwd(L, eng.flat, eng.ws["h"], eng.head_out),
             "ppo_head": lambda i: ops.ppo_head(eng.head_out, bt, eng.dhead, eng.scalars, hp, A, False, None),
             "lstm_bwd": lambda i: ops.lstm_bwd(L, eng.flat, eng.dhead, eng.ws, bt["cx"]),
-            "lstm_wgrad": lambda i: ops.lstm_wgrad(L, eng.flat, eng.ws, bt["hx"], u, eng.dhead, eng.partials),
+            "lstm_wgrad": lambda i: ops.lstm_wgrad(L, eng.flat, eng.ws, bt["hx"], u, eng.dhead, eng.partials, variant=eng.wgrad_variant),
             "reduce_partials": lambda i: ops.reduce_partials(eng.partials, eng.grad),
             "clip_rmsprop": lambda i: ops.clip_rmsprop(eng.flat, eng.grad, eng.sq_avg, L.P, 1.0, 40.0, 1e-4, 0.99, 1e-5, eng.grad_norm),
         }

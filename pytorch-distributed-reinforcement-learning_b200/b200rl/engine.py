@@ -15,6 +15,7 @@ in a second tiny buffer) and a 1/world scale inside the optimizer kernel reprodu
 full-batch gradient; the global-norm clip comes after the reduction.
 """
 import math
+import os
 
 import torch
 
@@ -51,6 +52,8 @@ class OnPolicyEngine:
         self._shape = None
         self.n_launches = 0
         self.debug_outs = None                                # set to {} to capture intermediates
+        # weight-gradient kernel: 1 = tcgen05 (3xTF32 split) for dW/db, 0 = all-FFMA
+        self.wgrad_variant = int(os.environ.get("B200RL_WGRAD_VARIANT", "1"))
 
     # ------------------------------------------------------------------ workspace
     def _workspace(self, B, T):
@@ -100,7 +103,7 @@ class OnPolicyEngine:
             ops.ppo_head(self.head_out, batch, self.dhead, self.scalars, hp, self.net.n_outputs,
                          self.net.continuous, outs)
         ops.lstm_bwd(L, self.flat, self.dhead, self.ws, batch["cx"])
-        ops.lstm_wgrad(L, self.flat, self.ws, batch["hx"], u, self.dhead, self.partials)
+        ops.lstm_wgrad(L, self.flat, self.ws, batch["hx"], u, self.dhead, self.partials, variant=self.wgrad_variant)
         ops.reduce_partials(self.partials, self.grad)
         scale = 1.0
         if self.world > 1:
@@ -108,7 +111,7 @@ class OnPolicyEngine:
             scale = 1.0 / self.world
         ops.clip_rmsprop(self.flat, self.grad, self.sq_avg, L.P, scale, hp["max_grad_norm"], hp["lr"],
                          0.99, 1e-5, self.grad_norm)
-        self.n_launches += 8
+        self.n_launches += 8 + (1 if self.wgrad_variant == 1 else 0)
 
     # -------------------------------------------------------------------- scalars
     def losses(self):

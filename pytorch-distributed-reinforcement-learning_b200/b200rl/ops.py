@@ -147,7 +147,7 @@ def _lstm_bwd(self, L, flat, dhead, ws, cx0):
                   B, T, L.NH, 0, self._stream(dev))
 
 
-def _lstm_wgrad(self, L, flat, ws, hx0, u, dhead, partials, du=None):
+def _lstm_wgrad(self, L, flat, ws, hx0, u, dhead, partials, du=None, variant=0):
     dev = self._chk(flat, ws["gates"], ws["h"], hx0, u, dhead, partials, du)
     B, T, Fin = u.shape
     nparts = partials.shape[0]
@@ -157,7 +157,7 @@ def _lstm_wgrad(self, L, flat, ws, hx0, u, dhead, partials, du=None):
     self.lib.call("b200rl_lstm_wgrad", ptr(ws["gates"]), ptr(ws["h"]), ptr(hx0), ptr(u), ptr(dhead),
                   v("Wt"), v("bt"), v("W_ih"), ptr(partials), nparts, L.P,
                   o("Wt"), o("bt"), o("W_ih"), o("W_hh"), o("b_ih"), o("b_hh"), o("W_head"), o("b_head"),
-                  ptr(du), B, T, Fin, L.NH, 0, self._stream(dev))
+                  ptr(du), B, T, Fin, L.NH, variant, self._stream(dev))
 
 
 def _reduce_partials(self, partials, grad):

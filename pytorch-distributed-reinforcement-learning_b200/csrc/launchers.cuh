@@ -1,0 +1,9 @@
+// Cross-translation-unit kernel launchers.
+#pragma once
+namespace b200rl {
+// wgrad_tc.cu: dW_ih, dW_hh, db_ih, db_hh partial slabs on tcgen05 (3xTF32 split)
+int launch_wgrad_tc(const float* dpre, const float* h, const float* hx0, const float* u,
+                    const float* Wt, const float* bt, float* partials, int nparts, long long P,
+                    long long off_Wih, long long off_Whh, long long off_bih, long long off_bhh,
+                    int B, int T, int Fin, void* stream);
+}  // namespace b200rl

@@ -21,6 +21,7 @@
 // Saved-activation layout (private): gates (B,T,64,4) = per hidden unit j the four
 // post-activation gates (i,f,g,o) as one float4; c, h (B,T,64).
 #include "common.cuh"
+#include "launchers.cuh"
 
 namespace b200rl {
 
@@ -32,17 +33,34 @@ constexpr int NT = 256;       // threads per CTA
 constexpr int DS = 36;        // row stride of r-minor (transposed) tiles: 16B aligned, bank-skewed
 constexpr int MAXF = 32;      // max torso input width
 
-// thread -> (4 rows, 2 hidden units).  lane&7 selects the row group so that the eight
-// lanes of a quarter-warp touch 128 contiguous bytes of every r-minor shared tile.
-struct Map {
+// thread -> (4 rows, 2 hidden units).  A shared-memory LDS.128 is served one quarter-warp
+// (8 lanes) per wavefront and identical quarter-warps merge, so the operand that is read
+// with 128-bit loads in the hot loop should vary with lane&7 and repeat across quarters.
+//   MapR: lane&7 -> row group  (r-minor tiles: backward D_T, wgrad)   [rows vary in-quarter]
+//   MapJ: lane&7 -> hidden unit (forward: the two W float4 loads per k dominate)
+struct MapR {
     int r0, j0, j1;
-    __device__ Map() {
+    __device__ MapR() {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         r0 = (lane & 7) * 4;
         j0 = warp * 4 + (lane >> 3);
         j1 = j0 + 32;
     }
 };
+struct MapJ {
+    int r0, j0, j1;
+    __device__ MapJ() {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        r0 = ((warp & 1) * 4 + (lane >> 3)) * 4;
+        j0 = (warp >> 1) * 8 + (lane & 7);
+        j1 = j0 + 32;
+    }
+};
+
+// sigmoid / tanh for the cell: expf + approximate reciprocal (~2 ulp), tanh(x) = 2*sigmoid(2x) - 1
+// (absolute error ~1e-7, far inside the rtol 1e-4 parity bar; avoids tanhf's branchy slow path).
+__device__ __forceinline__ float sigm(float x) { return __fdividef(1.0f, 1.0f + expf(-x)); }
+__device__ __forceinline__ float tanh_(float x) { return fmaf(2.0f, sigm(2.0f * x), -1.0f); }
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
@@ -68,7 +86,7 @@ lstm_fwd_kernel(const float* __restrict__ u, const float* __restrict__ hx0, cons
     float* WtS = bts + H;                   // WtS[q*64 + j]
     float* U = WtS + Fin * H;               // U[buf][r*Fin + q]
     const int tid = threadIdx.x;
-    const Map m;
+    const MapJ m;
 
     // ---- one-time: stage the weights (PyTorch layout (4H, H), gate order i,f,g,o)
     {
@@ -177,12 +195,12 @@ lstm_fwd_kernel(const float* __restrict__ u, const float* __restrict__ hx0, cons
             for (int i = 0; i < 4; ++i) {
 #pragma unroll
                 for (int jj = 0; jj < 2; ++jj) {
-                    float ig = sigmoidf_(acc[i][jj * 4 + 0]);
-                    float fg = sigmoidf_(acc[i][jj * 4 + 1]);
-                    float gg = tanhf(acc[i][jj * 4 + 2]);
-                    float og = sigmoidf_(acc[i][jj * 4 + 3]);
+                    float ig = sigm(acc[i][jj * 4 + 0]);
+                    float fg = sigm(acc[i][jj * 4 + 1]);
+                    float gg = tanh_(acc[i][jj * 4 + 2]);
+                    float og = sigm(acc[i][jj * 4 + 3]);
                     float cn = fmaf(fg, cst[i][jj], ig * gg);
-                    float hh = og * tanhf(cn);
+                    float hh = og * tanh_(cn);
                     cst[i][jj] = cn; hn[i][jj] = hh;
                     if (bok[i]) {
                         const int j = jj ? m.j1 : m.j0;
@@ -260,9 +278,10 @@ head_fwd_kernel(const float* __restrict__ h, const float* __restrict__ W, const 
 }
 
 // ======================================================================= backward (serial)
-// shared (floats): WhT[256][64] | DT[2][256][DS] | WhS[NH][64] | dHd[2][32][NH]
+constexpr int BS = 32;       // backward D_T row stride: 128-byte aligned rows -> one wavefront per LDS.128
+// shared (floats): WhT[256][64] | DT[2][256][BS] | WhS[NH][64] | dHd[2][32][NH]
 static inline size_t bwd_smem_bytes(int NH) {
-    return sizeof(float) * (size_t)(G * H + 2 * G * DS + NH * H + 2 * TM * NH);
+    return sizeof(float) * (size_t)(G * H + 2 * G * BS + NH * H + 2 * TM * NH);
 }
 
 __global__ void __launch_bounds__(NT, 1)
@@ -272,11 +291,11 @@ lstm_bwd_kernel(const float* __restrict__ dhead, const float* __restrict__ W_hea
                 int B, int T, int NH) {
     B200RL_DYN_SMEM(float, smem);
     float* WhT = smem;                       // WhT[p*64 + k] = W_hh[n(p)][k],  p = j*4+g, n = g*64+j
-    float* DT = WhT + G * H;                 // DT[buf][p*DS + r]
-    float* WhS = DT + 2 * G * DS;            // WhS[c*64 + k]
+    float* DT = WhT + G * H;                 // DT[buf][p*BS + r]
+    float* WhS = DT + 2 * G * BS;            // WhS[c*64 + k]
     float* dHd = WhS + NH * H;               // dHd[buf][r*NH + c]
     const int tid = threadIdx.x;
-    const Map m;
+    const MapR m;
     {
         const int n = tid, g = n >> 6, j = n & 63, p = j * 4 + g;
         for (int k4 = 0; k4 < H; k4 += 4) st4(WhT + p * H + k4, ld4(W_hh + (size_t)n * H + k4));
@@ -290,12 +309,38 @@ lstm_bwd_kernel(const float* __restrict__ dhead, const float* __restrict__ W_hea
         int brow[4]; bool bok[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) { int b = b0 + m.r0 + i; bok[i] = b < B; brow[i] = bok[i] ? b : B - 1; }
-        // dhead tile for t = T-1
-        for (int i = tid; i < nD; i += NT) {
-            int r = i / NH, c = i % NH; int b = b0 + r < B ? b0 + r : B - 1;
-            dHd[((T - 1) & 1) * nD + i] = dhead[((size_t)b * T + (T - 1)) * NH + c];
+        // software pipeline (global latency must never sit on the per-step critical path):
+        // registers hold gates_t, c_t, c_{t-1} for the step being processed; the loads of
+        // gates_{t-1} and c_{t-2} are issued at the top of step t and first used one full step
+        // later; the dhead tile of step t-2 is loaded at step t and parked in shared memory
+        // at the end of step t-1.
+        constexpr int NPF = (TM * B200RL_MAX_HEADS + NT - 1) / NT;
+        auto load_dhead = [&](int t, float (&dst)[NPF]) {
+#pragma unroll
+            for (int e = 0; e < NPF; ++e) {
+                int i = e * NT + tid;
+                if (i < nD) {
+                    int r = i / NH, c = i % NH; int b = b0 + r < B ? b0 + r : B - 1;
+                    dst[e] = __ldg(dhead + ((size_t)b * T + t) * NH + c);
+                }
+            }
+        };
+        auto park_dhead = [&](int t, const float (&src)[NPF]) {
+            float* Hd = dHd + (t & 1) * nD;
+#pragma unroll
+            for (int e = 0; e < NPF; ++e) {
+                int i = e * NT + tid;
+                if (i < nD) Hd[i] = src[e];
+            }
+        };
+        float dh_next[NPF];                       // dhead tile of step t-1 while step t runs
+        {
+            float tmp[NPF];
+            load_dhead(T - 1, tmp);
+            park_dhead(T - 1, tmp);
+            if (T > 1) load_dhead(T - 2, dh_next);
         }
-        float dc[4][2], dhr[4][2], ccur[4][2];
+        float dc[4][2], dhr[4][2], ccur[4][2], cprev[4][2];
         float4 gcur[4][2];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -305,39 +350,28 @@ lstm_bwd_kernel(const float* __restrict__ dhead, const float* __restrict__ W_hea
                 const size_t o = ((size_t)brow[i] * T + (T - 1)) * H + j;
                 dc[i][jj] = 0.f; dhr[i][jj] = 0.f;
                 ccur[i][jj] = c_sav[o];
+                cprev[i][jj] = T > 1 ? c_sav[o - H] : cx0[(size_t)brow[i] * H + j];
                 gcur[i][jj] = ld4(gates + o * 4);
             }
         __syncthreads();
 
         for (int t = T - 1; t >= 0; --t) {
-            float* Dc = DT + (t & 1) * G * DS;
-            // (a) prefetch for step t-1: saved gates, c_{t-1} (= cx0 at t == 0), dhead tile
-            float4 gnx[4][2]; float cprev[4][2];
-            float dpre_pref[(TM * B200RL_MAX_HEADS + NT - 1) / NT];
+            float* Dc = DT + (t & 1) * G * BS;
+            // (a) issue loads whose first use is one full step away
+            float4 gnx[4][2]; float cpp[4][2];
+            float dh_new[NPF];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int jj = 0; jj < 2; ++jj) {
                     const int j = jj ? m.j1 : m.j0;
-                    if (t > 0) {
-                        const size_t o = ((size_t)brow[i] * T + (t - 1)) * H + j;
-                        cprev[i][jj] = c_sav[o];
-                        gnx[i][jj] = ld4(gates + o * 4);
-                    } else {
-                        cprev[i][jj] = cx0[(size_t)brow[i] * H + j];
-                        gnx[i][jj] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
+                    gnx[i][jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    cpp[i][jj] = 0.f;
+                    if (t > 0) gnx[i][jj] = ld4(gates + (((size_t)brow[i] * T + (t - 1)) * H + j) * 4);
+                    if (t > 1) cpp[i][jj] = c_sav[((size_t)brow[i] * T + (t - 2)) * H + j];
+                    else if (t == 1) cpp[i][jj] = cx0[(size_t)brow[i] * H + j];
                 }
-            if (t > 0) {
-#pragma unroll
-                for (int e = 0; e < (TM * B200RL_MAX_HEADS + NT - 1) / NT; ++e) {
-                    int i = e * NT + tid;
-                    if (i < nD) {
-                        int r = i / NH, c = i % NH; int b = b0 + r < B ? b0 + r : B - 1;
-                        dpre_pref[e] = __ldg(dhead + ((size_t)b * T + (t - 1)) * NH + c);
-                    }
-                }
-            }
+            if (t > 1) load_dhead(t - 2, dh_new);
             // (b) dh = dh_rec + dhead_t . W_head ; LSTM cell backward
             const float* dH = dHd + (t & 1) * nD;
             float4 dp[4][2];
@@ -349,7 +383,7 @@ lstm_bwd_kernel(const float* __restrict__ dhead, const float* __restrict__ W_hea
                     float dh = dhr[i][jj];
                     for (int c = 0; c < NH; ++c) dh = fmaf(dH[(m.r0 + i) * NH + c], WhS[c * H + j], dh);
                     const float4 gt = gcur[i][jj];          // i, f, g, o (post-activation)
-                    const float tc = tanhf(ccur[i][jj]);
+                    const float tc = tanh_(ccur[i][jj]);
                     const float d_o = dh * tc;
                     const float dct = fmaf(dh * gt.w, 1.f - tc * tc, dc[i][jj]);
                     const float d_i = dct * gt.z, d_g = dct * gt.x, d_f = dct * cprev[i][jj];
@@ -362,27 +396,21 @@ lstm_bwd_kernel(const float* __restrict__ dhead, const float* __restrict__ W_hea
             // r-minor tile for the dh GEMM: one float4 (4 rows) per gate column
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
-                float* d = Dc + ((jj ? m.j1 : m.j0) * 4) * DS + m.r0;
-                st4(d + 0 * DS, make_float4(dp[0][jj].x, dp[1][jj].x, dp[2][jj].x, dp[3][jj].x));
-                st4(d + 1 * DS, make_float4(dp[0][jj].y, dp[1][jj].y, dp[2][jj].y, dp[3][jj].y));
-                st4(d + 2 * DS, make_float4(dp[0][jj].z, dp[1][jj].z, dp[2][jj].z, dp[3][jj].z));
-                st4(d + 3 * DS, make_float4(dp[0][jj].w, dp[1][jj].w, dp[2][jj].w, dp[3][jj].w));
+                float* d = Dc + ((jj ? m.j1 : m.j0) * 4) * BS + m.r0;
+                st4(d + 0 * BS, make_float4(dp[0][jj].x, dp[1][jj].x, dp[2][jj].x, dp[3][jj].x));
+                st4(d + 1 * BS, make_float4(dp[0][jj].y, dp[1][jj].y, dp[2][jj].y, dp[3][jj].y));
+                st4(d + 2 * BS, make_float4(dp[0][jj].z, dp[1][jj].z, dp[2][jj].z, dp[3][jj].z));
+                st4(d + 3 * BS, make_float4(dp[0][jj].w, dp[1][jj].w, dp[2][jj].w, dp[3][jj].w));
             }
-            if (t > 0) {
-                float* Hd = dHd + ((t - 1) & 1) * nD;
-#pragma unroll
-                for (int e = 0; e < (TM * B200RL_MAX_HEADS + NT - 1) / NT; ++e) {
-                    int i = e * NT + tid;
-                    if (i < nD) Hd[i] = dpre_pref[e];
-                }
-            }
+            // (d) park the dhead tile of step t-1 (loaded a step ago); visible after the barrier
+            if (t > 0) park_dhead(t - 1, dh_next);
             __syncthreads();
             // (c) dh_rec[r][k] = sum_p dpre[r][p] W_hh[n(p)][k]        (32 x 64 x 256 per CTA)
             if (t > 0) {
                 float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 8
                 for (int p = 0; p < G; ++p) {
-                    float4 d = ld4(Dc + p * DS + m.r0);
+                    float4 d = ld4(Dc + p * BS + m.r0);
                     float w0 = WhT[p * H + m.j0], w1 = WhT[p * H + m.j1];
                     a0[0] = fmaf(d.x, w0, a0[0]); a0[1] = fmaf(d.y, w0, a0[1]);
                     a0[2] = fmaf(d.z, w0, a0[2]); a0[3] = fmaf(d.w, w0, a0[3]);
@@ -395,7 +423,9 @@ lstm_bwd_kernel(const float* __restrict__ dhead, const float* __restrict__ W_hea
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int jj = 0; jj < 2; ++jj) { ccur[i][jj] = cprev[i][jj]; gcur[i][jj] = gnx[i][jj]; }
+                for (int jj = 0; jj < 2; ++jj) { ccur[i][jj] = cprev[i][jj]; cprev[i][jj] = cpp[i][jj]; gcur[i][jj] = gnx[i][jj]; }
+#pragma unroll
+            for (int e = 0; e < NPF; ++e) dh_next[e] = dh_new[e];
         }
     }
 }
@@ -408,6 +438,7 @@ static inline size_t wgrad_smem_bytes(int Fin, int NH) {
 }
 constexpr int WG_E = 8;   // per-thread slots for the small (head / torso) gradient accumulators
 
+template <bool WITH_DW>
 __global__ void __launch_bounds__(NT, 1)
 lstm_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ h, const float* __restrict__ hx0,
                   const float* __restrict__ u, const float* __restrict__ dhead,
@@ -428,14 +459,15 @@ lstm_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ h, c
     float* bts = WtS + Fin * H;
     float* WtR = bts + H;                    // WtR[j*Fin + q]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const Map m;
+    const MapR m;
     {
         const int n = tid, g = n >> 6, j = n & 63, p = j * 4 + g;
         for (int k4 = 0; k4 < H; k4 += 4) st4(WiT + p * H + k4, ld4(W_ih + (size_t)n * H + k4));
         if (tid < H) bts[tid] = bt[tid];
         for (int i = tid; i < Fin * H; i += NT) { int q = i / H, jj = i % H; WtS[i] = Wt[jj * Fin + q]; WtR[jj * Fin + q] = Wt[jj * Fin + q]; }
     }
-    // dW ownership: 16 gate columns (p) x 8 k.  pg = tid/16 -> p = pg*16..+15 ; kg = tid%16 -> k = kg*4..+3 and 64+kg*4..+3
+    // dW ownership: 16 gate columns (p) x 8 k.  pg = tid/16 -> p = pg*16..+15 ; kg = tid%16 -> k = kg + 16*e (e<4: x_t, e>=4: h_{t-1});
+    // lane-consecutive k rows of the stride-36 tile hit disjoint bank groups (no conflicts)
     const int pg = tid >> 4, kg = tid & 15;
     float acc[16][8];
 #pragma unroll
@@ -495,14 +527,15 @@ lstm_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ h, c
             AtT[j * DS + lane] = fmaxf(a, 0.f);
         }
         __syncthreads();
+        if constexpr (WITH_DW) {
         // ---- dW[p][k] += sum_r dpre[r][p] * A[r][k]        (256 x 128 x 32 per chunk)
 #pragma unroll 1
         for (int r4 = 0; r4 < TM; r4 += 4) {
             float4 av[8];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                av[e] = ld4(AtT + (kg * 4 + e) * DS + r4);
-                av[4 + e] = ld4(AtT + (H + kg * 4 + e) * DS + r4);
+                av[e] = ld4(AtT + (kg + 16 * e) * DS + r4);
+                av[4 + e] = ld4(AtT + (H + kg + 16 * e) * DS + r4);
             }
 #pragma unroll
             for (int a = 0; a < 16; ++a) {
@@ -514,12 +547,15 @@ lstm_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ h, c
                 }
             }
         }
+        }
+        if constexpr (WITH_DW) {
         // ---- db[p] (both b_ih and b_hh), p = tid
         {
             float s = 0.f;
 #pragma unroll 8
             for (int r = 0; r < TM; ++r) s += DtT[tid * DS + r];
             acc_b += s;
+        }
         }
         // ---- dx[r][k] = sum_p dpre[r][p] W_ih[n(p)][k], masked by x > 0   (32 x 64 x 256 per chunk)
         {
@@ -588,15 +624,20 @@ lstm_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ h, c
     }
     // ---- write this CTA's partial slab (PyTorch layouts: W_* (4H,H) with n = g*64+j)
     float* out = partials + (size_t)blockIdx.x * P;
+    if constexpr (WITH_DW) {
 #pragma unroll
     for (int a = 0; a < 16; ++a) {
         const int p = pg * 16 + a, j = p >> 2, g = p & 3, n = g * H + j;
-        st4(out + off_Wih + (size_t)n * H + kg * 4, make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]));
-        st4(out + off_Whh + (size_t)n * H + kg * 4, make_float4(acc[a][4], acc[a][5], acc[a][6], acc[a][7]));
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            out[off_Wih + (size_t)n * H + kg + 16 * e] = acc[a][e];
+            out[off_Whh + (size_t)n * H + kg + 16 * e] = acc[a][4 + e];
+        }
     }
     {
         const int p = tid, j = p >> 2, g = p & 3, n = g * H + j;
         out[off_bih + n] = acc_b; out[off_bhh + n] = acc_b;
+    }
     }
     if (tid < H) out[off_bt + tid] = acc_bt;
 #pragma unroll
@@ -691,12 +732,21 @@ extern "C" int b200rl_lstm_wgrad(const float* dpre, const float* h, const float*
     B200RL_REQUIRE(B >= 1 && T >= 1, "lstm_wgrad: bad shape B=%d T=%d", B, T);
     B200RL_REQUIRE(Fin >= 1 && Fin <= MAXF && NH >= 1 && NH <= B200RL_MAX_HEADS, "lstm_wgrad: Fin=%d NH=%d out of range", Fin, NH);
     B200RL_REQUIRE(H * Fin <= WG_E * NT && NH * H <= WG_E * NT, "lstm_wgrad: head/torso too wide");
-    B200RL_REQUIRE(variant == 0, "lstm_wgrad: unknown variant %d", variant);
+    B200RL_REQUIRE(variant == 0 || variant == 1, "lstm_wgrad: unknown variant %d", variant);
     B200RL_REQUIRE(nparts >= 1, "lstm_wgrad: nparts=%d", nparts);
     B200RL_REQUIRE((off_Wih % 4) == 0 && (off_Whh % 4) == 0 && (P % 4) == 0, "lstm_wgrad: W_ih/W_hh offsets and P must be multiples of 4 floats");
     const size_t smem = wgrad_smem_bytes(Fin, NH);
-    if (set_smem(lstm_wgrad_kernel, smem, "lstm_wgrad")) return 1;
-    B200RL_LAUNCH(lstm_wgrad_kernel, nparts, NT, smem, stream, dpre, h, hx0, u, dhead, Wt, bt, W_ih, partials, P,
+    if (variant == 1) {
+        // tensor-core path: dW_ih / dW_hh / db on tcgen05 (wgrad_tc.cu), the rest (dx, torso, heads) on FFMA
+        B200RL_REQUIRE((long long)nparts * 32 <= (long long)B * T + 31, "lstm_wgrad: nparts=%d exceeds the number of 32-row stages", nparts);
+        if (launch_wgrad_tc(dpre, h, hx0, u, Wt, bt, partials, nparts, P, off_Wih, off_Whh, off_bih, off_bhh, B, T, Fin, stream)) return 1;
+        if (set_smem(lstm_wgrad_kernel<false>, smem, "lstm_wgrad")) return 1;
+        B200RL_LAUNCH(lstm_wgrad_kernel<false>, nparts, NT, smem, stream, dpre, h, hx0, u, dhead, Wt, bt, W_ih, partials, P,
+                      off_Wt, off_bt, off_Wih, off_Whh, off_bih, off_bhh, off_Whead, off_bhead, du, B, T, Fin, NH);
+        return check_launch("lstm_wgrad(misc)");
+    }
+    if (set_smem(lstm_wgrad_kernel<true>, smem, "lstm_wgrad")) return 1;
+    B200RL_LAUNCH(lstm_wgrad_kernel<true>, nparts, NT, smem, stream, dpre, h, hx0, u, dhead, Wt, bt, W_ih, partials, P,
                   off_Wt, off_bt, off_Wih, off_Whh, off_bih, off_bhh, off_Whead, off_bhead, du, B, T, Fin, NH);
     return check_launch("lstm_wgrad");
 }

@@ -1,0 +1,155 @@
+// Minimal tcgen05 / TMEM / mbarrier wrappers (sm_100a inline PTX), plus a TEST-ONLY host
+// twin (B200RL_EMUL) that interprets the same shared-memory descriptors with plain loops
+// so that tile filling, descriptor strides and the epilogue mapping can be debugged
+// without a GPU.  Bit layouts follow the CUTLASS headers vendored in this image
+// (cute/arch/mma_sm100_desc.hpp: SmemDescriptor, InstrDescriptor;
+//  cute/atom/mma_traits_sm100.hpp: canonical no-swizzle layouts).
+//
+// Operands are fp32 containers read as TF32 (top 19 bits).  Canonical SWIZZLE_NONE
+// layouts, in bytes, T = 4 elements per 16 B:
+//   MN-major: elem(mn, k) at  (mn%4)*4 + (mn/4)*SBO + (k%8)*16 + (k/8)*LBO
+//   K-major : elem(mn, k) at  (mn%8)*16 + (mn/8)*SBO + (k%4)*4  + (k/4)*LBO
+// i.e. both are built from the same 128-byte "core matrix" of 8 rows x 16 bytes.
+#pragma once
+#include "common.cuh"
+
+namespace b200rl {
+namespace tc {
+
+constexpr uint32_t kTf32Mask = 0xffffe000u;
+
+__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
+    hi = __uint_as_float(__float_as_uint(v) & kTf32Mask);
+    lo = __uint_as_float(__float_as_uint(v - hi) & kTf32Mask);
+}
+
+// instruction descriptor for kind::tf32, fp32 accumulate
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn_major, bool b_mn_major) {
+    return (1u << 4)                         // c_format = F32
+         | (2u << 7) | (2u << 10)            // a_format = b_format = TF32
+         | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16)
+         | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+#ifndef B200RL_EMUL
+// ------------------------------------------------------------------------------ device
+typedef uint64_t SmemDesc;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ SmemDesc make_desc(const void* smem_ptr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    const uint32_t a = smem_u32(smem_ptr);
+    uint64_t d = 0;
+    d |= (uint64_t)((a >> 4) & 0x3FFF);                 // start address   bits [0,14)
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // leading offset  bits [16,30)
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;   // stride offset   bits [32,46)
+    d |= (uint64_t)1 << 46;                             // descriptor version 1 (Blackwell)
+    return d;                                           // base_offset 0, lbo_mode 0, SWIZZLE_NONE
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "B200RL_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra B200RL_DONE;\n"
+        "bra B200RL_WAIT;\n"
+        "B200RL_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// one full warp; writes the TMEM base address (lane 0, column 0 of the allocation) to *dst
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] . B[smem]^T, one elected thread
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, SmemDesc a, SmemDesc b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on `bar` once every MMA issued so far by this thread has completed
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 consecutive fp32 columns of this thread's TMEM lane (lane = 32*(warp%4) + laneid)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&r)[32]) {
+    uint32_t u[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+          "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]),
+          "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]),
+          "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ uint32_t tmem_addr(uint32_t base, int lane, int col) { return base + ((uint32_t)lane << 16) + (uint32_t)col; }
+
+#else
+// --------------------------------------------------------------------------- host twin
+struct SmemDesc { const unsigned char* base; uint32_t lbo, sbo; };
+inline SmemDesc make_desc(const void* p, uint32_t lbo, uint32_t sbo) { return SmemDesc{(const unsigned char*)p, lbo, sbo}; }
+
+struct EmulTmem { float d[128][512]; };
+inline EmulTmem& emul_tmem() { static EmulTmem t; return t; }
+
+inline void mbar_init(uint64_t* bar, uint32_t) { *bar = 0; }
+inline void fence_mbar_init() {}
+inline void mbar_wait(uint64_t*, uint32_t) {}        // emulated MMAs complete synchronously
+inline void fence_async_smem() {}
+inline void fence_before_sync() {}
+inline void fence_after_sync() {}
+inline void tmem_alloc(uint32_t* dst, uint32_t) { if ((threadIdx.x & 31) == 0) *dst = 0; }
+inline void tmem_dealloc(uint32_t, uint32_t) {}
+inline void mma_commit(uint64_t*) {}
+
+inline float emul_elem(const SmemDesc& d, bool mn_major, int mn, int k) {
+    size_t off = mn_major ? (size_t)(mn % 4) * 4 + (size_t)(mn / 4) * d.sbo + (size_t)(k % 8) * 16 + (size_t)(k / 8) * d.lbo
+                          : (size_t)(mn % 8) * 16 + (size_t)(mn / 8) * d.sbo + (size_t)(k % 4) * 4 + (size_t)(k / 4) * d.lbo;
+    float v;
+    memcpy(&v, d.base + off, 4);
+    return __uint_as_float(__float_as_uint(v) & kTf32Mask);
+}
+inline void mma_tf32(uint32_t d_tmem, SmemDesc a, SmemDesc b, uint32_t idesc, uint32_t accumulate) {
+    const int M = (int)((idesc >> 24) & 31) << 4, N = (int)((idesc >> 17) & 63) << 3;
+    const bool amn = (idesc >> 15) & 1, bmn = (idesc >> 16) & 1;
+    EmulTmem& t = emul_tmem();
+    for (int m = 0; m < M; ++m)
+        for (int n = 0; n < N; ++n) {
+            float s = accumulate ? t.d[m][d_tmem + n] : 0.f;
+            for (int k = 0; k < 8; ++k) s += emul_elem(a, amn, m, k) * emul_elem(b, bmn, n, k);
+            t.d[m][d_tmem + n] = s;
+        }
+}
+inline void tmem_ld32(uint32_t taddr, float (&r)[32]) {
+    const int lane = (int)(taddr >> 16), col = (int)(taddr & 0xffff);
+    for (int i = 0; i < 32; ++i) r[i] = emul_tmem().d[lane][col + i];
+}
+inline uint32_t tmem_addr(uint32_t base, int lane, int col) { return base + ((uint32_t)lane << 16) + (uint32_t)col; }
+#endif
+
+}  // namespace tc
+}  // namespace b200rl

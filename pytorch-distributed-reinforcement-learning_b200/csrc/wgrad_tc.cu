@@ -1,0 +1,229 @@
+// LSTM weight gradients on the 5th-generation tensor cores (tcgen05, sm_100a).
+//
+//   dW_ih[n][k] = sum_{b,t} dpre[b,t,n] * x[b,t,k]        (x = ReLU torso output, recomputed)
+//   dW_hh[n][k] = sum_{b,t} dpre[b,t,n] * h[b,t-1,k]
+//   db_ih = db_hh = sum_{b,t} dpre[b,t,:]
+//
+// i.e. the autograd `AddmmBackward` of every nn.LSTMCell step of the reference
+// (networks/models.py:71-75 replayed by loss.backward(), ppo/learning.py:92), as ONE
+// reduction GEMM over all B*T rows:  dW^T[128 x 256] = A^T[128 x BT] . D[BT x 256],
+// A = [x | h_prev].  Each CTA owns every `gridDim`-th stage of 32 rows, accumulates the
+// full 128x256 fp32 tile in TMEM (256 columns) and writes one partial slab at the end.
+//
+// Precision: fp32 parity needs more than one TF32 pass, so both operands
+// are split on the fly, v = hi + lo with hi, lo exactly representable in TF32, and three
+// MMAs are issued per K-step: hi*hi + hi*lo + lo*hi (the dropped lo*lo term is ~2^-22).
+//
+// Data path per stage (16 rows = 2 K-steps of 8): all 256 threads load fp32 rows from HBM
+// (16-byte loads, 2 full sectors per row segment), recompute x, split hi/lo and scatter the
+// values with 4-byte stores into the canonical no-swizzle K-major UMMA layout, where the
+// contraction index (the row r) is the fast one:
+//     elem(mn, r) at (mn%8)*16 + (mn/8)*SBO + (r%4)*4 + (r/4)*LBO        [bytes]
+// (measured on B200: kind::tf32 with MN-major descriptors returns zeros, K-major is exact
+// -- tools/tc_probe.cu -- so the tile is transposed on the way into shared memory).
+// LBO = 144 B and SBO = 672 B are chosen = 16 B / 32 B modulo 128 B, which makes the 32 lanes
+// of every scatter store hit 32 distinct banks.  fence.proxy.async + __syncthreads, then one
+// elected thread issues 6 tcgen05.mma and a tcgen05.commit onto the stage's mbarrier; the
+// next stages are filled while the tensor core works (3-stage ring, 189 KB of smem).
+#include "common.cuh"
+#include "tc05.cuh"
+#include "launchers.cuh"
+
+namespace b200rl {
+
+namespace wtc {
+constexpr int H = 64, G = 256, KC = 128, NT = 256;
+constexpr int SR = 16;                          // rows per stage (2 MMA K-steps of 8)
+constexpr int NSTAGE = 3;
+constexpr int LBO = 144;                        // K direction: next core matrix (4 rows)      = 16 B mod 128 B
+constexpr int SBO = 672;                        // MN direction: next group of 8 mn (4 core matrices + skew) = 32 B mod 128 B
+constexpr int A_TILE = (KC / 8) * SBO;          // 10752
+constexpr int D_TILE = (G / 8) * SBO;           // 21504
+constexpr int STAGE = 2 * A_TILE + 2 * D_TILE;  // A_hi | A_lo | D_hi | D_lo = 64512 B
+constexpr int MAXF = 32;
+static_assert((SR / 4 - 1) * LBO + 128 <= SBO, "core matrices of one mn-group must fit below SBO");
+__device__ __forceinline__ int koff(int mn, int r) { return (mn & 7) * 16 + (mn >> 3) * SBO + (r & 3) * 4 + (r >> 2) * LBO; }
+}  // namespace wtc
+
+static inline size_t wgrad_tc_smem_bytes(int Fin) {
+    return wtc::NSTAGE * (size_t)wtc::STAGE + sizeof(float) * (size_t)(Fin * wtc::H + wtc::H) + 64;
+}
+
+__global__ void __launch_bounds__(wtc::NT, 1)
+lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h, const float* __restrict__ hx0,
+                     const float* __restrict__ u, const float* __restrict__ Wt, const float* __restrict__ bt,
+                     float* __restrict__ partials, long long P,
+                     long long off_Wih, long long off_Whh, long long off_bih, long long off_bhh,
+                     int B, int T, int Fin) {
+    using namespace wtc;
+    B200RL_DYN_SMEM(unsigned char, smem);
+    unsigned char* stage0 = smem;                                   // 1024-aligned by construction (offset 0)
+    float* WtS = reinterpret_cast<float*>(smem + NSTAGE * STAGE);   // WtS[q*64 + j]
+    float* bts = WtS + Fin * H;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bts + H);          // [0..NSTAGE): stage free ; [NSTAGE]: all done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NSTAGE + 1);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r_in = lane & 7, q4 = lane >> 3;                       // row inside a core matrix, float4 column
+
+    for (int i = tid; i < Fin * H; i += NT) { int q = i / H, j = i % H; WtS[i] = Wt[j * Fin + q]; }
+    if (tid < H) bts[tid] = bt[tid];
+    if (tid == 0) {
+        for (int i = 0; i <= NSTAGE; ++i) tc::mbar_init(&bars[i], 1);
+        tc::fence_mbar_init();
+    }
+    if (warp == 0) tc::tmem_alloc(tmem_slot, 256);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t idesc = tc::make_idesc_tf32(KC, G, false, false);
+
+    const long long rows = (long long)B * T;
+    const long long nstages = (rows + SR - 1) / SR;
+    float4 dbacc[2];
+    dbacc[0] = make_float4(0.f, 0.f, 0.f, 0.f); dbacc[1] = dbacc[0];
+
+    int it = 0;
+    for (long long st = blockIdx.x; st < nstages; st += gridDim.x, ++it) {
+        const int buf = it % NSTAGE, use = it / NSTAGE;
+        unsigned char* sb = stage0 + (size_t)buf * STAGE;
+        unsigned char* A_hi = sb, *A_lo = sb + A_TILE, *D_hi = sb + 2 * A_TILE, *D_lo = sb + 2 * A_TILE + D_TILE;
+        if (use >= 1) tc::mbar_wait(&bars[buf], (uint32_t)((use - 1) & 1));   // MMAs of the previous use of this buffer are done
+        const long long row0 = st * SR;
+
+        // ---- D tile: 16 rows x 64 float4.  Thread: rows r8*8 + r_in (r8 = 0,1), float4 columns c4(hh) (hh = 0,1)
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+            const int r8 = i4 & 1, hh = i4 >> 1;
+            const int c4 = (warp * 2 + hh) * 4 + q4;
+            const int r = r8 * 8 + r_in;
+            const long long row = row0 + r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < rows) v = *reinterpret_cast<const float4*>(dpre + (size_t)row * G + c4 * 4);
+            dbacc[hh].x += v.x; dbacc[hh].y += v.y; dbacc[hh].z += v.z; dbacc[hh].w += v.w;
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float hi, lo;
+                tc::split_tf32(vv[e], hi, lo);
+                const int o = koff(c4 * 4 + e, r);
+                *reinterpret_cast<float*>(D_hi + o) = hi;
+                *reinterpret_cast<float*>(D_lo + o) = lo;
+            }
+        }
+        // ---- A tile: [x_t (k<64) | h_{t-1} (k>=64)], 16 float4 each per row; thread: row (warp&1)*8 + r_in
+        {
+            const int r = (warp & 1) * 8 + r_in, c4 = (warp >> 1) * 4 + q4;              // c4 in 0..15
+            const long long row = row0 + r;
+            float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), hv = xv;
+            if (row < rows) {
+                const int b = (int)(row / T), t = (int)(row % T);
+                const float* hp = (t == 0) ? hx0 + (size_t)b * H : h + (size_t)(row - 1) * H;
+                hv = *reinterpret_cast<const float4*>(hp + c4 * 4);
+                float4 a = *reinterpret_cast<const float4*>(bts + c4 * 4);
+                const float* ur = u + (size_t)row * Fin;
+                for (int q = 0; q < Fin; ++q) {
+                    const float uv = __ldg(ur + q);
+                    const float4 w = *reinterpret_cast<const float4*>(WtS + q * H + c4 * 4);
+                    a.x = fmaf(uv, w.x, a.x); a.y = fmaf(uv, w.y, a.y); a.z = fmaf(uv, w.z, a.z); a.w = fmaf(uv, w.w, a.w);
+                }
+                xv = make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
+            }
+            const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, hs[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float hi, lo;
+                tc::split_tf32(xs[e], hi, lo);
+                int o = koff(c4 * 4 + e, r);
+                *reinterpret_cast<float*>(A_hi + o) = hi;
+                *reinterpret_cast<float*>(A_lo + o) = lo;
+                tc::split_tf32(hs[e], hi, lo);
+                o = koff(H + c4 * 4 + e, r);
+                *reinterpret_cast<float*>(A_hi + o) = hi;
+                *reinterpret_cast<float*>(A_lo + o) = lo;
+            }
+        }
+        tc::fence_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+#pragma unroll
+            for (int s = 0; s < SR / 8; ++s) {
+                const int ko = s * 2 * LBO;                                           // 8 rows = 2 core matrices along K
+                const tc::SmemDesc ah = tc::make_desc(A_hi + ko, LBO, SBO);
+                const tc::SmemDesc al = tc::make_desc(A_lo + ko, LBO, SBO);
+                const tc::SmemDesc dh = tc::make_desc(D_hi + ko, LBO, SBO);
+                const tc::SmemDesc dl = tc::make_desc(D_lo + ko, LBO, SBO);
+                tc::mma_tf32(tmem, ah, dh, idesc, (it > 0 || s > 0) ? 1u : 0u);
+                tc::mma_tf32(tmem, ah, dl, idesc, 1u);
+                tc::mma_tf32(tmem, al, dh, idesc, 1u);
+            }
+            tc::mma_commit(&bars[buf]);
+        }
+    }
+    if (tid == 0) tc::mma_commit(&bars[NSTAGE]);
+    tc::mbar_wait(&bars[NSTAGE], 0);
+#ifdef B200RL_EMUL
+    __syncthreads();                 // the host twin runs MMAs synchronously on thread 0
+#endif
+    tc::fence_after_sync();
+
+    // ---- epilogue: TMEM lane = k (A column), TMEM column = p = j*4 + g ; PyTorch row n = g*64 + j
+    float* out = partials + (size_t)blockIdx.x * P;
+    {
+        const int lane_base = 32 * (warp & 3);
+        const int k = lane_base + lane;                    // 0..127
+        float* dst = out + (k < H ? off_Wih + k : off_Whh + (k - H));
+#ifdef B200RL_EMUL
+        const int addr_lane = k;
+#else
+        const int addr_lane = lane_base;
+#endif
+        for (int c0 = (warp >> 2) * 128; c0 < (warp >> 2) * 128 + 128; c0 += 32) {
+            float r[32];
+            tc::tmem_ld32(tc::tmem_addr(tmem, addr_lane, c0), r);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int p = c0 + i, n = (p & 3) * H + (p >> 2);
+                dst[(size_t)n * H] = it > 0 ? r[i] : 0.f;
+            }
+        }
+    }
+    // ---- bias gradient: reduce the 8 row-lanes that share a float4 column
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+        float4 s = dbacc[hh];
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            s.x += __shfl_xor_sync(kFull, s.x, o); s.y += __shfl_xor_sync(kFull, s.y, o);
+            s.z += __shfl_xor_sync(kFull, s.z, o); s.w += __shfl_xor_sync(kFull, s.w, o);
+        }
+        if (r_in == 0) {
+            const int c4 = (warp * 2 + hh) * 4 + q4;       // p = c4*4 + g  ->  j = c4, n = g*64 + c4
+            const float v[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+            for (int g = 0; g < 4; ++g) { out[off_bih + g * H + c4] = v[g]; out[off_bhh + g * H + c4] = v[g]; }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 256);
+}
+
+int launch_wgrad_tc(const float* dpre, const float* h, const float* hx0, const float* u,
+                    const float* Wt, const float* bt, float* partials, int nparts, long long P,
+                    long long off_Wih, long long off_Whh, long long off_bih, long long off_bhh,
+                    int B, int T, int Fin, void* stream) {
+    B200RL_REQUIRE(Fin >= 1 && Fin <= wtc::MAXF, "lstm_wgrad(tc): Fin=%d out of range", Fin);
+    const size_t smem = wgrad_tc_smem_bytes(Fin);
+#ifndef B200RL_EMUL
+    cudaError_t e = cudaFuncSetAttribute(lstm_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error("lstm_wgrad(tc): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+#endif
+    B200RL_LAUNCH(lstm_wgrad_tc_kernel, nparts, wtc::NT, smem, stream, dpre, h, hx0, u, Wt, bt, partials, P,
+                  off_Wih, off_Whh, off_bih, off_bhh, B, T, Fin);
+    return check_launch("lstm_wgrad(tc)");
+}
+
+}  // namespace b200rl

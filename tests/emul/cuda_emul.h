@@ -105,6 +105,7 @@ static inline unsigned atomicInc(unsigned* p, unsigned wrap) {
     *p = old >= wrap ? 0 : old + 1;
     return old;
 }
+static inline float __fdividef(float a, float b) { return a / b; }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 static inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }

@@ -34,7 +34,7 @@ def main(B=4096, T=128, f=4, A=2, iters=20, algo="PPO"):
         ("head_fwd", lambda: ops.head_fwd(L, eng.flat, eng.ws["h"], eng.head_out)),
         ("ppo_head", lambda: ops.ppo_head(eng.head_out, batch, eng.dhead, eng.scalars, HYPER, A, False, None)),
         ("lstm_bwd", lambda: ops.lstm_bwd(L, eng.flat, eng.dhead, eng.ws, batch["cx"])),
-        ("lstm_wgrad", lambda: ops.lstm_wgrad(L, eng.flat, eng.ws, batch["hx"], u, eng.dhead, eng.partials)),
+        ("lstm_wgrad", lambda: ops.lstm_wgrad(L, eng.flat, eng.ws, batch["hx"], u, eng.dhead, eng.partials, variant=eng.wgrad_variant)),
         ("reduce_partials", lambda: ops.reduce_partials(eng.partials, eng.grad)),
         ("clip_rmsprop", lambda: ops.clip_rmsprop(eng.flat, eng.grad, eng.sq_avg, L.P, 1.0, 40.0, 1e-4, 0.99, 1e-5, eng.grad_norm)),
     ]
