@@ -111,7 +111,7 @@ class OnPolicyEngine:
             scale = 1.0 / self.world
         ops.clip_rmsprop(self.flat, self.grad, self.sq_avg, L.P, scale, hp["max_grad_norm"], hp["lr"],
                          0.99, 1e-5, self.grad_norm)
-        self.n_launches += 8 + (1 if self.wgrad_variant == 1 else 0)
+        self.n_launches += 8 + {0: 0, 1: 2, 2: 1}[self.wgrad_variant]
 
     # -------------------------------------------------------------------- scalars
     def losses(self):

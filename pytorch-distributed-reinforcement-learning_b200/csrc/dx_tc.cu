@@ -1,0 +1,293 @@
+// Torso gradients through the LSTM input projection on tcgen05, and the head gradients.
+//
+//   dx[r][k]   = sum_p dpre[r][p] * W_ih[n(p)][k]        (r over all B*T rows, K = 256, N = 64)
+//   dxr        = dx * [x > 0]                            (ReLU of the torso, x recomputed from u)
+//   dWt[j][q]  = sum_r dxr[r][j] * u[r][q] ;  dbt[j] = sum_r dxr[r][j] ;  du[r][q] = sum_j dxr[r][j] Wt[j][q]
+//   dW_head[c][k] = sum_r dhead[r][c] * h[r][k] ;  db_head[c] = sum_r dhead[r][c]
+//
+// (autograd of `x = body(obs)` feeding nn.LSTMCell and of the value/logits Linear layers,
+//  networks/models.py:67-69,77-78, replayed by loss.backward(), ppo/learning.py:92.)
+//
+// dx kernel: a CTA owns 128-row tiles.  W_ih is split once into TF32 hi/lo and kept resident
+// in shared memory as the K-major B operand (2 x 64 KB).  dpre is streamed in chunks of 32
+// gate columns: every float4 of a row IS one 16-byte row of a K-major core matrix, so the A
+// operand is written with conflict-free 16-byte stores (hi and lo), no transposition.
+// 3xTF32: D_hi*W_hi + D_hi*W_lo + D_lo*W_hi accumulate into a 128x64 fp32 tile in TMEM.
+// Epilogue: tcgen05.ld -> ReLU mask -> shared tile -> per-column reductions on FFMA.
+#include "common.cuh"
+#include "tc05.cuh"
+#include "launchers.cuh"
+
+namespace b200rl {
+
+namespace dxk {
+constexpr int H = 64, G = 256, NT = 256;
+constexpr int TR = 128;                     // rows per tile (UMMA M)
+constexpr int CK = 32;                      // gate columns per chunk (4 MMA K-steps)
+constexpr int NCH = G / CK;                 // 8 chunks per tile
+constexpr int W_LBO = 128, W_SBO = (G / 4) * 128;          // B: 64 core matrices along K per 8-k group (8192)
+constexpr int W_BYTES = (H / 8) * W_SBO;                   // 65536 per hi / lo
+constexpr int D_LBO = 128, D_SBO = (CK / 4) * 128;         // A: 8 core matrices along K per 8-row group (1024)
+constexpr int D_BYTES = (TR / 8) * D_SBO;                  // 16384 per hi / lo
+constexpr int STAGE = 2 * D_BYTES;                         // 32 KB
+constexpr int NSTAGE = 2;
+constexpr int SS = H + 1;                                  // epilogue tile row stride (floats)
+constexpr int MAXF = 32;
+}  // namespace dxk
+
+static inline size_t dx_tc_smem_bytes(int Fin) {
+    return 2 * (size_t)dxk::W_BYTES + dxk::NSTAGE * (size_t)dxk::STAGE + sizeof(float) * (size_t)(Fin * dxk::H + dxk::H + dxk::H * Fin) + 64;
+}
+
+__global__ void __launch_bounds__(dxk::NT, 1)
+lstm_dx_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ u,
+                  const float* __restrict__ W_ih, const float* __restrict__ Wt, const float* __restrict__ bt,
+                  float* __restrict__ partials, long long P, long long off_Wt, long long off_bt,
+                  float* __restrict__ du, long long rows, int Fin) {
+    using namespace dxk;
+    B200RL_DYN_SMEM(unsigned char, smem);
+    unsigned char* W_hi = smem;
+    unsigned char* W_lo = smem + W_BYTES;
+    unsigned char* stage0 = smem + 2 * W_BYTES;
+    float* WtS = reinterpret_cast<float*>(stage0 + NSTAGE * STAGE);     // WtS[q*64 + j]
+    float* bts = WtS + Fin * H;
+    float* WtR = bts + H;                                                // WtR[j*Fin + q]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(WtR + H * Fin);         // [0],[1]: stage free ; [2]: tile done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+    // the epilogue reuses the (then idle) stage memory: S[128][65] floats, then U[128][Fin]
+    float* S = reinterpret_cast<float*>(stage0);
+    float* Us = S + TR * SS;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r_in = lane & 7, q4 = lane >> 3;
+
+    // ---- one-time: W_ih -> TF32 hi/lo, K-major B operand: elem(k, p) = W_ih[(p&3)*64 + (p>>2)][k]
+    for (int i = tid; i < G * H / 4; i += NT) {          // i -> (n, k4): PyTorch row n, float4 of k
+        const int n = i >> 4, k4 = i & 15;
+        const float4 w = *reinterpret_cast<const float4*>(W_ih + (size_t)n * H + k4 * 4);
+        const int p = (n & 63) * 4 + (n >> 6);
+        const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = k4 * 4 + e;
+            float hi, lo;
+            tc::split_tf32(wv[e], hi, lo);
+            const int o = (k & 7) * 16 + (k >> 3) * W_SBO + (p & 3) * 4 + (p >> 2) * W_LBO;
+            *reinterpret_cast<float*>(W_hi + o) = hi;
+            *reinterpret_cast<float*>(W_lo + o) = lo;
+        }
+    }
+    for (int i = tid; i < Fin * H; i += NT) { int q = i / H, j = i % H; WtS[i] = Wt[j * Fin + q]; WtR[j * Fin + q] = Wt[j * Fin + q]; }
+    if (tid < H) bts[tid] = bt[tid];
+    if (tid == 0) {
+        tc::mbar_init(&bars[0], 1); tc::mbar_init(&bars[1], 1); tc::mbar_init(&bars[2], 1);
+        tc::fence_mbar_init();
+    }
+    if (warp == 0) tc::tmem_alloc(tmem_slot, 64);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t idesc = tc::make_idesc_tf32(TR, H, false, false);
+
+    // reduction ownership: column j = tid % 64, row quarter part = tid / 64
+    const int rj = tid & 63, part = tid >> 6;
+    float acc_bt = 0.f, acc_wt[MAXF];
+#pragma unroll
+    for (int q = 0; q < MAXF; ++q) acc_wt[q] = 0.f;
+
+    const long long ntiles = (rows + TR - 1) / TR;
+    // register-staged chunk loads (issued one chunk ahead)
+    float4 dv[4];
+    auto issue_loads = [&](long long tile, int ch) {
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+            const int r = (warp * 2 + (i4 & 1)) * 8 + r_in, c4 = ch * (CK / 4) + (i4 >> 1) * 4 + q4;
+            const long long row = tile * TR + r;
+            dv[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < rows) dv[i4] = *reinterpret_cast<const float4*>(dpre + (size_t)row * G + c4 * 4);
+        }
+    };
+    if ((long long)blockIdx.x < ntiles) issue_loads(blockIdx.x, 0);
+
+    int g = 0;                                            // chunk counter across tiles (stage ring position)
+    int tdone = 0;                                        // tiles completed by this CTA (tile-done parity)
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tdone) {
+        for (int ch = 0; ch < NCH; ++ch, ++g) {
+            const int buf = g & 1, use = g >> 1;
+            unsigned char* D_hi = stage0 + (size_t)buf * STAGE, *D_lo = D_hi + D_BYTES;
+            float4 cd[4];
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) cd[i4] = dv[i4];
+            if (ch + 1 < NCH) issue_loads(tile, ch + 1);
+            else if (tile + gridDim.x < ntiles) issue_loads(tile + gridDim.x, 0);
+            if (use >= 1) tc::mbar_wait(&bars[buf], (uint32_t)((use - 1) & 1));
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+                const int r8 = warp * 2 + (i4 & 1), c4l = (i4 >> 1) * 4 + q4;
+                float4 hi, lo;
+                tc::split_tf32(cd[i4].x, hi.x, lo.x); tc::split_tf32(cd[i4].y, hi.y, lo.y);
+                tc::split_tf32(cd[i4].z, hi.z, lo.z); tc::split_tf32(cd[i4].w, hi.w, lo.w);
+                const int o = r_in * 16 + r8 * D_SBO + c4l * D_LBO;
+                *reinterpret_cast<float4*>(D_hi + o) = hi;
+                *reinterpret_cast<float4*>(D_lo + o) = lo;
+            }
+            tc::fence_async_smem();
+            __syncthreads();
+            if (tid == 0) {
+                tc::fence_after_sync();
+#pragma unroll
+                for (int s = 0; s < CK / 8; ++s) {
+                    const tc::SmemDesc ah = tc::make_desc(D_hi + s * 2 * D_LBO, D_LBO, D_SBO);
+                    const tc::SmemDesc al = tc::make_desc(D_lo + s * 2 * D_LBO, D_LBO, D_SBO);
+                    const int wo = (ch * (CK / 4) + s * 2) * W_LBO;
+                    const tc::SmemDesc wh = tc::make_desc(W_hi + wo, W_LBO, W_SBO);
+                    const tc::SmemDesc wl = tc::make_desc(W_lo + wo, W_LBO, W_SBO);
+                    tc::mma_tf32(tmem, ah, wh, idesc, (ch > 0 || s > 0) ? 1u : 0u);
+                    tc::mma_tf32(tmem, ah, wl, idesc, 1u);
+                    tc::mma_tf32(tmem, al, wh, idesc, 1u);
+                }
+                tc::mma_commit(&bars[buf]);
+                if (ch == NCH - 1) tc::mma_commit(&bars[2]);
+            }
+        }
+        // ---- epilogue of this tile
+        tc::mbar_wait(&bars[2], (uint32_t)(tdone & 1));
+#ifdef B200RL_EMUL
+        __syncthreads();
+#endif
+        tc::fence_after_sync();
+        {
+            const int r = 32 * (warp & 3) + lane, c0 = (warp >> 2) * 32;         // row, first of 32 columns
+            const long long row = tile * TR + r;
+#ifdef B200RL_EMUL
+            const int addr_lane = r;
+#else
+            const int addr_lane = 32 * (warp & 3);
+#endif
+            float dxv[32];
+            tc::tmem_ld32(tc::tmem_addr(tmem, addr_lane, c0), dxv);
+            const bool ok = row < rows;
+            const float* ur = u + (size_t)(ok ? row : 0) * Fin;
+#pragma unroll 4
+            for (int i = 0; i < 32; ++i) {
+                const int k = c0 + i;
+                float a = bts[k];
+                for (int q = 0; q < Fin; ++q) a = fmaf(__ldg(ur + q), WtS[q * H + k], a);
+                S[r * SS + k] = (ok && a > 0.f) ? dxv[i] : 0.f;
+            }
+            if (warp < 4)
+                for (int q = 0; q < Fin; ++q) Us[r * Fin + q] = ok ? __ldg(ur + q) : 0.f;
+        }
+        tc::fence_before_sync();
+        __syncthreads();
+        {
+            float sb = 0.f;
+#pragma unroll 4
+            for (int r = part * 32; r < part * 32 + 32; ++r) {
+                const float s = S[r * SS + rj];
+                sb += s;
+#pragma unroll
+                for (int q = 0; q < MAXF; ++q) if (q < Fin) acc_wt[q] = fmaf(s, Us[r * Fin + q], acc_wt[q]);
+            }
+            acc_bt += sb;
+        }
+        if (du != nullptr && tid < TR) {
+            const long long row = tile * TR + tid;
+            if (row < rows)
+                for (int q = 0; q < Fin; ++q) {
+                    float s = 0.f;
+                    for (int j = 0; j < H; ++j) s = fmaf(S[tid * SS + j], WtR[j * Fin + q], s);
+                    du[(size_t)row * Fin + q] = s;
+                }
+        }
+        __syncthreads();                                   // S / Us (stage memory) free for the next tile
+    }
+    // ---- combine the four row quarters and write this CTA's slab entries
+    float* red = reinterpret_cast<float*>(stage0);         // [4][64][Fin+1]
+    const int RW = Fin + 1;
+    red[(part * H + rj) * RW + Fin] = acc_bt;
+#pragma unroll
+    for (int q = 0; q < MAXF; ++q) if (q < Fin) red[(part * H + rj) * RW + q] = acc_wt[q];
+    __syncthreads();
+    float* out = partials + (size_t)blockIdx.x * P;
+    for (int i = tid; i < H * RW; i += NT) {
+        const int j = i / RW, q = i % RW;
+        const float s = red[(0 * H + j) * RW + q] + red[(1 * H + j) * RW + q] + red[(2 * H + j) * RW + q] + red[(3 * H + j) * RW + q];
+        if (q == Fin) out[off_bt + j] = s; else out[off_Wt + (size_t)j * Fin + q] = s;
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 64);
+}
+
+// --------------------------------------------------------------------------- head gradients
+constexpr int HG_R = 64;
+__global__ void __launch_bounds__(256)
+head_grad_kernel(const float* __restrict__ h, const float* __restrict__ dhead, float* __restrict__ partials,
+                 long long P, long long off_Whead, long long off_bhead, long long rows, int NH) {
+    __shared__ float S[HG_R * 65];
+    __shared__ float Dh[HG_R * B200RL_MAX_HEADS];
+    const int tid = threadIdx.x;
+    constexpr int E = (B200RL_MAX_HEADS * 64 + 255) / 256;
+    float acc[E], accb = 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[e] = 0.f;
+    const long long nch = (rows + HG_R - 1) / HG_R;
+    for (long long ch = blockIdx.x; ch < nch; ch += gridDim.x) {
+        const long long row0 = ch * HG_R;
+        __syncthreads();
+        for (int i = tid; i < HG_R * 16; i += 256) {
+            const int r = i >> 4, c4 = i & 15;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row0 + r < rows) v = *reinterpret_cast<const float4*>(h + (size_t)(row0 + r) * 64 + c4 * 4);
+            float* d = S + r * 65 + c4 * 4;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+        for (int i = tid; i < HG_R * NH; i += 256) Dh[i] = row0 + i / NH < rows ? dhead[(size_t)row0 * NH + i] : 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int o = e * 256 + tid;
+            if (o < NH * 64) {
+                const int c = o >> 6, k = o & 63;
+                float s = 0.f;
+#pragma unroll 8
+                for (int r = 0; r < HG_R; ++r) s = fmaf(Dh[r * NH + c], S[r * 65 + k], s);
+                acc[e] += s;
+            }
+        }
+        if (tid < NH) {
+            float s = 0.f;
+            for (int r = 0; r < HG_R; ++r) s += Dh[r * NH + tid];
+            accb += s;
+        }
+    }
+    float* out = partials + (size_t)blockIdx.x * P;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int o = e * 256 + tid;
+        if (o < NH * 64) out[off_Whead + o] = acc[e];
+    }
+    if (tid < NH) out[off_bhead + tid] = accb;
+}
+
+int launch_dx_tc(const float* dpre, const float* u, const float* W_ih, const float* Wt, const float* bt,
+                 const float* h, const float* dhead, float* partials, int nparts, long long P,
+                 long long off_Wt, long long off_bt, long long off_Whead, long long off_bhead,
+                 float* du, int B, int T, int Fin, int NH, void* stream) {
+    B200RL_REQUIRE(Fin >= 1 && Fin <= dxk::MAXF, "lstm_wgrad(dx tc): Fin=%d out of range", Fin);
+    const long long rows = (long long)B * T;
+    const size_t smem = dx_tc_smem_bytes(Fin);
+#ifndef B200RL_EMUL
+    cudaError_t e = cudaFuncSetAttribute(lstm_dx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error("lstm_wgrad(dx tc): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+#endif
+    B200RL_LAUNCH(lstm_dx_tc_kernel, nparts, dxk::NT, smem, stream, dpre, u, W_ih, Wt, bt, partials, P, off_Wt, off_bt, du, rows, Fin);
+    if (check_launch("lstm_wgrad(dx tc)")) return 1;
+    B200RL_LAUNCH(head_grad_kernel, nparts, 256, 0, stream, h, dhead, partials, P, off_Whead, off_bhead, rows, NH);
+    return check_launch("lstm_wgrad(head grad)");
+}
+
+}  // namespace b200rl

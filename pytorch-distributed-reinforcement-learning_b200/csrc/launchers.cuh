@@ -6,4 +6,9 @@ int launch_wgrad_tc(const float* dpre, const float* h, const float* hx0, const f
                     const float* Wt, const float* bt, float* partials, int nparts, long long P,
                     long long off_Wih, long long off_Whh, long long off_bih, long long off_bhh,
                     int B, int T, int Fin, void* stream);
+// dx_tc.cu: torso gradients (dx GEMM on tcgen05 + ReLU mask + reductions) and head gradients
+int launch_dx_tc(const float* dpre, const float* u, const float* W_ih, const float* Wt, const float* bt,
+                 const float* h, const float* dhead, float* partials, int nparts, long long P,
+                 long long off_Wt, long long off_bt, long long off_Whead, long long off_bhead,
+                 float* du, int B, int T, int Fin, int NH, void* stream);
 }  // namespace b200rl

@@ -732,13 +732,18 @@ extern "C" int b200rl_lstm_wgrad(const float* dpre, const float* h, const float*
     B200RL_REQUIRE(B >= 1 && T >= 1, "lstm_wgrad: bad shape B=%d T=%d", B, T);
     B200RL_REQUIRE(Fin >= 1 && Fin <= MAXF && NH >= 1 && NH <= B200RL_MAX_HEADS, "lstm_wgrad: Fin=%d NH=%d out of range", Fin, NH);
     B200RL_REQUIRE(H * Fin <= WG_E * NT && NH * H <= WG_E * NT, "lstm_wgrad: head/torso too wide");
-    B200RL_REQUIRE(variant == 0 || variant == 1, "lstm_wgrad: unknown variant %d", variant);
+    B200RL_REQUIRE(variant >= 0 && variant <= 2, "lstm_wgrad: unknown variant %d", variant);
     B200RL_REQUIRE(nparts >= 1, "lstm_wgrad: nparts=%d", nparts);
     B200RL_REQUIRE((off_Wih % 4) == 0 && (off_Whh % 4) == 0 && (P % 4) == 0, "lstm_wgrad: W_ih/W_hh offsets and P must be multiples of 4 floats");
     const size_t smem = wgrad_smem_bytes(Fin, NH);
     if (variant == 1) {
-        // tensor-core path: dW_ih / dW_hh / db on tcgen05 (wgrad_tc.cu), the rest (dx, torso, heads) on FFMA
+        // tensor-core path: dW_ih / dW_hh / db (wgrad_tc.cu) and dx -> torso grads (dx_tc.cu) on tcgen05
         B200RL_REQUIRE((long long)nparts * 32 <= (long long)B * T + 31, "lstm_wgrad: nparts=%d exceeds the number of 32-row stages", nparts);
+        if (launch_wgrad_tc(dpre, h, hx0, u, Wt, bt, partials, nparts, P, off_Wih, off_Whh, off_bih, off_bhh, B, T, Fin, stream)) return 1;
+        return launch_dx_tc(dpre, u, W_ih, Wt, bt, h, dhead, partials, nparts, P, off_Wt, off_bt, off_Whead, off_bhead,
+                            du, B, T, Fin, NH, stream);
+    }
+    if (variant == 2) {   // tcgen05 dW + FFMA remainder (kept for A/B measurements)
         if (launch_wgrad_tc(dpre, h, hx0, u, Wt, bt, partials, nparts, P, off_Wih, off_Whh, off_bih, off_bhh, B, T, Fin, stream)) return 1;
         if (set_smem(lstm_wgrad_kernel<false>, smem, "lstm_wgrad")) return 1;
         B200RL_LAUNCH(lstm_wgrad_kernel<false>, nparts, NT, smem, stream, dpre, h, hx0, u, dhead, Wt, bt, W_ih, partials, P,

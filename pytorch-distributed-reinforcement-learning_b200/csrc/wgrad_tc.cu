@@ -84,13 +84,50 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
     float4 dbacc[2];
     dbacc[0] = make_float4(0.f, 0.f, 0.f, 0.f); dbacc[1] = dbacc[0];
 
+    // Register-staged loads: the HBM reads of stage i+1 are issued before stage i is split and
+    // scattered, so their latency overlaps the shared-memory work (and the tensor core).
+    constexpr int UP = 8;                           // torso inputs prefetched in registers when Fin <= UP
+    float4 dv[4], hvv; float uvv[UP]; bool rowok[3];   // [0],[1]: D rows r8 = 0,1 ; [2]: A row
+    auto issue_loads = [&](long long stg) {
+        const long long row0 = stg * SR;
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+            const int r8 = i4 & 1, hh = i4 >> 1;
+            const int c4 = (warp * 2 + hh) * 4 + q4;
+            const long long row = row0 + r8 * 8 + r_in;
+            dv[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < rows) dv[i4] = *reinterpret_cast<const float4*>(dpre + (size_t)row * G + c4 * 4);
+        }
+        const int c4 = (warp >> 1) * 4 + q4;
+        const long long row = row0 + (warp & 1) * 8 + r_in;
+        hvv = make_float4(0.f, 0.f, 0.f, 0.f);
+        rowok[2] = row < rows;
+        if (rowok[2]) {
+            const int b = (int)(row / T), t = (int)(row % T);
+            const float* hp = (t == 0) ? hx0 + (size_t)b * H : h + (size_t)(row - 1) * H;
+            hvv = *reinterpret_cast<const float4*>(hp + c4 * 4);
+            if (Fin <= UP) {
+#pragma unroll
+                for (int q = 0; q < UP; ++q) uvv[q] = q < Fin ? __ldg(u + (size_t)row * Fin + q) : 0.f;
+            }
+        }
+    };
+    if ((long long)blockIdx.x < nstages) issue_loads(blockIdx.x);
+
     int it = 0;
     for (long long st = blockIdx.x; st < nstages; st += gridDim.x, ++it) {
         const int buf = it % NSTAGE, use = it / NSTAGE;
         unsigned char* sb = stage0 + (size_t)buf * STAGE;
         unsigned char* A_hi = sb, *A_lo = sb + A_TILE, *D_hi = sb + 2 * A_TILE, *D_lo = sb + 2 * A_TILE + D_TILE;
-        if (use >= 1) tc::mbar_wait(&bars[buf], (uint32_t)((use - 1) & 1));   // MMAs of the previous use of this buffer are done
         const long long row0 = st * SR;
+        // take ownership of this stage's registers, then immediately refill them for the next stage
+        float4 cd[4], ch = hvv; float cu[UP]; const bool aok = rowok[2];
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) cd[i4] = dv[i4];
+#pragma unroll
+        for (int q = 0; q < UP; ++q) cu[q] = uvv[q];
+        if (st + gridDim.x < nstages) issue_loads(st + gridDim.x);
+        if (use >= 1) tc::mbar_wait(&bars[buf], (uint32_t)((use - 1) & 1));   // MMAs of the previous use of this buffer are done
 
         // ---- D tile: 16 rows x 64 float4.  Thread: rows r8*8 + r_in (r8 = 0,1), float4 columns c4(hh) (hh = 0,1)
 #pragma unroll
@@ -98,9 +135,7 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
             const int r8 = i4 & 1, hh = i4 >> 1;
             const int c4 = (warp * 2 + hh) * 4 + q4;
             const int r = r8 * 8 + r_in;
-            const long long row = row0 + r;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < rows) v = *reinterpret_cast<const float4*>(dpre + (size_t)row * G + c4 * 4);
+            const float4 v = cd[i4];
             dbacc[hh].x += v.x; dbacc[hh].y += v.y; dbacc[hh].z += v.z; dbacc[hh].w += v.w;
             const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -116,17 +151,25 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
         {
             const int r = (warp & 1) * 8 + r_in, c4 = (warp >> 1) * 4 + q4;              // c4 in 0..15
             const long long row = row0 + r;
-            float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), hv = xv;
-            if (row < rows) {
-                const int b = (int)(row / T), t = (int)(row % T);
-                const float* hp = (t == 0) ? hx0 + (size_t)b * H : h + (size_t)(row - 1) * H;
-                hv = *reinterpret_cast<const float4*>(hp + c4 * 4);
+            float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 hv = ch;
+            if (aok) {
                 float4 a = *reinterpret_cast<const float4*>(bts + c4 * 4);
-                const float* ur = u + (size_t)row * Fin;
-                for (int q = 0; q < Fin; ++q) {
-                    const float uv = __ldg(ur + q);
-                    const float4 w = *reinterpret_cast<const float4*>(WtS + q * H + c4 * 4);
-                    a.x = fmaf(uv, w.x, a.x); a.y = fmaf(uv, w.y, a.y); a.z = fmaf(uv, w.z, a.z); a.w = fmaf(uv, w.w, a.w);
+                if (Fin <= UP) {
+#pragma unroll
+                    for (int q = 0; q < UP; ++q) {
+                        if (q < Fin) {
+                            const float4 w = *reinterpret_cast<const float4*>(WtS + q * H + c4 * 4);
+                            a.x = fmaf(cu[q], w.x, a.x); a.y = fmaf(cu[q], w.y, a.y); a.z = fmaf(cu[q], w.z, a.z); a.w = fmaf(cu[q], w.w, a.w);
+                        }
+                    }
+                } else {
+                    const float* ur = u + (size_t)row * Fin;
+                    for (int q = 0; q < Fin; ++q) {
+                        const float uv = __ldg(ur + q);
+                        const float4 w = *reinterpret_cast<const float4*>(WtS + q * H + c4 * 4);
+                        a.x = fmaf(uv, w.x, a.x); a.y = fmaf(uv, w.y, a.y); a.z = fmaf(uv, w.z, a.z); a.w = fmaf(uv, w.w, a.w);
+                    }
                 }
                 xv = make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
             }
