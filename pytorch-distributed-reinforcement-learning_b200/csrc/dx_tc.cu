@@ -39,6 +39,7 @@ static inline size_t dx_tc_smem_bytes(int Fin) {
     return 2 * (size_t)dxk::W_BYTES + dxk::NSTAGE * (size_t)dxk::STAGE + sizeof(float) * (size_t)(Fin * dxk::H + dxk::H + dxk::H * Fin) + 64;
 }
 
+template <int FMAX>            // compile-time bound on the torso input width (register accumulators)
 __global__ void __launch_bounds__(dxk::NT, 1)
 lstm_dx_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ u,
                   const float* __restrict__ W_ih, const float* __restrict__ Wt, const float* __restrict__ bt,
@@ -62,20 +63,15 @@ lstm_dx_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ u,
     const int r_in = lane & 7, q4 = lane >> 3;
 
     // ---- one-time: W_ih -> TF32 hi/lo, K-major B operand: elem(k, p) = W_ih[(p&3)*64 + (p>>2)][k]
-    for (int i = tid; i < G * H / 4; i += NT) {          // i -> (n, k4): PyTorch row n, float4 of k
-        const int n = i >> 4, k4 = i & 15;
-        const float4 w = *reinterpret_cast<const float4*>(W_ih + (size_t)n * H + k4 * 4);
-        const int p = (n & 63) * 4 + (n >> 6);
-        const float wv[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int k = k4 * 4 + e;
-            float hi, lo;
-            tc::split_tf32(wv[e], hi, lo);
-            const int o = (k & 7) * 16 + (k >> 3) * W_SBO + (p & 3) * 4 + (p >> 2) * W_LBO;
-            *reinterpret_cast<float*>(W_hi + o) = hi;
-            *reinterpret_cast<float*>(W_lo + o) = lo;
-        }
+    // lanes cover one 128-byte core matrix (8 k x 4 p) per store -> conflict-free
+    for (int i = tid; i < G * H; i += NT) {
+        const int p = ((i >> 5) & 63) * 4 + (i & 3), k = (i >> 11) * 8 + ((i >> 2) & 7);
+        const float w = W_ih[(size_t)((p & 3) * 64 + (p >> 2)) * H + k];
+        float hi, lo;
+        tc::split_tf32(w, hi, lo);
+        const int o = (k & 7) * 16 + (k >> 3) * W_SBO + (p & 3) * 4 + (p >> 2) * W_LBO;
+        *reinterpret_cast<float*>(W_hi + o) = hi;
+        *reinterpret_cast<float*>(W_lo + o) = lo;
     }
     for (int i = tid; i < Fin * H; i += NT) { int q = i / H, j = i % H; WtS[i] = Wt[j * Fin + q]; WtR[j * Fin + q] = Wt[j * Fin + q]; }
     if (tid < H) bts[tid] = bt[tid];
@@ -93,9 +89,9 @@ lstm_dx_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ u,
 
     // reduction ownership: column j = tid % 64, row quarter part = tid / 64
     const int rj = tid & 63, part = tid >> 6;
-    float acc_bt = 0.f, acc_wt[MAXF];
+    float acc_bt = 0.f, acc_wt[FMAX];
 #pragma unroll
-    for (int q = 0; q < MAXF; ++q) acc_wt[q] = 0.f;
+    for (int q = 0; q < FMAX; ++q) acc_wt[q] = 0.f;
 
     const long long ntiles = (rows + TR - 1) / TR;
     // register-staged chunk loads (issued one chunk ahead)
@@ -189,7 +185,7 @@ lstm_dx_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ u,
                 const float s = S[r * SS + rj];
                 sb += s;
 #pragma unroll
-                for (int q = 0; q < MAXF; ++q) if (q < Fin) acc_wt[q] = fmaf(s, Us[r * Fin + q], acc_wt[q]);
+                for (int q = 0; q < FMAX; ++q) if (q < Fin) acc_wt[q] = fmaf(s, Us[r * Fin + q], acc_wt[q]);
             }
             acc_bt += sb;
         }
@@ -209,7 +205,7 @@ lstm_dx_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ u,
     const int RW = Fin + 1;
     red[(part * H + rj) * RW + Fin] = acc_bt;
 #pragma unroll
-    for (int q = 0; q < MAXF; ++q) if (q < Fin) red[(part * H + rj) * RW + q] = acc_wt[q];
+    for (int q = 0; q < FMAX; ++q) if (q < Fin) red[(part * H + rj) * RW + q] = acc_wt[q];
     __syncthreads();
     float* out = partials + (size_t)blockIdx.x * P;
     for (int i = tid; i < H * RW; i += NT) {
@@ -273,6 +269,15 @@ head_grad_kernel(const float* __restrict__ h, const float* __restrict__ dhead, f
     if (tid < NH) out[off_bhead + tid] = accb;
 }
 
+template <typename K>
+static int dx_set_smem(K kern, size_t smem) {
+#ifndef B200RL_EMUL
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error("lstm_wgrad(dx tc): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+#endif
+    return 0;
+}
+
 int launch_dx_tc(const float* dpre, const float* u, const float* W_ih, const float* Wt, const float* bt,
                  const float* h, const float* dhead, float* partials, int nparts, long long P,
                  long long off_Wt, long long off_bt, long long off_Whead, long long off_bhead,
@@ -280,11 +285,16 @@ int launch_dx_tc(const float* dpre, const float* u, const float* W_ih, const flo
     B200RL_REQUIRE(Fin >= 1 && Fin <= dxk::MAXF, "lstm_wgrad(dx tc): Fin=%d out of range", Fin);
     const long long rows = (long long)B * T;
     const size_t smem = dx_tc_smem_bytes(Fin);
-#ifndef B200RL_EMUL
-    cudaError_t e = cudaFuncSetAttribute(lstm_dx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return set_error("lstm_wgrad(dx tc): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
-#endif
-    B200RL_LAUNCH(lstm_dx_tc_kernel, nparts, dxk::NT, smem, stream, dpre, u, W_ih, Wt, bt, partials, P, off_Wt, off_bt, du, rows, Fin);
+#define B200RL_DX_LAUNCH(FM)                                                                                          \
+    do {                                                                                                              \
+        if (dx_set_smem(lstm_dx_tc_kernel<FM>, smem)) return 1;                                                       \
+        B200RL_LAUNCH(lstm_dx_tc_kernel<FM>, nparts, dxk::NT, smem, stream, dpre, u, W_ih, Wt, bt, partials, P, off_Wt, off_bt, du, rows, Fin); \
+    } while (0)
+    if (Fin <= 4) B200RL_DX_LAUNCH(4);
+    else if (Fin <= 8) B200RL_DX_LAUNCH(8);
+    else if (Fin <= 16) B200RL_DX_LAUNCH(16);
+    else B200RL_DX_LAUNCH(32);
+#undef B200RL_DX_LAUNCH
     if (check_launch("lstm_wgrad(dx tc)")) return 1;
     B200RL_LAUNCH(head_grad_kernel, nparts, 256, 0, stream, h, dhead, partials, P, off_Whead, off_bhead, rows, NH);
     return check_launch("lstm_wgrad(head grad)");
