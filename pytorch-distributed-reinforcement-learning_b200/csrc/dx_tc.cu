@@ -14,6 +14,8 @@
 // operand is written with conflict-free 16-byte stores (hi and lo), no transposition.
 // 3xTF32: D_hi*W_hi + D_hi*W_lo + D_lo*W_hi accumulate into a 128x64 fp32 tile in TMEM.
 // Epilogue: tcgen05.ld -> ReLU mask -> shared tile -> per-column reductions on FFMA.
+// Warp-specialised like wgrad_tc: warps 0-7 produce stages and run the epilogue, warp 8 issues the MMAs;
+// full/empty mbarriers per stage, tile_done / tmem_free per tile, a named barrier among the producers.
 #include "common.cuh"
 #include "tc05.cuh"
 #include "launchers.cuh"
@@ -21,7 +23,7 @@
 namespace b200rl {
 
 namespace dxk {
-constexpr int H = 64, G = 256, NT = 256;
+constexpr int H = 64, G = 256, NP = 256, NT = NP + 32;     // 8 producer warps + the MMA issuer warp
 constexpr int TR = 128;                     // rows per tile (UMMA M)
 constexpr int CK = 32;                      // gate columns per chunk (4 MMA K-steps)
 constexpr int NCH = G / CK;                 // 8 chunks per tile
@@ -36,7 +38,7 @@ constexpr int MAXF = 32;
 }  // namespace dxk
 
 static inline size_t dx_tc_smem_bytes(int Fin) {
-    return 2 * (size_t)dxk::W_BYTES + dxk::NSTAGE * (size_t)dxk::STAGE + sizeof(float) * (size_t)(Fin * dxk::H + dxk::H + dxk::H * Fin) + 64;
+    return 2 * (size_t)dxk::W_BYTES + dxk::NSTAGE * (size_t)dxk::STAGE + sizeof(float) * (size_t)(Fin * dxk::H + dxk::H + dxk::H * Fin) + 96;
 }
 
 template <int FMAX>            // compile-time bound on the torso input width (register accumulators)
@@ -53,18 +55,20 @@ lstm_dx_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ u,
     float* WtS = reinterpret_cast<float*>(stage0 + NSTAGE * STAGE);     // WtS[q*64 + j]
     float* bts = WtS + Fin * H;
     float* WtR = bts + H;                                                // WtR[j*Fin + q]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(WtR + H * Fin);         // [0],[1]: stage free ; [2]: tile done
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(WtR + H * Fin);         // full[2] | empty[2] | tile_done | tmem_free
+    uint64_t* full = bars, *empty = bars + NSTAGE, *tile_done = bars + 2 * NSTAGE, *tmem_free = bars + 2 * NSTAGE + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 2);
     // the epilogue reuses the (then idle) stage memory: S[128][65] floats, then U[128][Fin]
     float* S = reinterpret_cast<float*>(stage0);
     float* Us = S + TR * SS;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool producer = warp < NP / 32;
     const int r_in = lane & 7, q4 = lane >> 3;
 
     // ---- one-time: W_ih -> TF32 hi/lo, K-major B operand: elem(k, p) = W_ih[(p&3)*64 + (p>>2)][k]
     // lanes cover one 128-byte core matrix (8 k x 4 p) per store -> conflict-free
-    for (int i = tid; i < G * H; i += NT) {
+    for (int i = tid; i < G * H; i += NT) {          // (any stride: every i is handled exactly once)
         const int p = ((i >> 5) & 63) * 4 + (i & 3), k = (i >> 11) * 8 + ((i >> 2) & 7);
         const float w = W_ih[(size_t)((p & 3) * 64 + (p >> 2)) * H + k];
         float hi, lo;
@@ -76,10 +80,11 @@ lstm_dx_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ u,
     for (int i = tid; i < Fin * H; i += NT) { int q = i / H, j = i % H; WtS[i] = Wt[j * Fin + q]; WtR[j * Fin + q] = Wt[j * Fin + q]; }
     if (tid < H) bts[tid] = bt[tid];
     if (tid == 0) {
-        tc::mbar_init(&bars[0], 1); tc::mbar_init(&bars[1], 1); tc::mbar_init(&bars[2], 1);
+        for (int i = 0; i < NSTAGE; ++i) { tc::mbar_init(&full[i], NP); tc::mbar_init(&empty[i], 1); }
+        tc::mbar_init(tile_done, 1); tc::mbar_init(tmem_free, NP);
         tc::fence_mbar_init();
     }
-    if (warp == 0) tc::tmem_alloc(tmem_slot, 64);
+    if (warp == NP / 32) tc::tmem_alloc(tmem_slot, 64);
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
@@ -87,38 +92,70 @@ lstm_dx_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ u,
     const uint32_t tmem = *tmem_slot;
     const uint32_t idesc = tc::make_idesc_tf32(TR, H, false, false);
 
+    const long long ntiles = (rows + TR - 1) / TR;
+    if (!producer) {
+        if (lane == 0) {
+            int g = 0, tdone = 0;
+            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tdone) {
+                if (tdone > 0) { tc::mbar_wait(tmem_free, (uint32_t)((tdone - 1) & 1)); tc::fence_after_sync(); }
+                for (int ch = 0; ch < NCH; ++ch, ++g) {
+                    const int buf = g & 1, use = g >> 1;
+                    unsigned char* D_hi = stage0 + (size_t)buf * STAGE, *D_lo = D_hi + D_BYTES;
+                    tc::mbar_wait(&full[buf], (uint32_t)(use & 1));
+                    tc::fence_after_sync();
+#pragma unroll
+                    for (int s = 0; s < CK / 8; ++s) {
+                        const tc::SmemDesc ah = tc::make_desc(D_hi + s * 2 * D_LBO, D_LBO, D_SBO);
+                        const tc::SmemDesc al = tc::make_desc(D_lo + s * 2 * D_LBO, D_LBO, D_SBO);
+                        const int wo = (ch * (CK / 4) + s * 2) * W_LBO;
+                        const tc::SmemDesc wh = tc::make_desc(W_hi + wo, W_LBO, W_SBO);
+                        const tc::SmemDesc wl = tc::make_desc(W_lo + wo, W_LBO, W_SBO);
+                        tc::mma_tf32(tmem, ah, wh, idesc, (ch > 0 || s > 0) ? 1u : 0u);
+                        tc::mma_tf32(tmem, ah, wl, idesc, 1u);
+                        tc::mma_tf32(tmem, al, wh, idesc, 1u);
+                    }
+                    tc::mma_commit(&empty[buf]);
+                    if (ch == NCH - 1) tc::mma_commit(tile_done);
+                }
+            }
+        }
+    } else {
     // reduction ownership: column j = tid % 64, row quarter part = tid / 64
     const int rj = tid & 63, part = tid >> 6;
     float acc_bt = 0.f, acc_wt[FMAX];
 #pragma unroll
     for (int q = 0; q < FMAX; ++q) acc_wt[q] = 0.f;
 
-    const long long ntiles = (rows + TR - 1) / TR;
-    // register-staged chunk loads (issued one chunk ahead)
-    float4 dv[4];
-    auto issue_loads = [&](long long tile, int ch) {
+    // register-staged chunk loads: a ring of 4 slots, loads issued 3 chunks (~3 barriers) ahead of
+    // their use so HBM latency overlaps the split/store/MMA work of the chunks in between
+    constexpr int RING = 4, AHEAD = 3;
+    static_assert(NCH % RING == 0, "ring slots must be compile-time constants inside the unrolled chunk loop");
+    float4 dv[RING][4];
+    auto issue_loads = [&](float4 (&dst)[4], long long tile, int ch) {
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) {
             const int r = (warp * 2 + (i4 & 1)) * 8 + r_in, c4 = ch * (CK / 4) + (i4 >> 1) * 4 + q4;
             const long long row = tile * TR + r;
-            dv[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < rows) dv[i4] = *reinterpret_cast<const float4*>(dpre + (size_t)row * G + c4 * 4);
+            dst[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tile < ntiles && row < rows) dst[i4] = *reinterpret_cast<const float4*>(dpre + (size_t)row * G + c4 * 4);
         }
     };
-    if ((long long)blockIdx.x < ntiles) issue_loads(blockIdx.x, 0);
+#pragma unroll
+    for (int c = 0; c < AHEAD; ++c) issue_loads(dv[c], blockIdx.x, c);
 
     int g = 0;                                            // chunk counter across tiles (stage ring position)
     int tdone = 0;                                        // tiles completed by this CTA (tile-done parity)
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tdone) {
+#pragma unroll
         for (int ch = 0; ch < NCH; ++ch, ++g) {
             const int buf = g & 1, use = g >> 1;
             unsigned char* D_hi = stage0 + (size_t)buf * STAGE, *D_lo = D_hi + D_BYTES;
             float4 cd[4];
 #pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4) cd[i4] = dv[i4];
-            if (ch + 1 < NCH) issue_loads(tile, ch + 1);
-            else if (tile + gridDim.x < ntiles) issue_loads(tile + gridDim.x, 0);
-            if (use >= 1) tc::mbar_wait(&bars[buf], (uint32_t)((use - 1) & 1));
+            for (int i4 = 0; i4 < 4; ++i4) cd[i4] = dv[ch % RING][i4];
+            if (ch + AHEAD < NCH) issue_loads(dv[(ch + AHEAD) % RING], tile, ch + AHEAD);
+            else issue_loads(dv[(ch + AHEAD) % RING], tile + gridDim.x, ch + AHEAD - NCH);
+            if (use >= 1) tc::mbar_wait(&empty[buf], (uint32_t)((use - 1) & 1));
 #pragma unroll
             for (int i4 = 0; i4 < 4; ++i4) {
                 const int r8 = warp * 2 + (i4 & 1), c4l = (i4 >> 1) * 4 + q4;
@@ -130,29 +167,10 @@ lstm_dx_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ u,
                 *reinterpret_cast<float4*>(D_lo + o) = lo;
             }
             tc::fence_async_smem();
-            __syncthreads();
-            if (tid == 0) {
-                tc::fence_after_sync();
-#pragma unroll
-                for (int s = 0; s < CK / 8; ++s) {
-                    const tc::SmemDesc ah = tc::make_desc(D_hi + s * 2 * D_LBO, D_LBO, D_SBO);
-                    const tc::SmemDesc al = tc::make_desc(D_lo + s * 2 * D_LBO, D_LBO, D_SBO);
-                    const int wo = (ch * (CK / 4) + s * 2) * W_LBO;
-                    const tc::SmemDesc wh = tc::make_desc(W_hi + wo, W_LBO, W_SBO);
-                    const tc::SmemDesc wl = tc::make_desc(W_lo + wo, W_LBO, W_SBO);
-                    tc::mma_tf32(tmem, ah, wh, idesc, (ch > 0 || s > 0) ? 1u : 0u);
-                    tc::mma_tf32(tmem, ah, wl, idesc, 1u);
-                    tc::mma_tf32(tmem, al, wh, idesc, 1u);
-                }
-                tc::mma_commit(&bars[buf]);
-                if (ch == NCH - 1) tc::mma_commit(&bars[2]);
-            }
+            tc::mbar_arrive(&full[buf]);
         }
         // ---- epilogue of this tile
-        tc::mbar_wait(&bars[2], (uint32_t)(tdone & 1));
-#ifdef B200RL_EMUL
-        __syncthreads();
-#endif
+        tc::mbar_wait(tile_done, (uint32_t)(tdone & 1));
         tc::fence_after_sync();
         {
             const int r = 32 * (warp & 3) + lane, c0 = (warp >> 2) * 32;         // row, first of 32 columns
@@ -166,18 +184,25 @@ lstm_dx_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ u,
             tc::tmem_ld32(tc::tmem_addr(tmem, addr_lane, c0), dxv);
             const bool ok = row < rows;
             const float* ur = u + (size_t)(ok ? row : 0) * Fin;
+            float uq[FMAX];                                   // this row's torso inputs, loaded once
+#pragma unroll
+            for (int q = 0; q < FMAX; ++q) uq[q] = (ok && q < Fin) ? __ldg(ur + q) : 0.f;
 #pragma unroll 4
             for (int i = 0; i < 32; ++i) {
                 const int k = c0 + i;
                 float a = bts[k];
-                for (int q = 0; q < Fin; ++q) a = fmaf(__ldg(ur + q), WtS[q * H + k], a);
+#pragma unroll
+                for (int q = 0; q < FMAX; ++q) if (q < Fin) a = fmaf(uq[q], WtS[q * H + k], a);
                 S[r * SS + k] = (ok && a > 0.f) ? dxv[i] : 0.f;
             }
-            if (warp < 4)
-                for (int q = 0; q < Fin; ++q) Us[r * Fin + q] = ok ? __ldg(ur + q) : 0.f;
+            if (warp < 4) {
+#pragma unroll
+                for (int q = 0; q < FMAX; ++q) if (q < Fin) Us[r * Fin + q] = uq[q];
+            }
         }
         tc::fence_before_sync();
-        __syncthreads();
+        tc::mbar_arrive(tmem_free);                        // accumulator drained: the issuer may start the next tile
+        tc::named_bar_sync(1, NP);
         {
             float sb = 0.f;
 #pragma unroll 4
@@ -198,7 +223,7 @@ lstm_dx_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ u,
                     du[(size_t)row * Fin + q] = s;
                 }
         }
-        __syncthreads();                                   // S / Us (stage memory) free for the next tile
+        tc::named_bar_sync(1, NP);                         // S / Us (stage memory) free for the next tile
     }
     // ---- combine the four row quarters and write this CTA's slab entries
     float* red = reinterpret_cast<float*>(stage0);         // [4][64][Fin+1]
@@ -206,32 +231,38 @@ lstm_dx_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ u,
     red[(part * H + rj) * RW + Fin] = acc_bt;
 #pragma unroll
     for (int q = 0; q < FMAX; ++q) if (q < Fin) red[(part * H + rj) * RW + q] = acc_wt[q];
-    __syncthreads();
+    tc::named_bar_sync(1, NP);
     float* out = partials + (size_t)blockIdx.x * P;
-    for (int i = tid; i < H * RW; i += NT) {
+    for (int i = tid; i < H * RW; i += NP) {
         const int j = i / RW, q = i % RW;
         const float s = red[(0 * H + j) * RW + q] + red[(1 * H + j) * RW + q] + red[(2 * H + j) * RW + q] + red[(3 * H + j) * RW + q];
         if (q == Fin) out[off_bt + j] = s; else out[off_Wt + (size_t)j * Fin + q] = s;
     }
+    }   // producer
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 64);
+    if (warp == NP / 32) tc::tmem_dealloc(tmem, 64);
 }
 
 // --------------------------------------------------------------------------- head gradients
-constexpr int HG_R = 64;
-__global__ void __launch_bounds__(256)
+// Bandwidth-bound over h (256 B per row): 1024 threads = 4 row groups x 256 so that each SM has
+// 32 warps of loads in flight; the groups are combined through shared memory at the end.
+constexpr int HG_R = 64, HG_G = 4;
+__global__ void __launch_bounds__(256 * HG_G)
 head_grad_kernel(const float* __restrict__ h, const float* __restrict__ dhead, float* __restrict__ partials,
                  long long P, long long off_Whead, long long off_bhead, long long rows, int NH) {
-    __shared__ float S[HG_R * 65];
-    __shared__ float Dh[HG_R * B200RL_MAX_HEADS];
-    const int tid = threadIdx.x;
+    B200RL_DYN_SMEM(float, smem);
+    const int grp = threadIdx.x >> 8, tid = threadIdx.x & 255;
+    float* S = smem + grp * (HG_R * 65 + HG_R * B200RL_MAX_HEADS);
+    float* Dh = S + HG_R * 65;
     constexpr int E = (B200RL_MAX_HEADS * 64 + 255) / 256;
     float acc[E], accb = 0.f;
 #pragma unroll
     for (int e = 0; e < E; ++e) acc[e] = 0.f;
     const long long nch = (rows + HG_R - 1) / HG_R;
-    for (long long ch = blockIdx.x; ch < nch; ch += gridDim.x) {
+    const long long nloop = (nch + (long long)gridDim.x * HG_G - 1) / ((long long)gridDim.x * HG_G);
+    for (long long it = 0; it < nloop; ++it) {
+        const long long ch = (it * gridDim.x + blockIdx.x) * HG_G + grp;
         const long long row0 = ch * HG_R;
         __syncthreads();
         for (int i = tid; i < HG_R * 16; i += 256) {
@@ -260,13 +291,23 @@ head_grad_kernel(const float* __restrict__ h, const float* __restrict__ dhead, f
             accb += s;
         }
     }
-    float* out = partials + (size_t)blockIdx.x * P;
+    // combine the row groups: red[grp][NH*64 + NH]
+    __syncthreads();
+    float* red = smem;
+    const int RW = NH * 64 + NH;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         const int o = e * 256 + tid;
-        if (o < NH * 64) out[off_Whead + o] = acc[e];
+        if (o < NH * 64) red[grp * RW + o] = acc[e];
     }
-    if (tid < NH) out[off_bhead + tid] = accb;
+    if (tid < NH) red[grp * RW + NH * 64 + tid] = accb;
+    __syncthreads();
+    float* out = partials + (size_t)blockIdx.x * P;
+    for (int i = threadIdx.x; i < RW; i += 256 * HG_G) {
+        float s = 0.f;
+        for (int gg = 0; gg < HG_G; ++gg) s += red[gg * RW + i];
+        if (i < NH * 64) out[off_Whead + i] = s; else out[off_bhead + (i - NH * 64)] = s;
+    }
 }
 
 template <typename K>
@@ -296,7 +337,9 @@ int launch_dx_tc(const float* dpre, const float* u, const float* W_ih, const flo
     else B200RL_DX_LAUNCH(32);
 #undef B200RL_DX_LAUNCH
     if (check_launch("lstm_wgrad(dx tc)")) return 1;
-    B200RL_LAUNCH(head_grad_kernel, nparts, 256, 0, stream, h, dhead, partials, P, off_Whead, off_bhead, rows, NH);
+    const size_t hsm = sizeof(float) * HG_G * (HG_R * 65 + HG_R * B200RL_MAX_HEADS);
+    if (dx_set_smem(head_grad_kernel, hsm)) return 1;
+    B200RL_LAUNCH(head_grad_kernel, nparts, 256 * HG_G, hsm, stream, h, dhead, partials, P, off_Whead, off_bhead, rows, NH);
     return check_launch("lstm_wgrad(head grad)");
 }
 

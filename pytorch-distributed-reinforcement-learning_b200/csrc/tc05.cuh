@@ -62,6 +62,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "B200RL_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+// barrier among a subset of the CTA's warps (id 1..15; `nthreads` a multiple of 32)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -116,15 +121,29 @@ inline SmemDesc make_desc(const void* p, uint32_t lbo, uint32_t sbo) { return Sm
 struct EmulTmem { float d[128][512]; };
 inline EmulTmem& emul_tmem() { static EmulTmem t; return t; }
 
-inline void mbar_init(uint64_t* bar, uint32_t) { *bar = 0; }
+// host mbarrier: bits [0,16) pending arrivals, [16,32) arrival count, bit 32 phase parity
+inline void mbar_init(uint64_t* bar, uint32_t count) { *bar = (uint64_t)count | ((uint64_t)count << 16); }
 inline void fence_mbar_init() {}
-inline void mbar_wait(uint64_t*, uint32_t) {}        // emulated MMAs complete synchronously
+inline void mbar_arrive(uint64_t* bar) {
+    std::lock_guard<std::mutex> g(emul::atomic_mu());
+    uint64_t v = *bar;
+    uint32_t pending = (uint32_t)(v & 0xffff) - 1, count = (uint32_t)((v >> 16) & 0xffff), phase = (uint32_t)((v >> 32) & 1);
+    if (pending == 0) { pending = count; phase ^= 1; }
+    *bar = (uint64_t)pending | ((uint64_t)count << 16) | ((uint64_t)phase << 32);
+}
+inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (;;) {
+        { std::lock_guard<std::mutex> g(emul::atomic_mu()); if ((uint32_t)((*bar >> 32) & 1) != (parity & 1)) return; }
+        std::this_thread::yield();
+    }
+}
+inline void named_bar_sync(int id, int nthreads) { emul::named_barrier(id, nthreads); }
 inline void fence_async_smem() {}
 inline void fence_before_sync() {}
 inline void fence_after_sync() {}
 inline void tmem_alloc(uint32_t* dst, uint32_t) { if ((threadIdx.x & 31) == 0) *dst = 0; }
 inline void tmem_dealloc(uint32_t, uint32_t) {}
-inline void mma_commit(uint64_t*) {}
+inline void mma_commit(uint64_t* bar) { mbar_arrive(bar); }   // emulated MMAs complete synchronously
 
 inline float emul_elem(const SmemDesc& d, bool mn_major, int mn, int k) {
     size_t off = mn_major ? (size_t)(mn % 4) * 4 + (size_t)(mn / 4) * d.sbo + (size_t)(k % 8) * 16 + (size_t)(k / 8) * d.lbo

@@ -22,9 +22,13 @@
 // (measured on B200: kind::tf32 with MN-major descriptors returns zeros, K-major is exact
 // -- tools/tc_probe.cu -- so the tile is transposed on the way into shared memory).
 // LBO = 144 B and SBO = 672 B are chosen = 16 B / 32 B modulo 128 B, which makes the 32 lanes
-// of every scatter store hit 32 distinct banks.  fence.proxy.async + __syncthreads, then one
-// elected thread issues 6 tcgen05.mma and a tcgen05.commit onto the stage's mbarrier; the
-// next stages are filled while the tensor core works (3-stage ring, 189 KB of smem).
+// of every scatter store hit 32 distinct banks.
+//
+// Warp-specialised pipeline (no CTA-wide barrier inside the loop): warps 0-7 are PRODUCERS
+// (load / split / scatter a stage, fence.proxy.async, arrive on full[stage]); warp 8 is the MMA
+// ISSUER (one lane waits on full[stage], issues 6 tcgen05.mma, tcgen05.commit -> empty[stage]).
+// A single thread needs ~50-100 cycles per tcgen05.mma issue (tools/tc_probe2.cu), so the
+// issuer must not be one of the filling threads.  3-stage ring, 189 KB of smem.
 #include "common.cuh"
 #include "tc05.cuh"
 #include "launchers.cuh"
@@ -32,7 +36,7 @@
 namespace b200rl {
 
 namespace wtc {
-constexpr int H = 64, G = 256, KC = 128, NT = 256;
+constexpr int H = 64, G = 256, KC = 128, NP = 256, NT = NP + 32;   // producers + issuer warp
 constexpr int SR = 16;                          // rows per stage (2 MMA K-steps of 8)
 constexpr int NSTAGE = 3;
 constexpr int LBO = 144;                        // K direction: next core matrix (4 rows)      = 16 B mod 128 B
@@ -60,19 +64,22 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
     unsigned char* stage0 = smem;                                   // 1024-aligned by construction (offset 0)
     float* WtS = reinterpret_cast<float*>(smem + NSTAGE * STAGE);   // WtS[q*64 + j]
     float* bts = WtS + Fin * H;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(bts + H);          // [0..NSTAGE): stage free ; [NSTAGE]: all done
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NSTAGE + 1);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bts + H);          // full[NSTAGE] | empty[NSTAGE] | done
+    uint64_t* full = bars, *empty = bars + NSTAGE, *done = bars + 2 * NSTAGE;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 1);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool producer = warp < NP / 32;
     const int r_in = lane & 7, q4 = lane >> 3;                       // row inside a core matrix, float4 column
 
     for (int i = tid; i < Fin * H; i += NT) { int q = i / H, j = i % H; WtS[i] = Wt[j * Fin + q]; }
     if (tid < H) bts[tid] = bt[tid];
     if (tid == 0) {
-        for (int i = 0; i <= NSTAGE; ++i) tc::mbar_init(&bars[i], 1);
+        for (int i = 0; i < NSTAGE; ++i) { tc::mbar_init(&full[i], NP); tc::mbar_init(&empty[i], 1); }
+        tc::mbar_init(done, 1);
         tc::fence_mbar_init();
     }
-    if (warp == 0) tc::tmem_alloc(tmem_slot, 256);
+    if (warp == NP / 32) tc::tmem_alloc(tmem_slot, 256);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -84,50 +91,46 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
     float4 dbacc[2];
     dbacc[0] = make_float4(0.f, 0.f, 0.f, 0.f); dbacc[1] = dbacc[0];
 
-    // Register-staged loads: the HBM reads of stage i+1 are issued before stage i is split and
-    // scattered, so their latency overlaps the shared-memory work (and the tensor core).
-    constexpr int UP = 8;                           // torso inputs prefetched in registers when Fin <= UP
-    float4 dv[4], hvv; float uvv[UP]; bool rowok[3];   // [0],[1]: D rows r8 = 0,1 ; [2]: A row
-    auto issue_loads = [&](long long stg) {
+    // Register-staged loads: a ring of 4 register sets; the HBM reads of stage i+3 are issued
+    // before stage i is split and scattered, so their latency overlaps three stages of work.
+    constexpr int UP = 4;                           // torso inputs prefetched in registers when Fin <= UP
+    struct StageRegs { float4 d[4]; float4 h; float u[UP]; bool ok; };
+    StageRegs ring[4];
+    auto issue_loads = [&](StageRegs& R, long long stg) {
         const long long row0 = stg * SR;
+        const bool live = stg < nstages;
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) {
             const int r8 = i4 & 1, hh = i4 >> 1;
             const int c4 = (warp * 2 + hh) * 4 + q4;
             const long long row = row0 + r8 * 8 + r_in;
-            dv[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < rows) dv[i4] = *reinterpret_cast<const float4*>(dpre + (size_t)row * G + c4 * 4);
+            R.d[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live && row < rows) R.d[i4] = *reinterpret_cast<const float4*>(dpre + (size_t)row * G + c4 * 4);
         }
         const int c4 = (warp >> 1) * 4 + q4;
         const long long row = row0 + (warp & 1) * 8 + r_in;
-        hvv = make_float4(0.f, 0.f, 0.f, 0.f);
-        rowok[2] = row < rows;
-        if (rowok[2]) {
-            const int b = (int)(row / T), t = (int)(row % T);
+        R.h = make_float4(0.f, 0.f, 0.f, 0.f);
+        R.ok = live && row < rows;
+#pragma unroll
+        for (int q = 0; q < UP; ++q) R.u[q] = 0.f;
+        if (R.ok) {
+            const unsigned urow = (unsigned)row, b = urow / (unsigned)T, t = urow - b * (unsigned)T;   // 32-bit: B*T < 2^31 is checked by the launcher
             const float* hp = (t == 0) ? hx0 + (size_t)b * H : h + (size_t)(row - 1) * H;
-            hvv = *reinterpret_cast<const float4*>(hp + c4 * 4);
+            R.h = *reinterpret_cast<const float4*>(hp + c4 * 4);
             if (Fin <= UP) {
 #pragma unroll
-                for (int q = 0; q < UP; ++q) uvv[q] = q < Fin ? __ldg(u + (size_t)row * Fin + q) : 0.f;
+                for (int q = 0; q < UP; ++q) if (q < Fin) R.u[q] = __ldg(u + (size_t)row * Fin + q);
             }
         }
     };
-    if ((long long)blockIdx.x < nstages) issue_loads(blockIdx.x);
 
     int it = 0;
-    for (long long st = blockIdx.x; st < nstages; st += gridDim.x, ++it) {
+    auto process = [&](const StageRegs& R, long long st) {
         const int buf = it % NSTAGE, use = it / NSTAGE;
         unsigned char* sb = stage0 + (size_t)buf * STAGE;
         unsigned char* A_hi = sb, *A_lo = sb + A_TILE, *D_hi = sb + 2 * A_TILE, *D_lo = sb + 2 * A_TILE + D_TILE;
         const long long row0 = st * SR;
-        // take ownership of this stage's registers, then immediately refill them for the next stage
-        float4 cd[4], ch = hvv; float cu[UP]; const bool aok = rowok[2];
-#pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) cd[i4] = dv[i4];
-#pragma unroll
-        for (int q = 0; q < UP; ++q) cu[q] = uvv[q];
-        if (st + gridDim.x < nstages) issue_loads(st + gridDim.x);
-        if (use >= 1) tc::mbar_wait(&bars[buf], (uint32_t)((use - 1) & 1));   // MMAs of the previous use of this buffer are done
+        if (use >= 1) tc::mbar_wait(&empty[buf], (uint32_t)((use - 1) & 1));  // MMAs of the previous use of this buffer are done
 
         // ---- D tile: 16 rows x 64 float4.  Thread: rows r8*8 + r_in (r8 = 0,1), float4 columns c4(hh) (hh = 0,1)
 #pragma unroll
@@ -135,7 +138,7 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
             const int r8 = i4 & 1, hh = i4 >> 1;
             const int c4 = (warp * 2 + hh) * 4 + q4;
             const int r = r8 * 8 + r_in;
-            const float4 v = cd[i4];
+            const float4 v = R.d[i4];
             dbacc[hh].x += v.x; dbacc[hh].y += v.y; dbacc[hh].z += v.z; dbacc[hh].w += v.w;
             const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -152,15 +155,15 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
             const int r = (warp & 1) * 8 + r_in, c4 = (warp >> 1) * 4 + q4;              // c4 in 0..15
             const long long row = row0 + r;
             float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 hv = ch;
-            if (aok) {
+            const float4 hv = R.h;
+            if (R.ok) {
                 float4 a = *reinterpret_cast<const float4*>(bts + c4 * 4);
                 if (Fin <= UP) {
 #pragma unroll
                     for (int q = 0; q < UP; ++q) {
                         if (q < Fin) {
                             const float4 w = *reinterpret_cast<const float4*>(WtS + q * H + c4 * 4);
-                            a.x = fmaf(cu[q], w.x, a.x); a.y = fmaf(cu[q], w.y, a.y); a.z = fmaf(cu[q], w.z, a.z); a.w = fmaf(cu[q], w.w, a.w);
+                            a.x = fmaf(R.u[q], w.x, a.x); a.y = fmaf(R.u[q], w.y, a.y); a.z = fmaf(R.u[q], w.z, a.z); a.w = fmaf(R.u[q], w.w, a.w);
                         }
                     }
                 } else {
@@ -188,8 +191,28 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
             }
         }
         tc::fence_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
-        __syncthreads();
-        if (tid == 0) {
+        tc::mbar_arrive(&full[buf]);
+        ++it;
+    };
+
+    if (producer) {
+        const long long g = gridDim.x;
+        long long st = blockIdx.x;
+        issue_loads(ring[0], st); issue_loads(ring[1], st + g); issue_loads(ring[2], st + 2 * g);
+        while (st < nstages) {
+            issue_loads(ring[3], st + 3 * g); process(ring[0], st); st += g; if (st >= nstages) break;
+            issue_loads(ring[0], st + 3 * g); process(ring[1], st); st += g; if (st >= nstages) break;
+            issue_loads(ring[1], st + 3 * g); process(ring[2], st); st += g; if (st >= nstages) break;
+            issue_loads(ring[2], st + 3 * g); process(ring[3], st); st += g;
+        }
+    } else if (lane == 0) {
+        // ---- MMA issuer: stage descriptors differ only in their start address (low 14 bits, 16-byte units)
+        int n = 0;
+        for (long long st = blockIdx.x; st < nstages; st += gridDim.x, ++n) {
+            const int buf = n % NSTAGE, use = n / NSTAGE;
+            unsigned char* sb = stage0 + (size_t)buf * STAGE;
+            unsigned char* A_hi = sb, *A_lo = sb + A_TILE, *D_hi = sb + 2 * A_TILE, *D_lo = sb + 2 * A_TILE + D_TILE;
+            tc::mbar_wait(&full[buf], (uint32_t)(use & 1));
             tc::fence_after_sync();
 #pragma unroll
             for (int s = 0; s < SR / 8; ++s) {
@@ -198,18 +221,16 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
                 const tc::SmemDesc al = tc::make_desc(A_lo + ko, LBO, SBO);
                 const tc::SmemDesc dh = tc::make_desc(D_hi + ko, LBO, SBO);
                 const tc::SmemDesc dl = tc::make_desc(D_lo + ko, LBO, SBO);
-                tc::mma_tf32(tmem, ah, dh, idesc, (it > 0 || s > 0) ? 1u : 0u);
+                tc::mma_tf32(tmem, ah, dh, idesc, (n > 0 || s > 0) ? 1u : 0u);
                 tc::mma_tf32(tmem, ah, dl, idesc, 1u);
                 tc::mma_tf32(tmem, al, dh, idesc, 1u);
             }
-            tc::mma_commit(&bars[buf]);
+            tc::mma_commit(&empty[buf]);
         }
+        tc::mma_commit(done);
     }
-    if (tid == 0) tc::mma_commit(&bars[NSTAGE]);
-    tc::mbar_wait(&bars[NSTAGE], 0);
-#ifdef B200RL_EMUL
-    __syncthreads();                 // the host twin runs MMAs synchronously on thread 0
-#endif
+    if (producer) {
+    tc::mbar_wait(done, 0);
     tc::fence_after_sync();
 
     // ---- epilogue: TMEM lane = k (A column), TMEM column = p = j*4 + g ; PyTorch row n = g*64 + j
@@ -249,9 +270,10 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
             for (int g = 0; g < 4; ++g) { out[off_bih + g * H + c4] = v[g]; out[off_bhh + g * H + c4] = v[g]; }
         }
     }
+    }   // producer
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 256);
+    if (warp == NP / 32) tc::tmem_dealloc(tmem, 256);
 }
 
 int launch_wgrad_tc(const float* dpre, const float* h, const float* hx0, const float* u,
@@ -259,6 +281,7 @@ int launch_wgrad_tc(const float* dpre, const float* h, const float* hx0, const f
                     long long off_Wih, long long off_Whh, long long off_bih, long long off_bhh,
                     int B, int T, int Fin, void* stream) {
     B200RL_REQUIRE(Fin >= 1 && Fin <= wtc::MAXF, "lstm_wgrad(tc): Fin=%d out of range", Fin);
+    B200RL_REQUIRE((long long)B * T < (1LL << 31), "lstm_wgrad(tc): B*T must be below 2^31");
     const size_t smem = wgrad_tc_smem_bytes(Fin);
 #ifndef B200RL_EMUL
     cudaError_t e = cudaFuncSetAttribute(lstm_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

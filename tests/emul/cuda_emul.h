@@ -45,6 +45,8 @@ struct WarpCtx {
 };
 struct BlockCtx {
     std::unique_ptr<std::barrier<>> bar;
+    std::mutex named_mu;
+    std::unique_ptr<std::barrier<>> named[16];
     std::vector<std::unique_ptr<WarpCtx>> warps;
     unsigned char* dyn = nullptr;
 };
@@ -52,6 +54,7 @@ inline BlockCtx*& cur_block() { static BlockCtx* b = nullptr; return b; }
 inline dim3& g_blockDim() { static dim3 d; return d; }
 inline dim3& g_gridDim() { static dim3 d; return d; }
 inline std::mutex& atomic_mu() { static std::mutex m; return m; }
+inline void named_barrier(int id, int nthreads);
 }  // namespace emul
 
 inline thread_local dim3 threadIdx;
@@ -112,6 +115,19 @@ static inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f
 static inline int __float_as_int(float f) { int v; memcpy(&v, &f, 4); return v; }
 static inline unsigned __float_as_uint(float f) { unsigned v; memcpy(&v, &f, 4); return v; }
 static inline float __uint_as_float(unsigned v) { float f; memcpy(&f, &v, 4); return f; }
+
+namespace emul {
+inline void named_barrier(int id, int nthreads) {
+    BlockCtx* b = cur_block();
+    std::barrier<>* bar;
+    {
+        std::lock_guard<std::mutex> g(b->named_mu);
+        if (!b->named[id]) b->named[id].reset(new std::barrier<>(nthreads));
+        bar = b->named[id].get();
+    }
+    bar->arrive_and_wait();
+}
+}  // namespace emul
 
 #define B200RL_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(emul::cur_block()->dyn)
 
