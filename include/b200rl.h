@@ -127,6 +127,31 @@ int b200rl_impala_head(const float* head_out, const float* act, const float* rew
                        float gamma, float rho_bar, float c_bar,
                        float c_policy, float c_value, float c_entropy, void* stream);
 
+/* V-MPO head                  agents/learner_module/v_mpo/learning.py:44-99, agents/learner.py:320-348
+ *   head_out (B,T,1+A) = [value, z]; duals = device {log_eta, log_alpha} (fp64, as in the reference).
+ *   vmpo_gae:    td target, delta, GAE scan -> gae (B,T-1); value loss sum -> scalars[1]; dLoss/dvalue -> dhead[...,0],
+ *                the policy columns of dhead are zeroed.
+ *   vmpo_select: per timestep column of gae_all (Bg,n): thr[t] = k-th largest over the batch (torch.topk(gae, k, dim=0));
+ *                colstat[t] = column max, colstat[n+t] = sum over the selected of exp((g - max)/(eta+1e-7)).
+ *                gae_all is the rank's own matrix on one GPU, the all-gathered one when the batch is sharded.
+ *   vmpo_grad:   psi = softmax over all selected; adds dLoss/dz (policy + alpha*KL term) to dhead; scalars[0] += L_pi,
+ *                scalars[2] += sum KL, scalars[3] += #selected, scalars[6],[7] = softmax max / normaliser.
+ *   vmpo_dual_step: L_eta, L_alpha, their gradients and the RMSprop step of log_eta/log_alpha (never clipped);
+ *                losses_out[6] = {L_pi, L_V, L_eta, L_alpha, total, mean KL}.
+ *   N_global = B_global*(T-1) (every mean of the update), n_selected = k*(T-1).                                   */
+int b200rl_vmpo_gae(const float* head_out, const float* rew, const float* is_fir,
+                    float* gae, float* dhead, double* scalars, int B, int T, int A,
+                    float gamma, float lambda_, float c_value, double N_global, void* stream);
+int b200rl_vmpo_select(const float* gae_all, int Bg, int n, int k, const double* duals,
+                       float* thr, float* colstat, void* stream);
+int b200rl_vmpo_grad(const float* head_out, const float* act, const float* behav_logits, const float* gae,
+                     const float* thr, const float* colstat, const double* duals,
+                     float* dhead, double* scalars, int B, int T, int A,
+                     float c_policy, double N_global, void* stream);
+int b200rl_vmpo_dual_step(double* duals, double* dual_sq, const double* scalars, double* losses_out,
+                          double coef_eta, double coef_alpha, double lr, double rms_alpha, double rms_eps,
+                          double N_global, double n_selected, double c_policy, double c_value, void* stream);
+
 /* ---- optimizer step ---------------------------------------------------------------
  * clip_grad_norm_(max_norm) + RMSprop(lr, alpha, eps)
  *                    agents/learner_module/ppo/learning.py:93-106, agents/learner.py:70

@@ -19,7 +19,7 @@ import pickle
 import numpy as np
 import torch
 
-from ..engine import OnPolicyEngine
+from ..engine import OnPolicyEngine, VMPOEngine
 from ..utils.utils import ExecutionTimer, HostStager, Params, Protocol, hyper_from_args, to_torch
 from .storage_module.shared_batch import SMInterFace
 from . import ppo_awrapper, v_mpo_awrapper, impala_awrapper, sac_awrapper, sac_continuous_awrapper
@@ -190,3 +190,30 @@ class LearnerSinglePPO(LearnerBase):
 class LearnerSingleIMPALA(LearnerSinglePPO):
     """(reference learner.py:317)"""
     engine_algo = "IMPALA"
+
+
+class LearnerSingleVMPO(LearnerBase):
+    """V-MPO (reference learner.py:320-348): the dual variables `log_eta`, `log_alpha` (fp64,
+    initialised to log(v_mpo_lagrange_multiplier_init)) and their RMSprop groups live in the
+    engine on the device; `get_coef_alpha()` draws eps_alpha log-uniformly in
+    [coef_alpha_below, coef_alpha_upper] exactly as the reference does."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        assert self.model.actor is self.model.critic
+        self.actor = self.model.actor
+        self.critic = self.model.critic
+        self.engine = VMPOEngine(self.actor, hyper_from_args(self.args), ops=self._ops, process_group=self.process_group)
+        self.to_gpu.skip = {"log_prob"}          # V-MPO reads the behaviour logits, not log_prob
+
+    @property
+    def log_eta(self):
+        return self.engine.duals[0]
+
+    @property
+    def log_alpha(self):
+        return self.engine.duals[1]
+
+    def get_coef_alpha(self):
+        from torch.distributions import Uniform
+        return Uniform(torch.tensor(self.args.coef_alpha_below).log(), torch.tensor(self.args.coef_alpha_upper).log()).sample().exp()

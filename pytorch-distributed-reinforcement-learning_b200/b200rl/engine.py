@@ -137,3 +137,74 @@ class OnPolicyEngine:
             "ratio-min": v[4], "ratio-max": v[5], "ratio-avg": v[3] / N,
             "grad-norm": float(self.grad_norm.item()),
         }
+
+
+class VMPOEngine(OnPolicyEngine):
+    """V-MPO update (reference `v_mpo/learning.py:44-124`, `learner.py:320-348`): same LSTM
+    kernels, the V-MPO head (GAE -> per-timestep top-k over the batch -> global softmax ->
+    policy / KL gradients) and the two fp64 dual variables with their own RMSprop state.
+    `log_eta`, `log_alpha` live on the device as `self.duals` (fp64)."""
+
+    def __init__(self, net, hyper, ops=None, process_group=None):
+        super().__init__(net, "V-MPO", hyper, ops=ops, process_group=process_group)
+        dev = self.device
+        init = math.log(self.hp["v_mpo_lagrange_multiplier_init"])
+        self.duals = torch.full((2,), init, dtype=torch.float64, device=dev)      # log_eta, log_alpha
+        self.dual_sq = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.losses_dev = torch.zeros(6, dtype=torch.float64, device=dev)
+        self._zero8 = torch.zeros(8, dtype=torch.float64, device=dev)
+
+    def _vm_workspace(self, B, T):
+        if getattr(self, "_vm_shape", None) == (B, T):
+            return
+        dev = self.device
+        self.gae = torch.empty(B, T - 1, device=dev)
+        self.gae_all = self.gae if self.world == 1 else torch.empty(B * self.world, T - 1, device=dev)
+        self.thr = torch.empty(T - 1, device=dev)
+        self.colstat = torch.empty(2 * (T - 1), device=dev)
+        self._vm_shape = (B, T)
+
+    def update(self, batch, coef_alpha):
+        """`coef_alpha`: this epoch's eps_alpha draw (`LearnerSingleVMPO.get_coef_alpha()`)."""
+        ops, L, hp, lib = self.ops, self.L, self.hp, self.ops.lib
+        obs = batch["obs"]
+        B, T = obs.shape[0], obs.shape[1]
+        A = self.net.n_outputs
+        self._workspace(B, T)
+        self._vm_workspace(B, T)
+        u = obs.reshape(B, T, -1)
+        st = ops._stream(self.device)
+        Bg = B * self.world
+        N = float(Bg * (T - 1))
+        k = math.ceil(Bg / 2)
+        from .native import ptr
+        ops._chk(batch["act"], batch["rew"], batch["is_fir"], batch["logits"], batch["hx"], batch["cx"])
+
+        ops.lstm_fwd(L, self.flat, u, batch["hx"], batch["cx"], self.ws)
+        ops.head_fwd(L, self.flat, self.ws["h"], self.head_out)
+        self.scalars.copy_(self._zero8)
+        lib.call("b200rl_vmpo_gae", ptr(self.head_out), ptr(batch["rew"]), ptr(batch["is_fir"]), ptr(self.gae),
+                 ptr(self.dhead), ptr(self.scalars), B, T, A, hp["gamma"], hp["lmbda"], hp["value_loss_coef"], N, st)
+        if self.world > 1:
+            torch.distributed.all_gather_into_tensor(self.gae_all, self.gae, group=self.pg)
+        lib.call("b200rl_vmpo_select", ptr(self.gae_all), Bg, T - 1, k, ptr(self.duals), ptr(self.thr), ptr(self.colstat), st)
+        lib.call("b200rl_vmpo_grad", ptr(self.head_out), ptr(batch["act"]), ptr(batch["logits"]), ptr(self.gae), ptr(self.thr),
+                 ptr(self.colstat), ptr(self.duals), ptr(self.dhead), ptr(self.scalars), B, T, A, hp["policy_loss_coef"], N, st)
+        ops.lstm_bwd(L, self.flat, self.dhead, self.ws, batch["cx"])
+        ops.lstm_wgrad(L, self.flat, self.ws, batch["hx"], u, self.dhead, self.partials, variant=self.wgrad_variant)
+        ops.reduce_partials(self.partials, self.grad)
+        if self.world > 1:                      # kernels already normalise by the GLOBAL N: plain sum, no 1/world
+            torch.distributed.all_reduce(self.grad, group=self.pg)
+            torch.distributed.all_reduce(self.scalars[:4], group=self.pg)
+        ops.clip_rmsprop(self.flat, self.grad, self.sq_avg, L.P, 1.0, hp["max_grad_norm"], hp["lr"], 0.99, 1e-5, self.grad_norm)
+        lib.call("b200rl_vmpo_dual_step", ptr(self.duals), ptr(self.dual_sq), ptr(self.scalars), ptr(self.losses_dev),
+                 hp["coef_eta"], float(coef_alpha), hp["lr"], 0.99, 1e-5, N, float(k * (T - 1)),
+                 hp["policy_loss_coef"], hp["value_loss_coef"], st)
+        self.n_launches += 12 + {0: 0, 1: 2, 2: 1}[self.wgrad_variant]
+
+    def losses(self):
+        v = self.losses_dev.cpu().tolist()
+        d = self.duals.cpu().tolist()
+        return {"policy-loss": v[0], "value-loss": v[1], "loss-temperature": v[2], "loss-alpha": v[3], "loss": v[4],
+                "kl-mean": v[5], "log_eta": d[0], "log_alpha": d[1], "selected": float(self.scalars[3].item()),
+                "grad-norm": float(self.grad_norm.item())}

@@ -32,6 +32,10 @@ SIGNATURES = {
     "b200rl_reduce_partials": [_P, _P, _I, _L, _P],
     "b200rl_ppo_head": [_P] * 13 + [_I, _I, _I, _I] + [_F] * 6 + [_P],
     "b200rl_impala_head": [_P] * 13 + [_I, _I, _I] + [_F] * 6 + [_P],
+    "b200rl_vmpo_gae": [_P] * 6 + [_I, _I, _I, _F, _F, _F, C.c_double, _P],
+    "b200rl_vmpo_select": [_P, _I, _I, _I, _P, _P, _P, _P],
+    "b200rl_vmpo_grad": [_P] * 9 + [_I, _I, _I, _F, C.c_double, _P],
+    "b200rl_vmpo_dual_step": [_P] * 4 + [C.c_double] * 9 + [_P],
     "b200rl_clip_rmsprop": [_P, _P, _P, _L] + [_F] * 5 + [_P, _P],
     "b200rl_clip_adam": [_P, _P, _P, _P, _L] + [_F] * 6 + [_I, _P, _P],
 }

@@ -108,3 +108,57 @@ def test_ragged_batch_and_single_row(backend):
         _close(L["loss"], float(r["loss"]), rtol=1e-4, atol=1e-7, what=f"loss B={B} T={T}")
         _close(_flat_sd_order(model.actor, eng.grad), r["grad"], rtol=1e-3, atol=2e-5 * max(1.0, float(r["grad"].abs().max())), what="grad")
         _close(_flat_sd_order(model.actor, eng.flat), r["params"], what="params")
+
+
+@pytest.mark.parametrize("name", ["vmpo_small", "vmpo_odd"])
+def test_vmpo_update_matches_reference(backend, name):
+    from b200rl.engine import VMPOEngine
+    ops, dev = backend
+    g = load_golden(name)
+    B, T, f, A, H, n, cont = [int(x) for x in g["meta"]]
+    model = _model(g, "V-MPO", dev)
+    eng = VMPOEngine(model.actor, oracle.DEFAULT_HYPER, ops=ops)
+    orc = oracle.OracleLearner("V-MPO", golden_sd(g, "sd0"))
+    for i in range(n):
+        ca = float(g["coef_alpha"][i])
+        r = orc.update(golden_batch(g, i), coef_alpha=torch.tensor(g["coef_alpha"][i]))
+        eng.update(golden_batch(g, i, dev), ca)
+        L = eng.losses()
+        assert L["selected"] == -(-B // 2) * (T - 1)                 # exactly ceil(B/2) per timestep
+        _close(eng.gae.cpu().unsqueeze(-1), r["gae"], what="gae")
+        _close(_flat_sd_order(model.actor, eng.grad), r["grad"], rtol=1e-3, atol=2e-5 * max(1.0, float(r["grad"].abs().max())), what="grad")
+        for k in ("policy-loss", "value-loss", "loss-temperature", "loss-alpha"):
+            _close(L[k], g["out/" + k][i], rtol=1e-4, atol=1e-7, what=f"{k}[{i}]")
+        _close(L["loss"], g["out/loss"][i], rtol=1e-4, atol=1e-7, what="loss")
+        _close(_flat_sd_order(model.actor, eng.flat), g[f"out/params/{i}"], what=f"params[{i}]", **PARAMS)
+        _close([L["log_eta"], L["log_alpha"]], g["out/duals"][i], rtol=1e-6, atol=1e-9, what="duals")
+
+
+@pytest.mark.gpu
+def test_vmpo_selection_properties_at_cfg4_shard_shape():
+    """B=1024 sequences per GPU, T=128 (BASELINE config 4's per-GPU shard): exactly ceil(B/2) advantages are
+    selected in every timestep column, the threshold is the k-th largest, psi sums to one."""
+    from b200rl.engine import VMPOEngine
+    from b200rl.networks import models as M
+    from b200rl.synth import make_rollouts
+    dev = torch.device("cuda:0")
+    B, T = 1024, 128
+    torch.manual_seed(0)
+    model = M.MlpLSTMSingle(4, 2, T, 64).to(dev)
+    eng = VMPOEngine(model.actor, oracle.DEFAULT_HYPER)
+    batch = {k: v.to(dev) for k, v in make_rollouts(B, T, 4, 2).items()}
+    eng.update(batch, 0.0075)
+    L = eng.losses()
+    assert L["selected"] == (B // 2) * (T - 1)
+    kth = torch.topk(eng.gae, B // 2, dim=0).values[-1]
+    torch.testing.assert_close(eng.thr, kth, rtol=0, atol=0)
+    eta = 5.0 + 1e-7
+    sel = eng.gae >= eng.thr[None, :]
+    u = (eng.gae / eta).double()
+    psi = torch.where(sel, (u - u[sel].max()).exp(), torch.zeros_like(u))
+    psi = psi / psi.sum()
+    assert abs(float(psi.sum()) - 1.0) < 1e-9
+    # the engine's normaliser equals the direct one
+    Z = float(eng.scalars[7].item())
+    direct = float(torch.where(sel, (u - float(eng.scalars[6].item())).exp(), torch.zeros_like(u)).sum())
+    assert abs(Z - direct) / direct < 1e-5

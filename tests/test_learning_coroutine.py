@@ -20,11 +20,13 @@ class StopAfter:
         return self.calls > self.n
 
 
-@pytest.mark.parametrize("name,algo", [("ppo_small", "PPO"), ("impala_small", "IMPALA"), ("ppo_continuous_small", "PPO-Continuous")])
+@pytest.mark.parametrize("name,algo", [("ppo_small", "PPO"), ("impala_small", "IMPALA"), ("ppo_continuous_small", "PPO-Continuous"),
+                                       ("vmpo_small", "V-MPO")])
 def test_learning_coroutine_matches_reference(backend, name, algo, tmp_path):
     from b200rl.agents import learner as LM
     from b200rl.agents.learner_module.ppo.learning import learning as learn_ppo
     from b200rl.agents.learner_module.impala.learning import learning as learn_impala
+    from b200rl.agents.learner_module.v_mpo.learning import learning as learn_vmpo
     from b200rl.networks import models as M
     from b200rl.utils.utils import ExecutionTimer, load_params
     ops, dev = backend
@@ -36,9 +38,12 @@ def test_learning_coroutine_matches_reference(backend, name, algo, tmp_path):
     args.loss_log_interval = 1
     model = (M.MlpLSTMSingleContinuous if cont else M.MlpLSTMSingle)(f, A, T, H)
     model.actor.load_state_dict(golden_sd(g, "sd0"))
-    cls = LM.LearnerSingleIMPALA if algo == "IMPALA" else LM.LearnerSinglePPO
+    cls = {"IMPALA": LM.LearnerSingleIMPALA, "V-MPO": LM.LearnerSingleVMPO}.get(algo, LM.LearnerSinglePPO)
     learner = cls(args, None, model, None, StopAfter(n), None, None, [f], ops=None if dev.type == "cuda" else ops)
     logs, pubs = [], []
+    if algo == "V-MPO":
+        coefs = iter(torch.tensor(c) for c in g["coef_alpha"])
+        learner.get_coef_alpha = lambda: next(coefs)
     learner.log_loss_tensorboard = lambda timer, loss, d: logs.append((float(loss), dict(d)))
     learner.pub_model = lambda sd: pubs.append(sd)
     keys = ("obs", "act", "rew", "logits", "log_prob", "is_fir", "hx", "cx")
@@ -52,16 +57,19 @@ def test_learning_coroutine_matches_reference(backend, name, algo, tmp_path):
             b["cx"] = b["cx"][:, None, :].expand(-1, T, -1).contiguous()
             q.put_nowait(tuple(b[k] for k in keys))
         learner.batch_queue = q
-        await (learn_impala if algo == "IMPALA" else learn_ppo)(learner, ExecutionTimer(num_transition=B * T))
+        fn = {"IMPALA": learn_impala, "V-MPO": learn_vmpo}.get(algo, learn_ppo)
+        await fn(learner, ExecutionTimer(num_transition=B * T))
 
     asyncio.run(go())
     assert learner.idx == n and len(logs) == n and len(pubs) == n
     for i in range(n):
         np.testing.assert_allclose(logs[i][0], g["out/loss"][i], rtol=1e-4, atol=1e-7)
-        for k in ("policy-loss", "value-loss", "policy-entropy"):
+        keys_ = ("policy-loss", "value-loss", "loss-temperature", "loss-alpha") if algo == "V-MPO" else ("policy-loss", "value-loss", "policy-entropy")
+        for k in keys_:
             np.testing.assert_allclose(float(logs[i][1][k]), g["out/" + k][i], rtol=1e-4, atol=1e-7)
-        r = g[f"out/ratio/{i}"]
-        np.testing.assert_allclose(float(logs[i][1]["ratio"].mean()), r.mean(), rtol=1e-4)
+        if algo != "V-MPO":
+            r = g[f"out/ratio/{i}"]
+            np.testing.assert_allclose(float(logs[i][1]["ratio"].mean()), r.mean(), rtol=1e-4)
         # published state dict: reference keys, order, shapes and values
         ref_keys = [k[4:] for k in g if k.startswith("sd0/")]
         assert list(pubs[i].keys()) == ref_keys
