@@ -164,7 +164,35 @@ int b200rl_clip_rmsprop(float* param, float* grad, float* sq_avg, long long n,
 /* clip_grad_norm_ + Adam (bias-corrected, step = 1-based)   agents/learner.py:360-367 */
 int b200rl_clip_adam(float* param, float* grad, float* m, float* v, long long n,
                      float grad_scale, float max_norm, float lr, float beta1, float beta2,
-                     float eps, int step, float* norm_out, void* stream);
+                     float eps, int step, const float* mask /* 0/1 per entry or NULL */,
+                     float* norm_out, void* stream);
+
+/* ---- SAC heads (element-wise over (B,T); scalars as above: [0] policy, [1] value, [2] entropy term) ----------
+ * discrete SAC                                     agents/learner_module/sac/learning.py:36-143
+ *   z, q1, q2, tq1, tq2 (B,T,A); log_alpha device double; dz / dq1 / dq2 (B,T,A); td_out (B,T-1) or NULL          */
+int b200rl_sac_actor_head(const float* z, const float* q1, const float* q2, const double* log_alpha,
+                          float* dz, double* scalars, int B, int T, int A, void* stream);
+int b200rl_sac_critic_head(const float* z, const float* q1, const float* q2, const float* tq1, const float* tq2,
+                           const float* act, const float* rew, const float* is_fir, const double* log_alpha,
+                           float* dq1, float* dq2, float* td_out, double* scalars,
+                           int B, int T, int A, float gamma, void* stream);
+/* continuous SAC                 agents/learner_module/sac_continuous/learning.py:36-131, networks/models.py:199-231
+ *   head_out (B,T,2A) = [mu | raw log-std]; eps / act / logp (B,T,A); q* (B,T,1); du* (B,T,f+A) = dLoss/d[obs|act]   */
+int b200rl_sac_cont_sample(const float* head_out, const float* eps, float* act_out, float* logp_out,
+                           int B, int T, int A, void* stream);
+int b200rl_sac_cont_minq_grad(const float* q1, const float* q2, float* dq1, float* dq2, double* scalars,
+                              int B, int T, int A, void* stream);
+int b200rl_sac_cont_actor_grad(const float* head_out, const float* eps, const float* act_in, const float* logp,
+                               const float* du1, const float* du2, const double* log_alpha,
+                               float* dhead, double* scalars, int B, int T, int A, int f, void* stream);
+int b200rl_sac_cont_critic_head(const float* tq1, const float* tq2, const float* logp, const float* q1, const float* q2,
+                                const float* rew, const float* is_fir, const double* log_alpha,
+                                float* dq1, float* dq2, float* td_out, double* scalars,
+                                int B, int T, int A, float gamma, void* stream);
+/* temperature: state = {log_alpha, adam_m, adam_v} (fp64); loss = exp(log_alpha)*(scalars[2]/denominator + target_entropy);
+ * out = {loss_alpha, alpha after the step}                                            agents/learner.py:363-367          */
+int b200rl_sac_alpha_step(double* state, const double* scalars, double* out, double denominator,
+                          double target_entropy, double lr, int step, void* stream);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,7 @@ import pickle
 import numpy as np
 import torch
 
-from ..engine import OnPolicyEngine, VMPOEngine
+from ..engine import OnPolicyEngine, SACEngine, VMPOEngine
 from ..utils.utils import ExecutionTimer, HostStager, Params, Protocol, hyper_from_args, to_torch
 from .storage_module.shared_batch import SMInterFace
 from . import ppo_awrapper, v_mpo_awrapper, impala_awrapper, sac_awrapper, sac_continuous_awrapper
@@ -170,6 +170,12 @@ class LearnerBase(SMInterFace):
     async def learning_chain_impala(self):
         await self._chain("batch_queue", self.learning_impala, self.put_batch_to_batch_q)
 
+    async def learning_chain_sac(self):
+        await self._chain("batch_buffer", self.learning_sac, self.put_batch_to_buffer_q)
+
+    async def learning_chain_sac_continuous(self):
+        await self._chain("batch_buffer", self.learning_sac_continuous, self.put_batch_to_buffer_q)
+
 
 class LearnerSinglePPO(LearnerBase):
     """PPO / PPO-Continuous (reference learner.py:308-314)."""
@@ -217,3 +223,37 @@ class LearnerSingleVMPO(LearnerBase):
     def get_coef_alpha(self):
         from torch.distributions import Uniform
         return Uniform(torch.tensor(self.args.coef_alpha_below).log(), torch.tensor(self.args.coef_alpha_upper).log()).sample().exp()
+
+
+class LearnerSeperate(LearnerBase):
+    """SAC / SAC-Continuous learner (reference learner.py:351-400; the spelling is the reference's):
+    separate actor and twin critic, three Adam optimizers (fused kernels on the flat buffers),
+    `log_alpha` = log(args.alpha) in fp64 on the device, `target_entropy = action_space`, and a
+    replay-style readiness latch: once the shared buffer has filled once it stays ready."""
+
+    def __init__(self, *args, separate_target=False, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.actor = self.model.actor
+        self.critic = self.model.critic
+        self.target_critic = self.critic                      # aliasing, as in the reference (learner.py:358)
+        cont = bool(getattr(self.actor, "continuous", False))
+        self.engine = SACEngine(self.model, hyper_from_args(self.args), cont, ops=self._ops, separate_target=separate_target)
+        self.target_entropy = self.args.action_space
+        self.to_gpu.skip = {"logits", "log_prob"}
+        self._latched = False
+
+    @property
+    def log_alpha(self):
+        return self.engine.log_alpha
+
+    def is_sh_ready(self):
+        if self.sh_data_num.value >= self.args.buffer_size:
+            self._latched = True
+            self.reset_data_num()
+        return self._latched
+
+    async def put_batch_to_buffer_q(self):
+        while not self.stop_event.is_set():
+            if self.is_sh_ready():
+                await self.batch_buffer.put(self.sample_batch_from_sh_memory(sampling_method="off-policy"))
+            await asyncio.sleep(0.001)

@@ -208,3 +208,165 @@ class VMPOEngine(OnPolicyEngine):
         return {"policy-loss": v[0], "value-loss": v[1], "loss-temperature": v[2], "loss-alpha": v[3], "loss": v[4],
                 "kl-mean": v[5], "log_eta": d[0], "log_alpha": d[1], "selected": float(self.scalars[3].item()),
                 "grad-norm": float(self.grad_norm.item())}
+
+
+class SACEngine:
+    """SAC / SAC-Continuous update (reference `sac/learning.py:36-143`,
+    `sac_continuous/learning.py:36-131`, optimizers `learner.py:351-367`): actor step, temperature
+    step, twin-critic step and the Polyak update, built from the shared LSTM kernels plus the
+    element-wise SAC heads.  By default the target critic ALIASES the critic exactly as the
+    reference does (`target_critic = model.critic.to(device)` is the same object, learner.py:358;
+    SURVEY.md A.6-8), so the "target" forward is the critic forward and `soft_update` is
+    theta <- (1-tau) theta + tau theta; `separate_target=True` keeps a real copy instead."""
+
+    def __init__(self, model, hyper, continuous, ops=None, separate_target=False, tau=0.005):
+        self.ops = ops or _ops.default()
+        self.hp = dict(hyper)
+        self.cont = continuous
+        self.actor, self.twin = model.actor, model.critic
+        self.q = [self.twin.q1, self.twin.q2]
+        self.fa = self.actor.flat_parameters()
+        self.fq = self.twin.flat_joint()
+        self.La, self.Lq = self.actor._layout, self.q[0]._layout
+        dev = self.fa.device
+        self.device = dev
+        z = lambda t: torch.zeros_like(t)
+        self.ga, self.ma, self.va = z(self.fa), z(self.fa), z(self.fa)
+        self.gq, self.mq, self.vq = z(self.fq), z(self.fq), z(self.fq)
+        self.separate_target = separate_target
+        self.ftq = self.fq.clone() if separate_target else self.fq
+        self.tau = tau
+        m = self.q[0].grad_mask()
+        self.qmask = None if m is None else torch.cat([m, self.q[1].grad_mask()])
+        self.alpha_state = torch.tensor([math.log(self.hp["alpha"]), 0.0, 0.0], dtype=torch.float64, device=dev)
+        self.alpha_out = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.scalars = torch.zeros(8, dtype=torch.float64, device=dev)
+        self.norm_a, self.norm_q = torch.zeros(1, device=dev), torch.zeros(1, device=dev)
+        self.step = 0
+        self._shape = None
+        self.n_launches = 0
+        self.wgrad_variant = int(os.environ.get("B200RL_WGRAD_VARIANT", "1"))
+        self.debug = None
+
+    @property
+    def log_alpha(self):
+        return self.alpha_state[0]
+
+    def _ws(self, B, T, Ad):
+        if self._shape == (B, T, Ad):
+            return
+        dev = self.device
+        mk = lambda: dict(gates=torch.empty(B, T, H, 4, device=dev), c=torch.empty(B, T, H, device=dev), h=torch.empty(B, T, H, device=dev))
+        self.wsa, self.wsq = mk(), [mk(), mk()]
+        nch = (B * T + 31) // 32
+        self.nparts = max(1, min(_sm_count(dev, self.ops), nch))
+        self.pa = torch.zeros(self.nparts, self.La.P, device=dev)
+        self.pq = [torch.zeros(self.nparts, self.Lq.P, device=dev) for _ in range(2)]
+        self.hoa = torch.empty(B, T, self.La.NH, device=dev)
+        self.dhoa = torch.empty_like(self.hoa)
+        NQ = self.Lq.NH
+        self.Q = [torch.empty(B, T, NQ, device=dev) for _ in range(2)]
+        self.TQ = [torch.empty(B, T, NQ, device=dev) for _ in range(2)] if (self.separate_target or self.cont) else self.Q
+        self.dQ = [torch.empty(B, T, NQ, device=dev) for _ in range(2)]
+        self.td = torch.empty(B, T - 1, device=dev)
+        if self.cont:
+            Fq = self.Lq.Fin
+            self.a_pol = torch.empty(B, T, Ad, device=dev)
+            self.logp = torch.empty(B, T, Ad, device=dev)
+            self.du = [torch.empty(B, T, Fq, device=dev) for _ in range(2)]
+            self.scratch = torch.zeros(self.nparts, self.Lq.P, device=dev)
+        self._shape = (B, T, Ad)
+
+    def _net_fwd(self, L, flat, off, u, hx, cx, ws, out):
+        f = flat[off:off + L.P]
+        self.ops.lstm_fwd(L, f, u, hx, cx, ws)
+        self.ops.head_fwd(L, f, ws["h"], out)
+
+    def _net_bwd(self, L, flat, off, u, hx, cx, ws, dhead, partials, grad, du=None):
+        f = flat[off:off + L.P]
+        self.ops.lstm_bwd(L, f, dhead, ws, cx)
+        self.ops.lstm_wgrad(L, f, ws, hx, u, dhead, partials, du=du, variant=self.wgrad_variant)
+        if grad is not None:
+            self.ops.reduce_partials(partials, grad)
+
+    def update(self, batch, noise=None):
+        ops, hp, lib = self.ops, self.hp, self.ops.lib
+        from .native import ptr
+        obs = batch["obs"]
+        B, T = obs.shape[0], obs.shape[1]
+        f = obs.reshape(B, T, -1).shape[-1]
+        act = batch["act"]
+        Ad = act.shape[-1] if self.cont else self.La.NH
+        self._ws(B, T, Ad)
+        ops._chk(act, batch["rew"], batch["is_fir"], batch["hx"], batch["cx"])
+        st = ops._stream(self.device)
+        hx, cx = batch["hx"], batch["cx"]
+        uo = obs.reshape(B, T, -1)
+        La, Lq, Pq = self.La, self.Lq, self.Lq.P
+        N = float(B * (T - 1))
+        self.step += 1
+        lr, mg = hp["lr"], hp["max_grad_norm"]
+        self.scalars.zero_()
+
+        if not self.cont:
+            A = La.NH
+            self._net_fwd(La, self.fa, 0, uo, hx, cx, self.wsa, self.hoa)
+            for i in range(2):
+                self._net_fwd(Lq, self.fq, i * Pq, uo, hx, cx, self.wsq[i], self.Q[i])
+            lib.call("b200rl_sac_actor_head", ptr(self.hoa), ptr(self.Q[0]), ptr(self.Q[1]), ptr(self.alpha_state),
+                     ptr(self.dhoa), ptr(self.scalars), B, T, A, st)
+            self._net_bwd(La, self.fa, 0, uo, hx, cx, self.wsa, self.dhoa, self.pa, self.ga)
+            ops.clip_adam(self.fa, self.ga, self.ma, self.va, La.P, 1.0, mg, lr, self.step, norm_out=self.norm_a)
+            lib.call("b200rl_sac_alpha_step", ptr(self.alpha_state), ptr(self.scalars), ptr(self.alpha_out), N, float(A), lr, self.step, st)
+            self._net_fwd(La, self.fa, 0, uo, hx, cx, self.wsa, self.hoa)            # updated actor
+            if self.separate_target:
+                for i in range(2):
+                    self._net_fwd(Lq, self.ftq, i * Pq, uo, hx, cx, self.wsa, self.TQ[i])
+            lib.call("b200rl_sac_critic_head", ptr(self.hoa), ptr(self.Q[0]), ptr(self.Q[1]), ptr(self.TQ[0]), ptr(self.TQ[1]),
+                     ptr(act), ptr(batch["rew"]), ptr(batch["is_fir"]), ptr(self.alpha_state), ptr(self.dQ[0]), ptr(self.dQ[1]),
+                     ptr(self.td), ptr(self.scalars), B, T, A, hp["gamma"], st)
+            for i in range(2):
+                self._net_bwd(Lq, self.fq, i * Pq, uo, hx, cx, self.wsq[i], self.dQ[i], self.pq[i], self.gq[i * Pq:(i + 1) * Pq])
+            pol_den = N
+        else:
+            A = Ad
+            eps1, eps2 = noise if noise is not None else (torch.randn(B, T, A, device=self.device), torch.randn(B, T, A, device=self.device))
+            self._net_fwd(La, self.fa, 0, uo, hx, cx, self.wsa, self.hoa)
+            lib.call("b200rl_sac_cont_sample", ptr(self.hoa), ptr(eps1), ptr(self.a_pol), ptr(self.logp), B, T, A, st)
+            u1 = torch.cat([uo, self.a_pol], -1)
+            for i in range(2):
+                self._net_fwd(Lq, self.fq, i * Pq, u1, hx, cx, self.wsq[i], self.Q[i])
+            lib.call("b200rl_sac_cont_minq_grad", ptr(self.Q[0]), ptr(self.Q[1]), ptr(self.dQ[0]), ptr(self.dQ[1]), ptr(self.scalars), B, T, A, st)
+            for i in range(2):                                                          # dQ/da: critic backward to its input only
+                self._net_bwd(Lq, self.fq, i * Pq, u1, hx, cx, self.wsq[i], self.dQ[i], self.scratch, None, du=self.du[i])
+            lib.call("b200rl_sac_cont_actor_grad", ptr(self.hoa), ptr(eps1), ptr(self.a_pol), ptr(self.logp), ptr(self.du[0]), ptr(self.du[1]),
+                     ptr(self.alpha_state), ptr(self.dhoa), ptr(self.scalars), B, T, A, f, st)
+            self._net_bwd(La, self.fa, 0, uo, hx, cx, self.wsa, self.dhoa, self.pa, self.ga)
+            ops.clip_adam(self.fa, self.ga, self.ma, self.va, La.P, 1.0, mg, lr, self.step, norm_out=self.norm_a)
+            lib.call("b200rl_sac_alpha_step", ptr(self.alpha_state), ptr(self.scalars), ptr(self.alpha_out), N * A, float(A), lr, self.step, st)
+            self._net_fwd(La, self.fa, 0, uo, hx, cx, self.wsa, self.hoa)            # updated actor, fresh noise
+            lib.call("b200rl_sac_cont_sample", ptr(self.hoa), ptr(eps2), ptr(self.a_pol), ptr(self.logp), B, T, A, st)
+            u2 = torch.cat([uo, self.a_pol], -1)
+            for i in range(2):
+                self._net_fwd(Lq, self.ftq, i * Pq, u2, hx, cx, self.wsq[i], self.TQ[i])
+            u3 = torch.cat([uo, act], -1)
+            for i in range(2):
+                self._net_fwd(Lq, self.fq, i * Pq, u3, hx, cx, self.wsq[i], self.Q[i])
+            lib.call("b200rl_sac_cont_critic_head", ptr(self.TQ[0]), ptr(self.TQ[1]), ptr(self.logp), ptr(self.Q[0]), ptr(self.Q[1]),
+                     ptr(batch["rew"]), ptr(batch["is_fir"]), ptr(self.alpha_state), ptr(self.dQ[0]), ptr(self.dQ[1]), ptr(self.td),
+                     ptr(self.scalars), B, T, A, hp["gamma"], st)
+            for i in range(2):
+                self._net_bwd(Lq, self.fq, i * Pq, u3, hx, cx, self.wsq[i], self.dQ[i], self.pq[i], self.gq[i * Pq:(i + 1) * Pq])
+            pol_den = N * A
+        ops.clip_adam(self.fq, self.gq, self.mq, self.vq, 2 * Pq, 1.0, mg, lr, self.step, norm_out=self.norm_q, mask=self.qmask)
+        ops.soft_update_flat(self.fq, self.ftq, self.tau)
+        self._pol_den, self._N = pol_den, N
+        self.n_launches += 1
+
+    def losses(self):
+        s = self.scalars.cpu().tolist()
+        ao = self.alpha_out.cpu().tolist()
+        pol, val = s[0] / self._pol_den, s[1] / self._N
+        return {"policy-loss": pol, "value-loss": val, "loss_alpha": ao[0], "alpha": ao[1],
+                "loss": self.hp["policy_loss_coef"] * pol + self.hp["value_loss_coef"] * val,
+                "log_alpha": float(self.alpha_state[0].item())}

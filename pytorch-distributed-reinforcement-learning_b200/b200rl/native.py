@@ -37,7 +37,14 @@ SIGNATURES = {
     "b200rl_vmpo_grad": [_P] * 9 + [_I, _I, _I, _F, C.c_double, _P],
     "b200rl_vmpo_dual_step": [_P] * 4 + [C.c_double] * 9 + [_P],
     "b200rl_clip_rmsprop": [_P, _P, _P, _L] + [_F] * 5 + [_P, _P],
-    "b200rl_clip_adam": [_P, _P, _P, _P, _L] + [_F] * 6 + [_I, _P, _P],
+    "b200rl_clip_adam": [_P, _P, _P, _P, _L] + [_F] * 6 + [_I, _P, _P, _P],
+    "b200rl_sac_actor_head": [_P] * 6 + [_I, _I, _I, _P],
+    "b200rl_sac_critic_head": [_P] * 13 + [_I, _I, _I, _F, _P],
+    "b200rl_sac_cont_sample": [_P] * 4 + [_I, _I, _I, _P],
+    "b200rl_sac_cont_minq_grad": [_P] * 5 + [_I, _I, _I, _P],
+    "b200rl_sac_cont_actor_grad": [_P] * 9 + [_I, _I, _I, _I, _P],
+    "b200rl_sac_cont_critic_head": [_P] * 12 + [_I, _I, _I, _F, _P],
+    "b200rl_sac_alpha_step": [_P, _P, _P, C.c_double, C.c_double, C.c_double, _I, _P],
 }
 _RESTYPE = {"b200rl_last_error": C.c_char_p}
 

@@ -53,11 +53,12 @@ class _FlatNet(nn.Module):
         lin = self.body[0]
         return [(lin.weight, 0, 0)], [(lin.bias, 0)]
 
-    def flatten_parameters(self):
-        """(Re)home all parameters into one flat buffer on their current device."""
+    def flatten_parameters(self, into=None):
+        """(Re)home all parameters into one flat buffer on their current device (`into`: a
+        preallocated zeroed slice, used by the twin critic to keep q1|q2 contiguous)."""
         L = self.layout()
         dev = self.body[0].weight.device
-        flat = torch.zeros(L.P, device=dev, dtype=torch.float32)
+        flat = torch.zeros(L.P, device=dev, dtype=torch.float32) if into is None else into
         Wt = L.view(flat, "Wt").view(H, L.Fin)
         bt = L.view(flat, "bt")
         wblocks, bblocks = self._torso_blocks()
@@ -227,3 +228,204 @@ class MlpLSTMSingleContinuous(nn.Module):
         super().__init__()
         self.actor = MlpLSTMContinuous(*args, **kwargs)
         self.critic = self.actor
+
+
+# ================================================================================ SAC networks
+class MlpLSTMActor(_FlatNet):
+    """Discrete SAC actor: softmax policy head only (reference models.py:121-159)."""
+
+    def after_torso(self):
+        self.lstmcell = nn.LSTMCell(self.hidden_size, self.hidden_size)
+        self.logits = nn.Linear(self.hidden_size, self.n_outputs)
+        self.CT = Categorical
+
+    def head_modules(self):
+        return [self.logits]
+
+    def get_dist(self, x):
+        return self.CT(torch.softmax(self.logits(x), dim=-1))
+
+    def act(self, obs, lstm_hxs):
+        with torch.no_grad():
+            hx, cx = self._cell(obs, lstm_hxs)
+            dist = self.get_dist(hx)
+            action = dist.sample().detach()
+        return action, dist.logits.detach(), dist.log_prob(action).detach(), (hx.detach(), cx.detach())
+
+    def forward(self, obs, lstm_hxs, ops=None):
+        """-> (probs (B,T,A), log(probs + 1e-8*[probs==0]) (B,T,A))"""
+        B, T = obs.shape[0], obs.shape[1]
+        z, _ = self.run_lstm(obs.reshape(B, T, -1), lstm_hxs, ops)
+        probs = torch.softmax(z, -1)
+        return probs, torch.log(probs + (probs == 0.0).float() * 1e-8)
+
+
+class MlpLSTMActorContinuous(_FlatNet):
+    """tanh-Gaussian SAC actor: mu and clamped log-std heads (reference models.py:162-231)."""
+
+    continuous = True
+
+    def after_torso(self):
+        self.lstmcell = nn.LSTMCell(self.hidden_size, self.hidden_size)
+        self.logits = nn.Linear(self.hidden_size, self.n_outputs)
+        self.logits_log_std = nn.Linear(self.hidden_size, self.n_outputs)
+        self.NM = Normal
+
+    def head_modules(self):
+        return [self.logits, self.logits_log_std]
+
+    def get_dist(self, x):
+        return self.NM(self.logits(x), torch.clamp(self.logits_log_std(x), min=-20, max=2).exp())
+
+    def action_log_prob(self, x):
+        dist = self.get_dist(x)
+        x_t = dist.rsample()
+        action = torch.tanh(x_t)
+        log_prob = dist.log_prob(x_t) - torch.log(1 - action.pow(2) + 1e-7)
+        return dist, action, log_prob
+
+    def act(self, obs, lstm_hxs):
+        with torch.no_grad():
+            hx, cx = self._cell(obs, lstm_hxs)
+            _, action, log_prob = self.action_log_prob(hx)
+        return action.detach(), torch.zeros(action.shape), log_prob.detach(), (hx.detach(), cx.detach())
+
+
+class MlpLSTMCritic(_FlatNet):
+    """Discrete Q network, Q(s, .) (reference models.py:234-270).  The reference constructs the
+    torso twice (`MlpLSTMBase.__init__` then the override, models.py:239-242); the same RNG draws
+    are consumed here so seeded weights agree."""
+
+    def __init__(self, f, n_outputs, sequence_length, hidden_size):
+        super().__init__(f, n_outputs, sequence_length, hidden_size)
+        fresh = nn.Linear(f, hidden_size)
+        with torch.no_grad():
+            self.body[0].weight.copy_(fresh.weight)
+            self.body[0].bias.copy_(fresh.bias)
+
+    def after_torso(self):
+        self.lstmcell = nn.LSTMCell(self.hidden_size, self.hidden_size)
+        self.q_value = nn.Linear(self.hidden_size, self.n_outputs)
+
+    def head_modules(self):
+        return [self.q_value]
+
+    def forward(self, obs, lstm_hxs, ops=None):
+        B, T = obs.shape[0], obs.shape[1]
+        q, _ = self.run_lstm(obs.reshape(B, T, -1), lstm_hxs, ops)
+        return q
+
+
+class MlpLSTMCriticContinuous(_FlatNet):
+    """Q(s, a): obs -> H/2 and act -> H/2 encoders, concatenated, LSTM, scalar head
+    (reference models.py:273-322).  Both encoders live in ONE dense torso matrix Wt (H, f + act_dim)
+    with zero off-diagonal blocks, so the shared LSTM kernels apply; `grad_mask()` keeps the zero
+    blocks out of the optimizer.  `act_dim` generalises the reference's hard-coded 1 (models.py:290,
+    SURVEY.md 0.1); `n_outputs` is the action dimension as in the reference constructor."""
+
+    def __init__(self, f, n_outputs, sequence_length, hidden_size, act_dim=1):
+        self.act_dim = act_dim
+        super().__init__(f, n_outputs, sequence_length, hidden_size)
+        fresh = nn.Linear(f, hidden_size // 2)                      # models.py:278-284 (second construction)
+        with torch.no_grad():
+            self.body[0].weight.copy_(fresh.weight)
+            self.body[0].bias.copy_(fresh.bias)
+
+    def after_torso(self):
+        # Base.__init__ built body as Linear(f, H) (RNG draw kept for parity); replace by the H/2 encoder
+        with torch.random.fork_rng():                  # placeholder values; the real draw happens in __init__, in reference order
+            self.body = nn.Sequential(nn.Linear(self.input_size, self.hidden_size // 2), nn.ReLU())
+        self.lstmcell = nn.LSTMCell(self.hidden_size, self.hidden_size)
+        self.encode_action = nn.Sequential(nn.Linear(self.act_dim, self.hidden_size // 2), nn.ReLU())
+        self.q_value = nn.Linear(self.hidden_size, 1)
+
+    @property
+    def torso_in(self):
+        return self.input_size + self.act_dim
+
+    def head_modules(self):
+        return [self.q_value]
+
+    def _torso_blocks(self):
+        half = self.hidden_size // 2
+        return ([(self.body[0].weight, 0, 0), (self.encode_action[0].weight, half, self.input_size)],
+                [(self.body[0].bias, 0), (self.encode_action[0].bias, half)])
+
+    def grad_mask(self):
+        L = self._layout
+        m = torch.ones(L.P, device=self.flat_parameters().device)
+        Wt = L.view(m, "Wt").view(H, L.Fin)
+        half = self.hidden_size // 2
+        Wt[:half, self.input_size:] = 0
+        Wt[half:, :self.input_size] = 0
+        m[L.n:] = 0
+        return m
+
+    def forward(self, obs, act, lstm_hxs, ops=None):
+        B, T = obs.shape[0], obs.shape[1]
+        u = torch.cat([obs.reshape(B, T, -1), act.reshape(B, T, -1)], -1)
+        q, _ = self.run_lstm(u, lstm_hxs, ops)
+        return q
+
+
+class _Twin(nn.Module):
+    """q1 and q2 side by side in ONE flat buffer [q1 | q2], so `clip_grad_norm_(critic.parameters())`
+    (a joint norm over both networks, sac/learning.py:117-119) and Adam are one launch."""
+
+    def forward(self, *args, **kwargs):
+        return self.q1(*args, **kwargs), self.q2(*args, **kwargs)
+
+    def flat_joint(self):
+        P = self.q1._layout.P
+        f1, f2 = self.q1.flat_parameters(), self.q2.flat_parameters()
+        joint = getattr(self, "_joint", None)
+        if joint is None or f1.data_ptr() != joint.data_ptr() or f2.data_ptr() != joint.data_ptr() + 4 * P:
+            joint = torch.zeros(2 * P, device=f1.device, dtype=torch.float32)
+            self.q1.flatten_parameters(into=joint[:P])
+            self.q2.flatten_parameters(into=joint[P:])
+            self._joint = joint
+        return joint
+
+    def flat_buffers(self):
+        return [self.flat_joint()]
+
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st.pop("_joint", None)
+        return st
+
+
+class MlpLSTMDoubleCritic(_Twin):
+    """(reference models.py:335-342)"""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        self.q1 = MlpLSTMCritic(*args, **kwargs)
+        self.q2 = MlpLSTMCritic(*args, **kwargs)
+
+
+class MlpLSTMDoubleCriticContinuous(_Twin):
+    """(reference models.py:325-332)"""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        self.q1 = MlpLSTMCriticContinuous(*args, **kwargs)
+        self.q2 = MlpLSTMCriticContinuous(*args, **kwargs)
+
+
+class MlpLSTMSeperate(nn.Module):
+    """Separate actor and twin-critic torsos (reference models.py:363-369; the spelling is the reference's)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        self.actor = MlpLSTMActor(*args, **kwargs)
+        self.critic = MlpLSTMDoubleCritic(*args, **kwargs)
+
+
+class MlpLSTMSeperateContinuous(nn.Module):
+    """(reference models.py:372-378).  `act_dim` (default 1 = the reference's domain) widens the action."""
+
+    def __init__(self, f, n_outputs, sequence_length, hidden_size, act_dim=1):
+        super().__init__()
+        self.actor = MlpLSTMActorContinuous(f, n_outputs, sequence_length, hidden_size)
+        self.critic = MlpLSTMDoubleCriticContinuous(f, n_outputs, sequence_length, hidden_size, act_dim=act_dim)

@@ -195,10 +195,10 @@ def _clip_rmsprop(self, param, grad, sq, n, grad_scale, max_norm, lr, alpha=0.99
                   ptr(norm_out), self._stream(dev))
 
 
-def _clip_adam(self, param, grad, m, v, n, grad_scale, max_norm, lr, step, b1=0.9, b2=0.999, eps=1e-8, norm_out=None):
-    dev = self._chk(param, grad, m, v, norm_out)
+def _clip_adam(self, param, grad, m, v, n, grad_scale, max_norm, lr, step, b1=0.9, b2=0.999, eps=1e-8, norm_out=None, mask=None):
+    dev = self._chk(param, grad, m, v, norm_out, mask)
     self.lib.call("b200rl_clip_adam", ptr(param), ptr(grad), ptr(m), ptr(v), n, grad_scale, max_norm, lr, b1, b2, eps,
-                  step, ptr(norm_out), self._stream(dev))
+                  step, ptr(mask), ptr(norm_out), self._stream(dev))
 
 
 for _n, _f in (("lstm_fwd", _lstm_fwd), ("head_fwd", _head_fwd), ("lstm_bwd", _lstm_bwd), ("lstm_wgrad", _lstm_wgrad),

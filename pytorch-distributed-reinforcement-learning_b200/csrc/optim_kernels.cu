@@ -15,12 +15,12 @@ namespace b200rl {
 constexpr int kOptThreads = 1024;
 
 __device__ __forceinline__ float grad_norm_and_coef(const float* grad, long long n, float grad_scale,
-                                                    float max_norm, float* norm_out) {
+                                                    float max_norm, float* norm_out, const float* mask = nullptr) {
     __shared__ double scratch[32];
     __shared__ float coef_s;
     double s = 0.0;
     for (long long i = threadIdx.x; i < n; i += kOptThreads) {
-        const double g = (double)(grad[i] * grad_scale);
+        const double g = (double)(grad[i] * grad_scale * (mask ? mask[i] : 1.0f));
         s += g * g;
     }
     const double tot = block_sum(s, scratch);
@@ -52,14 +52,14 @@ clip_rmsprop_kernel(float* __restrict__ param, float* __restrict__ grad, float* 
 __global__ void __launch_bounds__(kOptThreads)
 clip_adam_kernel(float* __restrict__ param, float* __restrict__ grad, float* __restrict__ m,
                  float* __restrict__ v, long long n, float grad_scale, float max_norm, float lr,
-                 float beta1, float beta2, float eps, int step, float* norm_out) {
-    const float coef = grad_norm_and_coef(grad, n, grad_scale, max_norm, norm_out);
+                 float beta1, float beta2, float eps, int step, float* norm_out, const float* __restrict__ mask) {
+    const float coef = grad_norm_and_coef(grad, n, grad_scale, max_norm, norm_out, mask);
     const double bc1 = 1.0 - pow((double)beta1, (double)step);
     const double bc2 = 1.0 - pow((double)beta2, (double)step);
     const float step_size = (float)((double)lr / bc1);
     const float rsq_bc2 = (float)(1.0 / sqrt(bc2));
     for (long long i = threadIdx.x; i < n; i += kOptThreads) {
-        const float g = grad[i] * grad_scale * coef;
+        const float g = grad[i] * grad_scale * coef * (mask ? mask[i] : 1.0f);
         grad[i] = g;
         const float mi = m[i] * beta1 + (1.0f - beta1) * g;
         const float vi = v[i] * beta2 + (1.0f - beta2) * g * g;
@@ -82,8 +82,8 @@ extern "C" int b200rl_clip_rmsprop(float* param, float* grad, float* sq_avg, lon
 
 extern "C" int b200rl_clip_adam(float* param, float* grad, float* m, float* v, long long n,
                                 float grad_scale, float max_norm, float lr, float beta1, float beta2,
-                                float eps, int step, float* norm_out, void* stream) {
+                                float eps, int step, const float* mask, float* norm_out, void* stream) {
     B200RL_REQUIRE(n >= 1 && step >= 1, "clip_adam: n=%lld step=%d", n, step);
-    B200RL_LAUNCH(clip_adam_kernel, 1, kOptThreads, 0, stream, param, grad, m, v, n, grad_scale, max_norm, lr, beta1, beta2, eps, step, norm_out);
+    B200RL_LAUNCH(clip_adam_kernel, 1, kOptThreads, 0, stream, param, grad, m, v, n, grad_scale, max_norm, lr, beta1, beta2, eps, step, norm_out, mask);
     return check_launch("clip_adam");
 }

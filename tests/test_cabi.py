@@ -17,7 +17,7 @@ def _declared():
 def test_header_symbols_are_bound_and_exported():
     from b200rl import build, native
     names = _declared()
-    assert len(names) >= 16
+    assert len(names) >= 27
     assert set(names) == set(native.SIGNATURES), "ctypes table and include/b200rl.h disagree"
     lib = native.Lib(build.build())
     assert lib.missing == []

@@ -162,3 +162,59 @@ def test_vmpo_selection_properties_at_cfg4_shard_shape():
     Z = float(eng.scalars[7].item())
     direct = float(torch.where(sel, (u - float(eng.scalars[6].item())).exp(), torch.zeros_like(u)).sum())
     assert abs(Z - direct) / direct < 1e-5
+
+
+@pytest.mark.parametrize("name,cont", [("sac_small", False), ("sac_continuous_small", True)])
+def test_sac_update_matches_reference(backend, name, cont):
+    from b200rl.engine import SACEngine
+    from b200rl.networks import models as M
+    ops, dev = backend
+    g = load_golden(name)
+    B, T, f, A, H, n, _ = [int(x) for x in g["meta"]]
+    model = (M.MlpLSTMSeperateContinuous if cont else M.MlpLSTMSeperate)(f, A, T, H)
+    model.actor.load_state_dict(golden_sd(g, "actor0"))
+    model.critic.load_state_dict(golden_sd(g, "critic0"))
+    model = model.to(dev)
+    eng = SACEngine(model, oracle.DEFAULT_HYPER, cont, ops=ops)
+    for i in range(n):
+        noise = [torch.from_numpy(g[f"noise/{i}/{j}"]).to(dev) for j in range(2)] if cont else None
+        eng.update(golden_batch(g, i, dev), noise=noise)
+        L = eng.losses()
+        for k in ("policy-loss", "value-loss", "loss_alpha", "alpha"):
+            _close(L[k], g["out/" + k][i], rtol=1e-4, atol=1e-7, what=f"{k}[{i}]")
+        _close(L["loss"], g["out/loss"][i], rtol=1e-4, atol=1e-7, what="loss")
+        _close(L["log_alpha"], g["out/log_alpha"][i], rtol=1e-6, atol=1e-9, what="log_alpha")
+        pa = torch.cat([v.reshape(-1) for v in model.actor.state_dict().values()]).cpu()
+        pc = torch.cat([v.reshape(-1) for v in model.critic.state_dict().values()]).cpu()
+        _close(pa, g[f"out/actor_params/{i}"], what=f"actor params[{i}]", **PARAMS)
+        _close(pc, g[f"out/critic_params/{i}"], what=f"critic params[{i}]", **PARAMS)
+
+
+def test_sac_continuous_generalised_action_width(backend):
+    """BASELINE config 5 shape (obs=17, act=6): outside the reference's domain (its critic hard-codes a
+    1-wide action, networks/models.py:290); the oracle is the reference math with that single generalisation,
+    including the `.sum(-1)` target quirk."""
+    from collections import OrderedDict
+    from b200rl.engine import SACEngine
+    from b200rl.networks import models as M
+    from b200rl.synth import make_rollouts
+    ops, dev = backend
+    B, T, f, A = (16, 5, 17, 6)
+    torch.manual_seed(5)
+    model = M.MlpLSTMSeperateContinuous(f, A, T, 64, act_dim=A)
+    pa = OrderedDict((k, v.clone()) for k, v in model.actor.state_dict().items())
+    pc = OrderedDict((k, v.clone()) for k, v in model.critic.state_dict().items())
+    model = model.to(dev)
+    eng = SACEngine(model, oracle.DEFAULT_HYPER, True, ops=ops)
+    orc = oracle.OracleLearner("SAC-Continuous", {"actor": pa, "critic": pc})
+    g = torch.Generator().manual_seed(9)
+    for i in range(2):
+        batch = make_rollouts(B, T, f, A, continuous=True, batch_index=i, act_dim=A)
+        noise = [torch.randn(B, T, A, generator=g), torch.randn(B, T, A, generator=g)]
+        r = orc.update(batch, noise=noise)
+        eng.update({k: v.to(dev) for k, v in batch.items()}, noise=[e.to(dev) for e in noise])
+        L = eng.losses()
+        for k in ("policy-loss", "value-loss", "loss_alpha", "alpha"):
+            _close(L[k], float(r[k]), rtol=1e-4, atol=1e-7, what=f"{k}[{i}]")
+        _close(torch.cat([v.reshape(-1) for v in model.actor.state_dict().values()]).cpu(), r["actor_params"], what="actor params", **PARAMS)
+        _close(torch.cat([v.reshape(-1) for v in model.critic.state_dict().values()]).cpu(), r["critic_params"], what="critic params", **PARAMS)
