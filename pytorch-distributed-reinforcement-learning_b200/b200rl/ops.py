@@ -2,12 +2,17 @@
 
 torch is used here only for device memory and the current CUDA stream.
 """
+import os
+
 import torch
 
 from . import native
 from .native import ptr
 
 H = 64
+# kernel variants (env-overridable for A/B measurements): forward 1 = 16-warp split-K, 0 = 8-warp
+FWD_VARIANT = int(os.environ.get("B200RL_FWD_VARIANT", "1"))
+BWD_VARIANT = int(os.environ.get("B200RL_BWD_VARIANT", "0"))
 
 
 class Ops:
@@ -122,14 +127,15 @@ class NetLayout:
         return flat[o:o + n]
 
 
-def _lstm_fwd(self, L, flat, u, hx0, cx0, ws):
+def _lstm_fwd(self, L, flat, u, hx0, cx0, ws, variant=None):
     """ws: workspace dict with gates (B,T,H,4), c, h (B,T,H)."""
     dev = self._chk(flat, u, hx0, cx0, ws["gates"], ws["c"], ws["h"])
     B, T, Fin = u.shape
     assert Fin == L.Fin
     v = lambda k: ptr(flat) + 4 * L.off[k][0]
     self.lib.call("b200rl_lstm_fwd", ptr(u), ptr(hx0), ptr(cx0), v("Wt"), v("bt"), v("W_ih"), v("W_hh"),
-                  v("b_ih"), v("b_hh"), ptr(ws["gates"]), ptr(ws["c"]), ptr(ws["h"]), B, T, Fin, 0, self._stream(dev))
+                  v("b_ih"), v("b_hh"), ptr(ws["gates"]), ptr(ws["c"]), ptr(ws["h"]), B, T, Fin,
+                  FWD_VARIANT if variant is None else variant, self._stream(dev))
 
 
 def _head_fwd(self, L, flat, h, head_out):

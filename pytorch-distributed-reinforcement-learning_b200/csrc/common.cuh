@@ -68,6 +68,28 @@ __device__ __forceinline__ float smooth_l1_grad(float d) { return fabsf(d) < 1.0
 
 }  // namespace b200rl
 
+// ---- packed fp32 pairs: Blackwell issues two independent FMAs with one FFMA2 (fma.rn.f32x2) at the
+// same FLOP rate as two FFMAs (tools/ffma2_probe.cu: 126 FMA/clk/SM either way), halving the issue
+// slots of FFMA-bound inner loops.  Host twin: a plain struct.
+namespace b200rl {
+#ifdef B200RL_EMUL
+struct f2 { float x, y; };
+inline f2 f2_make(float a, float b) { return f2{a, b}; }
+inline void f2_fma(f2& d, f2 a, f2 b) { d.x = fmaf(a.x, b.x, d.x); d.y = fmaf(a.y, b.y, d.y); }
+inline float f2_lo(f2 v) { return v.x; }
+inline float f2_hi(f2 v) { return v.y; }
+inline void f2_ld2(const float* p, f2& a, f2& b) { a = f2{p[0], p[1]}; b = f2{p[2], p[3]}; }
+#else
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 f2_make(float a, float b) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void f2_fma(f2& d, f2 a, f2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b)); }
+__device__ __forceinline__ float f2_lo(f2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+__device__ __forceinline__ float f2_hi(f2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+// 16-byte load of four floats as two packed pairs
+__device__ __forceinline__ void f2_ld2(const float* p, f2& a, f2& b) { const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p); a = v.x; b = v.y; }
+#endif
+}  // namespace b200rl
+
 // Error plumbing shared by the C-ABI entry points.
 namespace b200rl {
 int set_error(const char* fmt, ...);

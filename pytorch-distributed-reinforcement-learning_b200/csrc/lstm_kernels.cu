@@ -165,30 +165,33 @@ lstm_fwd_kernel(const float* __restrict__ u, const float* __restrict__ hx0, cons
                     }
                 }
             }
-            // (b) gates = bias + [x_t | h_{t-1}] . Wp       (32 x 256 x 128 per CTA)
-            float acc[4][8];
+            // (b) gates = bias + [x_t | h_{t-1}] . Wp       (32 x 256 x 128 per CTA), packed FFMA2:
+            //     accumulator pairs run along the gate index, the activation is broadcast into both halves
+            f2 acc2[4][4];
             {
-                float4 b0v = ld4(bsum + m.j0 * 4), b1v = ld4(bsum + m.j1 * 4);
+                f2 b00, b01, b10, b11;
+                f2_ld2(bsum + m.j0 * 4, b00, b01); f2_ld2(bsum + m.j1 * 4, b10, b11);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    acc[i][0] = b0v.x; acc[i][1] = b0v.y; acc[i][2] = b0v.z; acc[i][3] = b0v.w;
-                    acc[i][4] = b1v.x; acc[i][5] = b1v.y; acc[i][6] = b1v.z; acc[i][7] = b1v.w;
-                }
+                for (int i = 0; i < 4; ++i) { acc2[i][0] = b00; acc2[i][1] = b01; acc2[i][2] = b10; acc2[i][3] = b11; }
             }
 #pragma unroll 4
             for (int k = 0; k < KC; ++k) {
-                float4 a = ld4(Ac + k * TM + m.r0);
-                float4 w0 = ld4(Wp + k * G + m.j0 * 4);
-                float4 w1 = ld4(Wp + k * G + m.j1 * 4);
-                const float av[4] = {a.x, a.y, a.z, a.w};
+                const float4 a = ld4(Ac + k * TM + m.r0);
+                f2 w00, w01, w10, w11;
+                f2_ld2(Wp + k * G + m.j0 * 4, w00, w01);
+                f2_ld2(Wp + k * G + m.j1 * 4, w10, w11);
+                const f2 av[4] = {f2_make(a.x, a.x), f2_make(a.y, a.y), f2_make(a.z, a.z), f2_make(a.w, a.w)};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    acc[i][0] = fmaf(av[i], w0.x, acc[i][0]); acc[i][1] = fmaf(av[i], w0.y, acc[i][1]);
-                    acc[i][2] = fmaf(av[i], w0.z, acc[i][2]); acc[i][3] = fmaf(av[i], w0.w, acc[i][3]);
-                    acc[i][4] = fmaf(av[i], w1.x, acc[i][4]); acc[i][5] = fmaf(av[i], w1.y, acc[i][5]);
-                    acc[i][6] = fmaf(av[i], w1.z, acc[i][6]); acc[i][7] = fmaf(av[i], w1.w, acc[i][7]);
+                    f2_fma(acc2[i][0], av[i], w00); f2_fma(acc2[i][1], av[i], w01);
+                    f2_fma(acc2[i][2], av[i], w10); f2_fma(acc2[i][3], av[i], w11);
                 }
             }
+            float acc[4][8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { acc[i][2 * c] = f2_lo(acc2[i][c]); acc[i][2 * c + 1] = f2_hi(acc2[i][c]); }
             // (c) cell update, save activations, publish h_t for the next step
             float hn[4][2];
 #pragma unroll
@@ -233,6 +236,180 @@ lstm_fwd_kernel(const float* __restrict__ u, const float* __restrict__ hx0, cons
 #pragma unroll
                 for (int e = 0; e < (TM * MAXF + NT - 1) / NT; ++e) {
                     int i = e * NT + tid;
+                    if (i < nU) Ud[i] = upre[e];
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------ forward, 16-warp variant
+// Same tiling, but 512 threads: warp group 0 multiplies the x half of K (k < 64), group 1 the
+// h half; each thread then hands the partial sums of the unit it does NOT own to its partner
+// through shared memory and finishes the 4 cells (4 rows x 1 unit) it owns.  Four warps per
+// scheduler instead of two hide the LDS latency the 8-warp kernel stalls on (ncu r1a/r1c:
+// short-scoreboard, 52 % of the FP32 pipe).
+constexpr int NT16 = 512;
+static inline size_t fwd16_smem_bytes(int Fin) {
+    return fwd_smem_bytes(Fin) + sizeof(float4) * (size_t)(4 * 2 * 256);
+}
+
+__global__ void __launch_bounds__(NT16, 1)
+lstm_fwd16_kernel(const float* __restrict__ u, const float* __restrict__ hx0, const float* __restrict__ cx0,
+                  const float* __restrict__ Wt, const float* __restrict__ bt,
+                  const float* __restrict__ W_ih, const float* __restrict__ W_hh,
+                  const float* __restrict__ b_ih, const float* __restrict__ b_hh,
+                  float* __restrict__ gates, float* __restrict__ c_out, float* __restrict__ h_out,
+                  int B, int T, int Fin) {
+    B200RL_DYN_SMEM(float, smem);
+    float* Wp = smem;
+    float* AT = Wp + KC * G;
+    float* bsum = AT + 2 * KC * TM;
+    float* bts = bsum + G;
+    float* WtS = bts + H;
+    float* U = WtS + Fin * H;
+    float4* X = reinterpret_cast<float4*>(U + 2 * TM * Fin + ((4 - ((2 * TM * Fin) & 3)) & 3));   // 16-byte aligned exchange buffer
+    const int tid = threadIdx.x, grp = tid >> 8, t8 = tid & 255;
+    const int lane = tid & 31, warp8 = t8 >> 5;
+    const int r0 = ((warp8 & 1) * 4 + (lane >> 3)) * 4;
+    const int j0 = (warp8 >> 1) * 8 + (lane & 7), j1 = j0 + 32;
+    const int jown = grp ? j1 : j0;
+
+    if (tid < G) {
+        const int n = tid, g = n >> 6, j = n & 63, pc = j * 4 + g;
+        for (int k4 = 0; k4 < H; k4 += 4) {
+            float4 a = ld4(W_ih + (size_t)n * H + k4);
+            float4 b = ld4(W_hh + (size_t)n * H + k4);
+            Wp[(k4 + 0) * G + pc] = a.x; Wp[(k4 + 1) * G + pc] = a.y;
+            Wp[(k4 + 2) * G + pc] = a.z; Wp[(k4 + 3) * G + pc] = a.w;
+            Wp[(H + k4 + 0) * G + pc] = b.x; Wp[(H + k4 + 1) * G + pc] = b.y;
+            Wp[(H + k4 + 2) * G + pc] = b.z; Wp[(H + k4 + 3) * G + pc] = b.w;
+        }
+        bsum[pc] = b_ih[n] + b_hh[n];
+    }
+    if (tid < H) bts[tid] = bt[tid];
+    for (int i = tid; i < Fin * H; i += NT16) { int q = i / H, jj = i % H; WtS[i] = Wt[jj * Fin + q]; }
+
+    const int ntiles = (B + TM - 1) / TM;
+    const int nU = TM * Fin;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int b0 = tile * TM;
+        __syncthreads();
+        int brow[4]; bool bok[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { int b = b0 + r0 + i; bok[i] = b < B; brow[i] = bok[i] ? b : B - 1; }
+        float cst[4];
+        {
+            float hv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { cst[i] = cx0[(size_t)brow[i] * H + jown]; hv[i] = hx0[(size_t)brow[i] * H + jown]; }
+            st4(AT + (H + jown) * TM + r0, make_float4(hv[0], hv[1], hv[2], hv[3]));
+        }
+        for (int i = tid; i < nU; i += NT16) {
+            int r = i / Fin, q = i % Fin; int b = b0 + r < B ? b0 + r : B - 1;
+            U[i] = u[((size_t)b * T + 0) * Fin + q];
+            if (T > 1) U[nU + i] = u[((size_t)b * T + 1) * Fin + q];
+        }
+        __syncthreads();
+        {
+            float x[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float a = bts[jown];
+                for (int q = 0; q < Fin; ++q) a = fmaf(U[(r0 + i) * Fin + q], WtS[q * H + jown], a);
+                x[i] = fmaxf(a, 0.f);
+            }
+            st4(AT + jown * TM + r0, make_float4(x[0], x[1], x[2], x[3]));
+        }
+        __syncthreads();
+
+        for (int t = 0; t < T; ++t) {
+            const float* Ac = AT + (t & 1) * KC * TM;
+            float* An = AT + ((t + 1) & 1) * KC * TM;
+            float upre[(TM * MAXF + NT16 - 1) / NT16];
+            const bool do_pre = t + 2 < T;
+            if (do_pre) {
+#pragma unroll
+                for (int e = 0; e < (TM * MAXF + NT16 - 1) / NT16; ++e) {
+                    int i = e * NT16 + tid;
+                    if (i < nU) {
+                        int r = i / Fin, q = i % Fin; int b = b0 + r < B ? b0 + r : B - 1;
+                        upre[e] = __ldg(u + ((size_t)b * T + (t + 2)) * Fin + q);
+                    }
+                }
+            }
+            float acc[4][8];
+            {
+                float4 b0v = make_float4(0.f, 0.f, 0.f, 0.f), b1v = b0v;
+                if (grp == 0) { b0v = ld4(bsum + j0 * 4); b1v = ld4(bsum + j1 * 4); }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    acc[i][0] = b0v.x; acc[i][1] = b0v.y; acc[i][2] = b0v.z; acc[i][3] = b0v.w;
+                    acc[i][4] = b1v.x; acc[i][5] = b1v.y; acc[i][6] = b1v.z; acc[i][7] = b1v.w;
+                }
+            }
+            const float* Ak = Ac + grp * H * TM;
+            const float* Wk = Wp + grp * H * G;
+#pragma unroll 4
+            for (int k = 0; k < H; ++k) {
+                float4 a = ld4(Ak + k * TM + r0);
+                float4 w0 = ld4(Wk + k * G + j0 * 4);
+                float4 w1 = ld4(Wk + k * G + j1 * 4);
+                const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    acc[i][0] = fmaf(av[i], w0.x, acc[i][0]); acc[i][1] = fmaf(av[i], w0.y, acc[i][1]);
+                    acc[i][2] = fmaf(av[i], w0.z, acc[i][2]); acc[i][3] = fmaf(av[i], w0.w, acc[i][3]);
+                    acc[i][4] = fmaf(av[i], w1.x, acc[i][4]); acc[i][5] = fmaf(av[i], w1.y, acc[i][5]);
+                    acc[i][6] = fmaf(av[i], w1.z, acc[i][6]); acc[i][7] = fmaf(av[i], w1.w, acc[i][7]);
+                }
+            }
+            // hand over the partial sums of the unit the partner owns
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int o = grp ? 0 : 4;
+                X[(i * 2 + grp) * 256 + t8] = make_float4(acc[i][o], acc[i][o + 1], acc[i][o + 2], acc[i][o + 3]);
+            }
+            __syncthreads();
+            float pre[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 v = X[(i * 2 + (grp ^ 1)) * 256 + t8];
+                const int o = grp ? 4 : 0;
+                pre[i][0] = acc[i][o] + v.x; pre[i][1] = acc[i][o + 1] + v.y;
+                pre[i][2] = acc[i][o + 2] + v.z; pre[i][3] = acc[i][o + 3] + v.w;
+            }
+            float hn[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float ig = sigm(pre[i][0]), fg = sigm(pre[i][1]), gg = tanh_(pre[i][2]), og = sigm(pre[i][3]);
+                float cn = fmaf(fg, cst[i], ig * gg);
+                float hh = og * tanh_(cn);
+                cst[i] = cn; hn[i] = hh;
+                if (bok[i]) {
+                    const size_t o = ((size_t)brow[i] * T + t) * H + jown;
+                    st4(gates + o * 4, make_float4(ig, fg, gg, og));
+                    c_out[o] = cn; h_out[o] = hh;
+                }
+            }
+            st4(An + (H + jown) * TM + r0, make_float4(hn[0], hn[1], hn[2], hn[3]));
+            if (t + 1 < T) {
+                const float* Un = U + ((t + 1) & 1) * nU;
+                float x[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float a = bts[jown];
+                    for (int q = 0; q < Fin; ++q) a = fmaf(Un[(r0 + i) * Fin + q], WtS[q * H + jown], a);
+                    x[i] = fmaxf(a, 0.f);
+                }
+                st4(An + jown * TM + r0, make_float4(x[0], x[1], x[2], x[3]));
+            }
+            if (do_pre) {
+                float* Ud = U + (t & 1) * nU;
+#pragma unroll
+                for (int e = 0; e < (TM * MAXF + NT16 - 1) / NT16; ++e) {
+                    int i = e * NT16 + tid;
                     if (i < nU) Ud[i] = upre[e];
                 }
             }
@@ -407,16 +584,19 @@ lstm_bwd_kernel(const float* __restrict__ dhead, const float* __restrict__ W_hea
             __syncthreads();
             // (c) dh_rec[r][k] = sum_p dpre[r][p] W_hh[n(p)][k]        (32 x 64 x 256 per CTA)
             if (t > 0) {
-                float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+                // packed FFMA2: accumulator pairs run along the rows (the float4 of D_T), W is the scalar operand
+                f2 a0l = f2_make(0.f, 0.f), a0h = a0l, a1l = a0l, a1h = a0l;
 #pragma unroll 8
                 for (int p = 0; p < G; ++p) {
-                    float4 d = ld4(Dc + p * BS + m.r0);
-                    float w0 = WhT[p * H + m.j0], w1 = WhT[p * H + m.j1];
-                    a0[0] = fmaf(d.x, w0, a0[0]); a0[1] = fmaf(d.y, w0, a0[1]);
-                    a0[2] = fmaf(d.z, w0, a0[2]); a0[3] = fmaf(d.w, w0, a0[3]);
-                    a1[0] = fmaf(d.x, w1, a1[0]); a1[1] = fmaf(d.y, w1, a1[1]);
-                    a1[2] = fmaf(d.z, w1, a1[2]); a1[3] = fmaf(d.w, w1, a1[3]);
+                    f2 dl, dh2;
+                    f2_ld2(Dc + p * BS + m.r0, dl, dh2);
+                    const float w0 = WhT[p * H + m.j0], w1 = WhT[p * H + m.j1];
+                    const f2 w0b = f2_make(w0, w0), w1b = f2_make(w1, w1);
+                    f2_fma(a0l, dl, w0b); f2_fma(a0h, dh2, w0b);
+                    f2_fma(a1l, dl, w1b); f2_fma(a1h, dh2, w1b);
                 }
+                const float a0[4] = {f2_lo(a0l), f2_hi(a0l), f2_lo(a0h), f2_hi(a0h)};
+                const float a1[4] = {f2_lo(a1l), f2_hi(a1l), f2_lo(a1h), f2_hi(a1h)};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { dhr[i][0] = a0[i]; dhr[i][1] = a1[i]; }
             }
@@ -691,11 +871,17 @@ extern "C" int b200rl_lstm_fwd(const float* u, const float* hx0, const float* cx
                                int B, int T, int Fin, int variant, void* stream) {
     B200RL_REQUIRE(B >= 1 && T >= 1, "lstm_fwd: bad shape B=%d T=%d", B, T);
     B200RL_REQUIRE(Fin >= 1 && Fin <= MAXF, "lstm_fwd: Fin=%d out of range [1,%d]", Fin, MAXF);
-    B200RL_REQUIRE(variant == 0, "lstm_fwd: unknown variant %d", variant);
-    const size_t smem = fwd_smem_bytes(Fin);
-    if (set_smem(lstm_fwd_kernel, smem, "lstm_fwd")) return 1;
+    B200RL_REQUIRE(variant == 0 || variant == 1, "lstm_fwd: unknown variant %d", variant);
     const int ntiles = (B + TM - 1) / TM;
     const int grid = ntiles < sm_count() ? ntiles : sm_count();
+    if (variant == 1) {
+        const size_t smem16 = fwd16_smem_bytes(Fin) + 16;
+        if (set_smem(lstm_fwd16_kernel, smem16, "lstm_fwd16")) return 1;
+        B200RL_LAUNCH(lstm_fwd16_kernel, grid, NT16, smem16, stream, u, hx0, cx0, Wt, bt, W_ih, W_hh, b_ih, b_hh, gates, c, h, B, T, Fin);
+        return check_launch("lstm_fwd16");
+    }
+    const size_t smem = fwd_smem_bytes(Fin);
+    if (set_smem(lstm_fwd_kernel, smem, "lstm_fwd")) return 1;
     B200RL_LAUNCH(lstm_fwd_kernel, grid, NT, smem, stream, u, hx0, cx0, Wt, bt, W_ih, W_hh, b_ih, b_hh, gates, c, h, B, T, Fin);
     return check_launch("lstm_fwd");
 }
