@@ -56,17 +56,23 @@ async def run_learning(parent, timer, queue_name, update, losses, publish_state,
     queue = getattr(parent, queue_name)
     args = parent.args
     cuda = torch.device(parent.device).type == "cuda"
+    ahead = None                      # next host batch, already travelling to the device on the copy stream
+    can_prefetch = cuda and hasattr(parent.to_gpu, "prefetch")
     while not parent.stop_event.is_set():
         batch_args = None
         with timer.timer("learner-throughput", check_throughput=True):
             with timer.timer("learner-batching-time"):
-                batch_args = await queue.get()
+                batch_args, ahead = (ahead, None) if ahead is not None else (await queue.get(), None)
             if batch_args is not None:
                 with timer.timer("learner-forward-time"):
                     dev_batch = parent.to_gpu(*batch_args)
                     for _ in range(args.K_epoch):
                         with timer.timer("learner-backward-time"):
                             update(parent, dev_batch)
+                    if can_prefetch and not queue.empty():       # overlap the next H2D with this update
+                        ahead = queue.get_nowait()
+                        if ahead is not None:
+                            parent.to_gpu.prefetch(*ahead)
                     if cuda:
                         torch.cuda.current_stream(parent.device).synchronize()
                 parent.pub_model(publish_state(parent))

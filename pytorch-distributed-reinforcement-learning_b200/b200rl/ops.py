@@ -10,8 +10,9 @@ from . import native
 from .native import ptr
 
 H = 64
-# kernel variants (env-overridable for A/B measurements): forward 1 = 16-warp split-K, 0 = 8-warp
-FWD_VARIANT = int(os.environ.get("B200RL_FWD_VARIANT", "1"))
+# kernel variants (env-overridable for A/B measurements): forward 2 = tcgen05 input projection + K=64
+# recurrent kernel, 1 = 16-warp split-K FFMA, 0 = 8-warp FFMA with the projection in the loop
+FWD_VARIANT = int(os.environ.get("B200RL_FWD_VARIANT", "2"))
 BWD_VARIANT = int(os.environ.get("B200RL_BWD_VARIANT", "0"))
 
 

@@ -87,25 +87,33 @@ BATCH_FIELDS = ("obs", "act", "rew", "logits", "log_prob", "is_fir", "hx", "cx")
 
 
 class HostStager:
-    """Pinned staging + one async H2D per field, shipping only what the update reads:
-    `hx`/`cx` are cut to `[:, 0]` on the host (the reference copies all (B,T,H) of both --
-    268 MB at (4096,128) -- and then reads `[:, 0]`, ppo/learning.py:26,37-40)."""
+    """Pinned staging + async H2D, shipping only what the update reads: `hx`/`cx` are cut to
+    `[:, 0]` on the host (the reference copies all (B,T,H) of both -- 268 MB at (4096,128) -- and then
+    reads `[:, 0]`, ppo/learning.py:26,37-40) and fields the algorithm never reads are skipped.
+
+    `stager(*batch)` copies on the current stream.  `prefetch(*batch)` starts the same copies on a
+    side stream into the other of two buffer sets, so the next batch crosses PCIe while the
+    current update runs; the following `stager(*batch)` call for that same tuple just makes the
+    compute stream wait on the copy event."""
 
     def __init__(self, device):
         self.device = torch.device(device)
-        self.pinned = {}
+        self.pinned = [{}, {}]
+        self.flip = 0
         self.bytes_last = 0
         self.skip = set()            # fields the algorithm never reads (not shipped)
+        self._pending = None         # (id of host tuple, device tuple, event, nbytes)
+        self._copy_stream = None
 
-    def _pin(self, name, t):
-        buf = self.pinned.get(name)
+    def _pin(self, slot, name, t):
+        buf = self.pinned[slot].get(name)
         if buf is None or buf.shape != t.shape:
             buf = torch.empty(t.shape, dtype=torch.float32, pin_memory=self.device.type == "cuda")
-            self.pinned[name] = buf
+            self.pinned[slot][name] = buf
         buf.copy_(t)
         return buf
 
-    def __call__(self, *batch_args):
+    def _ship(self, batch_args, slot):
         out, nbytes = [], 0
         for name, t in zip(BATCH_FIELDS, batch_args):
             if t is None or name in self.skip:
@@ -116,11 +124,36 @@ class HostStager:
             if t.device == self.device:
                 out.append(t.contiguous())
                 continue
-            src = t if t.is_pinned() else self._pin(name, t)
+            src = t if (t.is_pinned() and t.is_contiguous()) else self._pin(slot, name, t)
             out.append(src.to(self.device, non_blocking=True))
             nbytes += src.numel() * 4
-        self.bytes_last = nbytes
-        return tuple(out)
+        return tuple(out), nbytes
+
+    def prefetch(self, *batch_args):
+        if self.device.type != "cuda" or self._pending is not None:
+            return
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        self.flip ^= 1
+        with torch.cuda.stream(self._copy_stream):
+            dev, nbytes = self._ship(batch_args, self.flip)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._pending = (id(batch_args), batch_args, dev, ev, nbytes)
+
+    def __call__(self, *batch_args):
+        pend = self._pending
+        if pend is not None and pend[1] is batch_args:
+            self._pending = None
+            torch.cuda.current_stream(self.device).wait_event(pend[3])
+            for t in pend[2]:
+                if t is not None:
+                    t.record_stream(torch.cuda.current_stream(self.device))
+            self.bytes_last = pend[4]
+            return pend[2]
+        self.flip ^= 1
+        dev, self.bytes_last = self._ship(batch_args, self.flip)
+        return dev
 
 
 def make_gpu_batch(*args, device):

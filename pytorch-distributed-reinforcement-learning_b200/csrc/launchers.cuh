@@ -11,4 +11,7 @@ int launch_dx_tc(const float* dpre, const float* u, const float* W_ih, const flo
                  const float* h, const float* dhead, float* partials, int nparts, long long P,
                  long long off_Wt, long long off_bt, long long off_Whead, long long off_bhead,
                  float* du, int B, int T, int Fin, int NH, void* stream);
+// xproj_tc.cu: xproj[b,t,p] = bias + ReLU(torso) . W_ih^T for all rows, gate-interleaved columns
+int launch_xproj_tc(const float* u, const float* Wt, const float* bt, const float* W_ih, const float* b_ih, const float* b_hh,
+                    float* xproj, int B, int T, int Fin, int sms, void* stream);
 }  // namespace b200rl

@@ -244,6 +244,111 @@ lstm_fwd_kernel(const float* __restrict__ u, const float* __restrict__ hx0, cons
     }
 }
 
+// ------------------------------------------------- forward, recurrent half only (variant 2, default)
+// gates_t = xproj_t + h_{t-1} . W_hh^T : the input projection (incl. both biases) was computed for all
+// timesteps by lstm_xproj_tc_kernel (xproj_tc.cu, tcgen05).  Only W_hh (64 KB) stays in shared memory,
+// the K loop is 64 deep, and the accumulators start from the prefetched xproj row segment.
+// `xg` is BOTH input and output: xg[b,t,j,:] holds the projection until the thread that owns (b,t,j)
+// overwrites those 16 bytes with the gate activations (no extra 0.5 GB buffer, no extra traffic).
+static inline size_t fwdx_smem_bytes() { return sizeof(float) * (size_t)(H * G + 2 * H * TM); }
+
+__global__ void __launch_bounds__(NT, 1)
+lstm_fwdx_kernel(float* xg, const float* __restrict__ hx0, const float* __restrict__ cx0,
+                 const float* __restrict__ W_hh, float* __restrict__ c_out,
+                 float* __restrict__ h_out, int B, int T) {
+    B200RL_DYN_SMEM(float, smem);
+    float* Wp = smem;                       // Wp[k*256 + j*4 + g] = W_hh[g*64 + j][k]
+    float* HT = Wp + H * G;                 // HT[buf][k*32 + r] = h_{t-1}
+    const int tid = threadIdx.x;
+    const MapJ m;
+    {
+        const int n = tid, g = n >> 6, j = n & 63, pc = j * 4 + g;
+        for (int k4 = 0; k4 < H; k4 += 4) {
+            float4 b = ld4(W_hh + (size_t)n * H + k4);
+            Wp[(k4 + 0) * G + pc] = b.x; Wp[(k4 + 1) * G + pc] = b.y;
+            Wp[(k4 + 2) * G + pc] = b.z; Wp[(k4 + 3) * G + pc] = b.w;
+        }
+    }
+    const int ntiles = (B + TM - 1) / TM;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int b0 = tile * TM;
+        __syncthreads();
+        int brow[4]; bool bok[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { int b = b0 + m.r0 + i; bok[i] = b < B; brow[i] = bok[i] ? b : B - 1; }
+        float cst[4][2];
+        {
+            float hv0[4], hv1[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                cst[i][0] = cx0[(size_t)brow[i] * H + m.j0]; cst[i][1] = cx0[(size_t)brow[i] * H + m.j1];
+                hv0[i] = hx0[(size_t)brow[i] * H + m.j0];    hv1[i] = hx0[(size_t)brow[i] * H + m.j1];
+            }
+            st4(HT + m.j0 * TM + m.r0, make_float4(hv0[0], hv0[1], hv0[2], hv0[3]));
+            st4(HT + m.j1 * TM + m.r0, make_float4(hv1[0], hv1[1], hv1[2], hv1[3]));
+        }
+        float4 xp[4][2];                     // projection of the step being processed (loaded one step ahead)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const size_t o = ((size_t)brow[i] * T + 0) * G;
+            xp[i][0] = ld4(xg + o + m.j0 * 4); xp[i][1] = ld4(xg + o + m.j1 * 4);
+        }
+        __syncthreads();
+
+        for (int t = 0; t < T; ++t) {
+            const float* Hc = HT + (t & 1) * H * TM;
+            float* Hn = HT + ((t + 1) & 1) * H * TM;
+            f2 acc2[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                acc2[i][0] = f2_make(xp[i][0].x, xp[i][0].y); acc2[i][1] = f2_make(xp[i][0].z, xp[i][0].w);
+                acc2[i][2] = f2_make(xp[i][1].x, xp[i][1].y); acc2[i][3] = f2_make(xp[i][1].z, xp[i][1].w);
+            }
+            if (t + 1 < T) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const size_t o = ((size_t)brow[i] * T + (t + 1)) * G;
+                    xp[i][0] = ld4(xg + o + m.j0 * 4); xp[i][1] = ld4(xg + o + m.j1 * 4);
+                }
+            }
+#pragma unroll 4
+            for (int k = 0; k < H; ++k) {
+                const float4 a = ld4(Hc + k * TM + m.r0);
+                f2 w00, w01, w10, w11;
+                f2_ld2(Wp + k * G + m.j0 * 4, w00, w01);
+                f2_ld2(Wp + k * G + m.j1 * 4, w10, w11);
+                const f2 av[4] = {f2_make(a.x, a.x), f2_make(a.y, a.y), f2_make(a.z, a.z), f2_make(a.w, a.w)};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    f2_fma(acc2[i][0], av[i], w00); f2_fma(acc2[i][1], av[i], w01);
+                    f2_fma(acc2[i][2], av[i], w10); f2_fma(acc2[i][3], av[i], w11);
+                }
+            }
+            float hn[4][2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const float ig = sigm(f2_lo(acc2[i][jj * 2])), fg = sigm(f2_hi(acc2[i][jj * 2]));
+                    const float gg = tanh_(f2_lo(acc2[i][jj * 2 + 1])), og = sigm(f2_hi(acc2[i][jj * 2 + 1]));
+                    const float cn = fmaf(fg, cst[i][jj], ig * gg);
+                    const float hh = og * tanh_(cn);
+                    cst[i][jj] = cn; hn[i][jj] = hh;
+                    if (bok[i]) {
+                        const int j = jj ? m.j1 : m.j0;
+                        const size_t o = ((size_t)brow[i] * T + t) * H + j;
+                        st4(xg + o * 4, make_float4(ig, fg, gg, og));
+                        c_out[o] = cn; h_out[o] = hh;
+                    }
+                }
+            }
+            st4(Hn + m.j0 * TM + m.r0, make_float4(hn[0][0], hn[1][0], hn[2][0], hn[3][0]));
+            st4(Hn + m.j1 * TM + m.r0, make_float4(hn[0][1], hn[1][1], hn[2][1], hn[3][1]));
+            __syncthreads();
+        }
+    }
+}
+
 // ------------------------------------------------------------------ forward, 16-warp variant
 // Same tiling, but 512 threads: warp group 0 multiplies the x half of K (k < 64), group 1 the
 // h half; each thread then hands the partial sums of the unit it does NOT own to its partner
@@ -458,7 +563,7 @@ head_fwd_kernel(const float* __restrict__ h, const float* __restrict__ W, const 
 constexpr int BS = 32;       // backward D_T row stride: 128-byte aligned rows -> one wavefront per LDS.128
 // shared (floats): WhT[256][64] | DT[2][256][BS] | WhS[NH][64] | dHd[2][32][NH]
 static inline size_t bwd_smem_bytes(int NH) {
-    return sizeof(float) * (size_t)(G * H + 2 * G * BS + NH * H + 2 * TM * NH);
+    return sizeof(float) * (size_t)(G * H + 2 * G * BS + NH * H + 2 * TM * NH + 4 + 4 * TM * H);
 }
 
 __global__ void __launch_bounds__(NT, 1)
@@ -471,8 +576,12 @@ lstm_bwd_kernel(const float* __restrict__ dhead, const float* __restrict__ W_hea
     float* DT = WhT + G * H;                 // DT[buf][p*BS + r]
     float* WhS = DT + 2 * G * BS;            // WhS[c*64 + k]
     float* dHd = WhS + NH * H;               // dHd[buf][r*NH + c]
+    float* Rp = dHd + 2 * TM * NH + ((4 - ((2 * TM * NH) & 3)) & 3);   // Rp[slice][row*64 + k]: split-K partial sums (16-byte aligned)
     const int tid = threadIdx.x;
     const MapR m;
+    // dh GEMM ownership: K (the 256 gate columns) is split 4 ways over warp pairs; within a slice a thread owns
+    // 4 rows x 8 k: 12 shared-memory wavefronts per 32 FMA instead of 6 per 8 (the kernel is wavefront-bound)
+    const int gs = tid >> 6, grg = tid & 7, gk0 = (((tid >> 5) & 1) * 4 + ((tid & 31) >> 3)) * 8;
     {
         const int n = tid, g = n >> 6, j = n & 63, p = j * 4 + g;
         for (int k4 = 0; k4 < H; k4 += 4) st4(WhT + p * H + k4, ld4(W_hh + (size_t)n * H + k4));
@@ -584,21 +693,43 @@ lstm_bwd_kernel(const float* __restrict__ dhead, const float* __restrict__ W_hea
             __syncthreads();
             // (c) dh_rec[r][k] = sum_p dpre[r][p] W_hh[n(p)][k]        (32 x 64 x 256 per CTA)
             if (t > 0) {
-                // packed FFMA2: accumulator pairs run along the rows (the float4 of D_T), W is the scalar operand
-                f2 a0l = f2_make(0.f, 0.f), a0h = a0l, a1l = a0l, a1h = a0l;
-#pragma unroll 8
-                for (int p = 0; p < G; ++p) {
-                    f2 dl, dh2;
-                    f2_ld2(Dc + p * BS + m.r0, dl, dh2);
-                    const float w0 = WhT[p * H + m.j0], w1 = WhT[p * H + m.j1];
-                    const f2 w0b = f2_make(w0, w0), w1b = f2_make(w1, w1);
-                    f2_fma(a0l, dl, w0b); f2_fma(a0h, dh2, w0b);
-                    f2_fma(a1l, dl, w1b); f2_fma(a1h, dh2, w1b);
-                }
-                const float a0[4] = {f2_lo(a0l), f2_hi(a0l), f2_lo(a0h), f2_hi(a0h)};
-                const float a1[4] = {f2_lo(a1l), f2_hi(a1l), f2_lo(a1h), f2_hi(a1h)};
+                f2 acc[4][4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { dhr[i][0] = a0[i]; dhr[i][1] = a1[i]; }
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[i][c] = f2_make(0.f, 0.f);
+#pragma unroll 4
+                for (int pp = 0; pp < G / 4; ++pp) {
+                    const int p = gs * (G / 4) + pp;
+                    const float4 d = ld4(Dc + p * BS + grg * 4);
+                    f2 w0, w1, w2, w3;
+                    f2_ld2(WhT + p * H + gk0, w0, w1);
+                    f2_ld2(WhT + p * H + gk0 + 4, w2, w3);
+                    const f2 dv[4] = {f2_make(d.x, d.x), f2_make(d.y, d.y), f2_make(d.z, d.z), f2_make(d.w, d.w)};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        f2_fma(acc[i][0], dv[i], w0); f2_fma(acc[i][1], dv[i], w1);
+                        f2_fma(acc[i][2], dv[i], w2); f2_fma(acc[i][3], dv[i], w3);
+                    }
+                }
+                float* Rs = Rp + gs * TM * H;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float* dst = Rs + (grg * 4 + i) * H + gk0;
+                    st4(dst, make_float4(f2_lo(acc[i][0]), f2_hi(acc[i][0]), f2_lo(acc[i][1]), f2_hi(acc[i][1])));
+                    st4(dst + 4, make_float4(f2_lo(acc[i][2]), f2_hi(acc[i][2]), f2_lo(acc[i][3]), f2_hi(acc[i][3])));
+                }
+                __syncthreads();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                    for (int sl = 0; sl < 4; ++sl) {
+                        s0 += Rp[sl * TM * H + (m.r0 + i) * H + m.j0];
+                        s1 += Rp[sl * TM * H + (m.r0 + i) * H + m.j1];
+                    }
+                    dhr[i][0] = s0; dhr[i][1] = s1;
+                }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -871,9 +1002,17 @@ extern "C" int b200rl_lstm_fwd(const float* u, const float* hx0, const float* cx
                                int B, int T, int Fin, int variant, void* stream) {
     B200RL_REQUIRE(B >= 1 && T >= 1, "lstm_fwd: bad shape B=%d T=%d", B, T);
     B200RL_REQUIRE(Fin >= 1 && Fin <= MAXF, "lstm_fwd: Fin=%d out of range [1,%d]", Fin, MAXF);
-    B200RL_REQUIRE(variant == 0 || variant == 1, "lstm_fwd: unknown variant %d", variant);
+    B200RL_REQUIRE(variant >= 0 && variant <= 2, "lstm_fwd: unknown variant %d", variant);
     const int ntiles = (B + TM - 1) / TM;
     const int grid = ntiles < sm_count() ? ntiles : sm_count();
+    if (variant == 2) {
+        // input projection on tcgen05 for all (b,t), staged in the (not yet written) `gates` buffer
+        if (launch_xproj_tc(u, Wt, bt, W_ih, b_ih, b_hh, gates, B, T, Fin, sm_count(), stream)) return 1;
+        const size_t smx = fwdx_smem_bytes();
+        if (set_smem(lstm_fwdx_kernel, smx, "lstm_fwd(recurrent)")) return 1;
+        B200RL_LAUNCH(lstm_fwdx_kernel, grid, NT, smx, stream, gates, hx0, cx0, W_hh, c, h, B, T);
+        return check_launch("lstm_fwd(recurrent)");
+    }
     if (variant == 1) {
         const size_t smem16 = fwd16_smem_bytes(Fin) + 16;
         if (set_smem(lstm_fwd16_kernel, smem16, "lstm_fwd16")) return 1;
