@@ -22,6 +22,7 @@
 // post-activation gates (i,f,g,o) as one float4; c, h (B,T,64).
 #include "common.cuh"
 #include "launchers.cuh"
+#include "tc05.cuh"
 
 namespace b200rl {
 
@@ -252,15 +253,22 @@ lstm_fwd_kernel(const float* __restrict__ u, const float* __restrict__ hx0, cons
 // overwrites those 16 bytes with the gate activations (no extra 0.5 GB buffer, no extra traffic).
 static inline size_t fwdx_smem_bytes() { return sizeof(float) * (size_t)(H * G + 2 * H * TM); }
 
+// The CTA is two INDEPENDENT halves of 128 threads, 16 sequences each, sharing only the read-only W_hh
+// tile: each half synchronises with itself through a named barrier, so the halves drift apart and one
+// half's FFMA-bound GEMM phase overlaps the other's MUFU-bound cell phase (with all eight warps in
+// lock-step the two pipes took turns idling: ncu r1g, 9.9K cycles per timestep for 4.1K FMA cycles).
+constexpr int HM = TM / 2;                  // sequences per half
+
 __global__ void __launch_bounds__(NT, 1)
 lstm_fwdx_kernel(float* xg, const float* __restrict__ hx0, const float* __restrict__ cx0,
                  const float* __restrict__ W_hh, float* __restrict__ c_out,
                  float* __restrict__ h_out, int B, int T) {
     B200RL_DYN_SMEM(float, smem);
     float* Wp = smem;                       // Wp[k*256 + j*4 + g] = W_hh[g*64 + j][k]
-    float* HT = Wp + H * G;                 // HT[buf][k*32 + r] = h_{t-1}
-    const int tid = threadIdx.x;
-    const MapJ m;
+    const int tid = threadIdx.x, half = tid >> 7, ht = tid & 127, lane = tid & 31, hw = ht >> 5;
+    float* HT = Wp + H * G + half * 2 * H * HM;     // HT[buf][k*16 + r] = h_{t-1} of this half
+    const int r0 = (lane >> 3) * 4;                 // 4 of the half's 16 rows
+    const int j0 = hw * 8 + (lane & 7), j1 = j0 + 32;
     {
         const int n = tid, g = n >> 6, j = n & 63, pc = j * 4 + g;
         for (int k4 = 0; k4 < H; k4 += 4) {
@@ -269,35 +277,36 @@ lstm_fwdx_kernel(float* xg, const float* __restrict__ hx0, const float* __restri
             Wp[(k4 + 2) * G + pc] = b.z; Wp[(k4 + 3) * G + pc] = b.w;
         }
     }
+    __syncthreads();
     const int ntiles = (B + TM - 1) / TM;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int b0 = tile * TM;
-        __syncthreads();
+        const int b0 = tile * TM + half * HM;
+        tc::named_bar_sync(1 + half, 128);           // previous tile of this half finished with HT
         int brow[4]; bool bok[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { int b = b0 + m.r0 + i; bok[i] = b < B; brow[i] = bok[i] ? b : B - 1; }
+        for (int i = 0; i < 4; ++i) { int b = b0 + r0 + i; bok[i] = b < B; brow[i] = bok[i] ? b : B - 1; }
         float cst[4][2];
         {
             float hv0[4], hv1[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                cst[i][0] = cx0[(size_t)brow[i] * H + m.j0]; cst[i][1] = cx0[(size_t)brow[i] * H + m.j1];
-                hv0[i] = hx0[(size_t)brow[i] * H + m.j0];    hv1[i] = hx0[(size_t)brow[i] * H + m.j1];
+                cst[i][0] = cx0[(size_t)brow[i] * H + j0]; cst[i][1] = cx0[(size_t)brow[i] * H + j1];
+                hv0[i] = hx0[(size_t)brow[i] * H + j0];    hv1[i] = hx0[(size_t)brow[i] * H + j1];
             }
-            st4(HT + m.j0 * TM + m.r0, make_float4(hv0[0], hv0[1], hv0[2], hv0[3]));
-            st4(HT + m.j1 * TM + m.r0, make_float4(hv1[0], hv1[1], hv1[2], hv1[3]));
+            st4(HT + j0 * HM + r0, make_float4(hv0[0], hv0[1], hv0[2], hv0[3]));
+            st4(HT + j1 * HM + r0, make_float4(hv1[0], hv1[1], hv1[2], hv1[3]));
         }
         float4 xp[4][2];                     // projection of the step being processed (loaded one step ahead)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const size_t o = ((size_t)brow[i] * T + 0) * G;
-            xp[i][0] = ld4(xg + o + m.j0 * 4); xp[i][1] = ld4(xg + o + m.j1 * 4);
+            xp[i][0] = ld4(xg + o + j0 * 4); xp[i][1] = ld4(xg + o + j1 * 4);
         }
-        __syncthreads();
+        tc::named_bar_sync(1 + half, 128);
 
         for (int t = 0; t < T; ++t) {
-            const float* Hc = HT + (t & 1) * H * TM;
-            float* Hn = HT + ((t + 1) & 1) * H * TM;
+            const float* Hc = HT + (t & 1) * H * HM;
+            float* Hn = HT + ((t + 1) & 1) * H * HM;
             f2 acc2[4][4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -308,15 +317,15 @@ lstm_fwdx_kernel(float* xg, const float* __restrict__ hx0, const float* __restri
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const size_t o = ((size_t)brow[i] * T + (t + 1)) * G;
-                    xp[i][0] = ld4(xg + o + m.j0 * 4); xp[i][1] = ld4(xg + o + m.j1 * 4);
+                    xp[i][0] = ld4(xg + o + j0 * 4); xp[i][1] = ld4(xg + o + j1 * 4);
                 }
             }
 #pragma unroll 4
             for (int k = 0; k < H; ++k) {
-                const float4 a = ld4(Hc + k * TM + m.r0);
+                const float4 a = ld4(Hc + k * HM + r0);
                 f2 w00, w01, w10, w11;
-                f2_ld2(Wp + k * G + m.j0 * 4, w00, w01);
-                f2_ld2(Wp + k * G + m.j1 * 4, w10, w11);
+                f2_ld2(Wp + k * G + j0 * 4, w00, w01);
+                f2_ld2(Wp + k * G + j1 * 4, w10, w11);
                 const f2 av[4] = {f2_make(a.x, a.x), f2_make(a.y, a.y), f2_make(a.z, a.z), f2_make(a.w, a.w)};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -335,16 +344,16 @@ lstm_fwdx_kernel(float* xg, const float* __restrict__ hx0, const float* __restri
                     const float hh = og * tanh_(cn);
                     cst[i][jj] = cn; hn[i][jj] = hh;
                     if (bok[i]) {
-                        const int j = jj ? m.j1 : m.j0;
+                        const int j = jj ? j1 : j0;
                         const size_t o = ((size_t)brow[i] * T + t) * H + j;
                         st4(xg + o * 4, make_float4(ig, fg, gg, og));
                         c_out[o] = cn; h_out[o] = hh;
                     }
                 }
             }
-            st4(Hn + m.j0 * TM + m.r0, make_float4(hn[0][0], hn[1][0], hn[2][0], hn[3][0]));
-            st4(Hn + m.j1 * TM + m.r0, make_float4(hn[0][1], hn[1][1], hn[2][1], hn[3][1]));
-            __syncthreads();
+            st4(Hn + j0 * HM + r0, make_float4(hn[0][0], hn[1][0], hn[2][0], hn[3][0]));
+            st4(Hn + j1 * HM + r0, make_float4(hn[0][1], hn[1][1], hn[2][1], hn[3][1]));
+            tc::named_bar_sync(1 + half, 128);
         }
     }
 }
@@ -715,9 +724,11 @@ lstm_bwd_kernel(const float* __restrict__ dhead, const float* __restrict__ W_hea
                 float* Rs = Rp + gs * TM * H;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    float* dst = Rs + (grg * 4 + i) * H + gk0;
-                    st4(dst, make_float4(f2_lo(acc[i][0]), f2_hi(acc[i][0]), f2_lo(acc[i][1]), f2_hi(acc[i][1])));
-                    st4(dst + 4, make_float4(f2_lo(acc[i][2]), f2_hi(acc[i][2]), f2_lo(acc[i][3]), f2_hi(acc[i][3])));
+                    // columns XOR-swizzled by the row group (16-byte granules): without it the eight row groups of a
+                    // quarter-warp hit one bank group on both sides of the exchange (ncu r1g: 41 % of all wavefronts)
+                    float* dst = Rs + (grg * 4 + i) * H;
+                    st4(dst + (gk0 ^ (grg << 2)), make_float4(f2_lo(acc[i][0]), f2_hi(acc[i][0]), f2_lo(acc[i][1]), f2_hi(acc[i][1])));
+                    st4(dst + ((gk0 + 4) ^ (grg << 2)), make_float4(f2_lo(acc[i][2]), f2_hi(acc[i][2]), f2_lo(acc[i][3]), f2_hi(acc[i][3])));
                 }
                 __syncthreads();
 #pragma unroll
@@ -725,8 +736,8 @@ lstm_bwd_kernel(const float* __restrict__ dhead, const float* __restrict__ W_hea
                     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
                     for (int sl = 0; sl < 4; ++sl) {
-                        s0 += Rp[sl * TM * H + (m.r0 + i) * H + m.j0];
-                        s1 += Rp[sl * TM * H + (m.r0 + i) * H + m.j1];
+                        s0 += Rp[sl * TM * H + (m.r0 + i) * H + (m.j0 ^ m.r0)];       // r0 = 4 * row group
+                        s1 += Rp[sl * TM * H + (m.r0 + i) * H + (m.j1 ^ m.r0)];
                     }
                     dhr[i][0] = s0; dhr[i][1] = s1;
                 }

@@ -13,7 +13,10 @@
 // row of a 128-row tile: it recomputes x (4-wide obs), splits hi/lo and writes the K-major A operand
 // with 16-byte stores.  3xTF32 (hi*hi + hi*lo + lo*hi) into one of TWO 128x256 fp32 accumulators in
 // TMEM (all 512 columns), so the epilogue of tile i (tcgen05.ld, + bias, 128 KB of stores) overlaps the
-// MMAs of tile i+1.  Bound: the 1 KB/row HBM write.
+// MMAs of tile i+1.  Bound: the 1 KB/row HBM write.  tcgen05.ld hands each thread one ROW, so direct
+// stores touch 32 different 128-byte lines per warp instruction (ncu r1g: LSU wavefronts 72 %, all
+// store traffic); the epilogue therefore transposes 32 x 16 blocks through a per-warp smem patch and
+// writes 64-byte row segments.  The obs row of the next tile is loaded before the epilogue runs.
 #include "common.cuh"
 #include "tc05.cuh"
 #include "launchers.cuh"
@@ -28,12 +31,14 @@ constexpr int W_BYTES = (G / 8) * W_SBO;                   // 65536 per hi / lo
 constexpr int A_LBO = 128, A_SBO = (H / 4) * 128;          // A: 16 core matrices along K per 8-row group (2048)
 constexpr int A_BYTES = (TR / 8) * A_SBO;                  // 32768 per hi / lo
 constexpr int MAXF = 32;
+constexpr int SC = 16, SST = SC + 1;                       // epilogue patch: 32 rows x 16 columns, stride 17
 }  // namespace xpk
 
 static inline size_t xproj_smem_bytes(int Fin) {
-    return 2 * (size_t)xpk::W_BYTES + 2 * (size_t)xpk::A_BYTES + sizeof(float) * (size_t)(Fin * xpk::H + xpk::H + xpk::G) + 96;
+    return 2 * (size_t)xpk::W_BYTES + 2 * (size_t)xpk::A_BYTES + sizeof(float) * (size_t)(Fin * xpk::H + xpk::H + xpk::G + (xpk::NP / 32) * 32 * xpk::SST) + 96;
 }
 
+template <int FMAX>
 __global__ void __launch_bounds__(xpk::NT, 1)
 lstm_xproj_tc_kernel(const float* __restrict__ u, const float* __restrict__ Wt, const float* __restrict__ bt,
                      const float* __restrict__ W_ih, const float* __restrict__ b_ih, const float* __restrict__ b_hh,
@@ -47,7 +52,8 @@ lstm_xproj_tc_kernel(const float* __restrict__ u, const float* __restrict__ Wt, 
     float* WtS = reinterpret_cast<float*>(A_lo + A_BYTES);              // WtS[q*64 + k]
     float* bts = WtS + Fin * H;
     float* bsum = bts + H;                                               // bsum[p]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(bsum + G);             // a_full | a_empty | acc_done[2] | acc_free[2]
+    float* patch = bsum + G;                                             // [warp][32 * SST]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(patch + (NP / 32) * 32 * SST);   // a_full | a_empty | acc_done[2] | acc_free[2]
     uint64_t* a_full = bars, *a_empty = bars + 1, *acc_done = bars + 2, *acc_free = bars + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
 
@@ -105,19 +111,25 @@ lstm_xproj_tc_kernel(const float* __restrict__ u, const float* __restrict__ Wt, 
     } else {
         // producer thread: row r of the tile (threads 0..127) / the same rows again for the second half of K (128..255)
         const int r = tid & 127, khalf = tid >> 7;                          // k in [32*khalf, 32*khalf + 32)
+        float uq[FMAX];
+        auto load_u = [&](long long tile) {
+            const long long row = tile * TR + r;
+#pragma unroll
+            for (int q = 0; q < FMAX; ++q) uq[q] = (q < Fin && row < rows) ? __ldg(u + (size_t)row * Fin + q) : 0.f;
+        };
         auto fill = [&](long long tile, int n) {
             if (n >= 1) tc::mbar_wait(a_empty, (uint32_t)((n - 1) & 1));
-            const long long row = tile * TR + r;
-            float uq[MAXF];
-            const bool ok = row < rows;
-            for (int q = 0; q < Fin; ++q) uq[q] = ok ? __ldg(u + (size_t)row * Fin + q) : 0.f;
+            const bool ok = tile * TR + r < rows;
 #pragma unroll
             for (int c4 = 0; c4 < 8; ++c4) {
                 const int k0 = khalf * 32 + c4 * 4;
                 float4 a = *reinterpret_cast<const float4*>(bts + k0);
-                for (int q = 0; q < Fin; ++q) {
-                    const float4 w = *reinterpret_cast<const float4*>(WtS + q * H + k0);
-                    a.x = fmaf(uq[q], w.x, a.x); a.y = fmaf(uq[q], w.y, a.y); a.z = fmaf(uq[q], w.z, a.z); a.w = fmaf(uq[q], w.w, a.w);
+#pragma unroll
+                for (int q = 0; q < FMAX; ++q) {
+                    if (q < Fin) {
+                        const float4 w = *reinterpret_cast<const float4*>(WtS + q * H + k0);
+                        a.x = fmaf(uq[q], w.x, a.x); a.y = fmaf(uq[q], w.y, a.y); a.z = fmaf(uq[q], w.z, a.z); a.w = fmaf(uq[q], w.w, a.w);
+                    }
                 }
                 const float xv[4] = {ok ? fmaxf(a.x, 0.f) : 0.f, ok ? fmaxf(a.y, 0.f) : 0.f, ok ? fmaxf(a.z, 0.f) : 0.f, ok ? fmaxf(a.w, 0.f) : 0.f};
                 float4 hi, lo;
@@ -130,26 +142,33 @@ lstm_xproj_tc_kernel(const float* __restrict__ u, const float* __restrict__ Wt, 
             tc::fence_async_smem();
             tc::mbar_arrive(a_full);
         };
+        float* P = patch + warp * 32 * SST;
         auto epilogue = [&](long long tile, int n) {
             const int acc = n & 1, use = n >> 1;
             tc::mbar_wait(&acc_done[acc], (uint32_t)(use & 1));
             tc::fence_after_sync();
-            const int rr = 32 * (warp & 3) + lane, c_base = (warp >> 2) * 128;      // warps 0-3: columns 0..127, 4-7: 128..255
-            const long long row = tile * TR + rr;
+            const int rbase = 32 * (warp & 3), c_base = (warp >> 2) * 128;          // warps 0-3: columns 0..127, 4-7: 128..255
 #ifdef B200RL_EMUL
-            const int addr_lane = rr;
+            const int addr_lane = rbase + lane;
 #else
-            const int addr_lane = 32 * (warp & 3);
+            const int addr_lane = rbase;
 #endif
+            const int wr = lane >> 4, wc = lane & 15;                                // store role: 2 rows x 16 columns per instruction
             for (int c0 = c_base; c0 < c_base + 128; c0 += 32) {
                 float v[32];
                 tc::tmem_ld32(tc::tmem_addr(tmem, addr_lane, acc * G + c0), v);
-                if (row < rows) {
-                    float* dst = xproj + (size_t)row * G + c0;
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float4 b = *reinterpret_cast<const float4*>(bsum + c0 + i);
-                        *reinterpret_cast<float4*>(dst + i) = make_float4(v[i] + b.x, v[i + 1] + b.y, v[i + 2] + b.z, v[i + 3] + b.w);
+                for (int hseg = 0; hseg < 2; ++hseg) {
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < SC; ++i) P[lane * SST + i] = v[hseg * SC + i];
+                    __syncwarp();
+                    const int col = c0 + hseg * SC + wc;
+                    const float bias = bsum[col];
+#pragma unroll 8
+                    for (int rr = 0; rr < 32; rr += 2) {
+                        const long long row = tile * TR + rbase + rr + wr;
+                        if (row < rows) xproj[(size_t)row * G + col] = P[(rr + wr) * SST + wc] + bias;
                     }
                 }
             }
@@ -158,8 +177,10 @@ lstm_xproj_tc_kernel(const float* __restrict__ u, const float* __restrict__ Wt, 
         };
         int n = 0;
         long long prev = -1;
+        if ((long long)blockIdx.x < ntiles) load_u(blockIdx.x);
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++n) {
             fill(tile, n);
+            if (tile + gridDim.x < ntiles) load_u(tile + gridDim.x);
             if (prev >= 0) epilogue(prev, n - 1);
             prev = tile;
         }
@@ -176,12 +197,27 @@ int launch_xproj_tc(const float* u, const float* Wt, const float* bt, const floa
     const long long rows = (long long)B * T;
     const long long ntiles = (rows + xpk::TR - 1) / xpk::TR;
     const size_t smem = xproj_smem_bytes(Fin);
-#ifndef B200RL_EMUL
-    cudaError_t e = cudaFuncSetAttribute(lstm_xproj_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return set_error("lstm_fwd(xproj): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
-#endif
     const int grid = (int)(ntiles < sms ? ntiles : sms);
-    B200RL_LAUNCH(lstm_xproj_tc_kernel, grid, xpk::NT, smem, stream, u, Wt, bt, W_ih, b_ih, b_hh, xproj, rows, Fin);
+#ifndef B200RL_EMUL
+#define B200RL_XPROJ_ATTR(F)                                                                                             \
+    {                                                                                                                    \
+        cudaError_t e = cudaFuncSetAttribute(lstm_xproj_tc_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return set_error("lstm_fwd(xproj): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e)); \
+    }
+#else
+#define B200RL_XPROJ_ATTR(F)
+#endif
+    if (Fin <= 4) {
+        B200RL_XPROJ_ATTR(4)
+        B200RL_LAUNCH(lstm_xproj_tc_kernel<4>, grid, xpk::NT, smem, stream, u, Wt, bt, W_ih, b_ih, b_hh, xproj, rows, Fin);
+    } else if (Fin <= 8) {
+        B200RL_XPROJ_ATTR(8)
+        B200RL_LAUNCH(lstm_xproj_tc_kernel<8>, grid, xpk::NT, smem, stream, u, Wt, bt, W_ih, b_ih, b_hh, xproj, rows, Fin);
+    } else {
+        B200RL_XPROJ_ATTR(32)
+        B200RL_LAUNCH(lstm_xproj_tc_kernel<32>, grid, xpk::NT, smem, stream, u, Wt, bt, W_ih, b_ih, b_hh, xproj, rows, Fin);
+    }
+#undef B200RL_XPROJ_ATTR
     return check_launch("lstm_fwd(xproj)");
 }
 
