@@ -22,6 +22,16 @@
 
 namespace b200rl {
 
+// phase timeline for tools/dx_prof.cu (never compiled into the product library)
+#ifdef B200RL_DXPROF
+__device__ unsigned long long g_dxprof[16];
+#define DXP_INIT unsigned long long dxp_prev = clock64();
+#define DXP(i) do { if (tid == 0) { unsigned long long now_ = clock64(); atomicAdd(&g_dxprof[i], now_ - dxp_prev); dxp_prev = now_; } } while (0)
+#else
+#define DXP_INIT
+#define DXP(i) do { } while (0)
+#endif
+
 namespace dxk {
 constexpr int H = 64, G = 256, NP = 256, NT = NP + 32;     // 8 producer warps + the MMA issuer warp
 constexpr int TR = 128;                     // rows per tile (UMMA M)
@@ -29,8 +39,11 @@ constexpr int CK = 32;                      // gate columns per chunk (4 MMA K-s
 constexpr int NCH = G / CK;                 // 8 chunks per tile
 constexpr int W_LBO = 128, W_SBO = (G / 4) * 128;          // B: 64 core matrices along K per 8-k group (8192)
 constexpr int W_BYTES = (H / 8) * W_SBO;                   // 65536 per hi / lo
-constexpr int D_LBO = 128, D_SBO = (CK / 4) * 128;         // A: 8 core matrices along K per 8-row group (1024)
-constexpr int D_BYTES = (TR / 8) * D_SBO;                  // 16384 per hi / lo
+// A: 8 core matrices along K per 8-row group.  K-adjacent core matrices sit 144 bytes apart (128 + 16) so that the
+// eight float4 of one row's 128-byte global segment -- one quarter-warp -- land in eight different bank groups:
+// full-line global requests AND conflict-free 16-byte stores.
+constexpr int D_LBO = 144, D_SBO = (CK / 4) * D_LBO;       // 1152
+constexpr int D_BYTES = (TR / 8) * D_SBO;                  // 18432 per hi / lo
 constexpr int STAGE = 2 * D_BYTES;                         // 32 KB
 constexpr int NSTAGE = 2;
 constexpr int SS = H + 1;                                  // epilogue tile row stride (floats)
@@ -64,7 +77,6 @@ lstm_dx_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ u,
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool producer = warp < NP / 32;
-    const int r_in = lane & 7, q4 = lane >> 3;
 
     // ---- one-time: W_ih -> TF32 hi/lo, K-major B operand: elem(k, p) = W_ih[(p&3)*64 + (p>>2)][k]
     // lanes cover one 128-byte core matrix (8 k x 4 p) per store -> conflict-free
@@ -80,8 +92,8 @@ lstm_dx_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ u,
     for (int i = tid; i < Fin * H; i += NT) { int q = i / H, j = i % H; WtS[i] = Wt[j * Fin + q]; WtR[j * Fin + q] = Wt[j * Fin + q]; }
     if (tid < H) bts[tid] = bt[tid];
     if (tid == 0) {
-        for (int i = 0; i < NSTAGE; ++i) { tc::mbar_init(&full[i], NP); tc::mbar_init(&empty[i], 1); }
-        tc::mbar_init(tile_done, 1); tc::mbar_init(tmem_free, NP);
+        for (int i = 0; i < NSTAGE; ++i) { tc::mbar_init(&full[i], NP / 32); tc::mbar_init(&empty[i], 1); }
+        tc::mbar_init(tile_done, 1); tc::mbar_init(tmem_free, NP / 32);
         tc::fence_mbar_init();
     }
     if (warp == NP / 32) tc::tmem_alloc(tmem_slot, 64);
@@ -134,7 +146,7 @@ lstm_dx_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ u,
     auto issue_loads = [&](float4 (&dst)[4], long long tile, int ch) {
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) {
-            const int r = (warp * 2 + (i4 & 1)) * 8 + r_in, c4 = ch * (CK / 4) + (i4 >> 1) * 4 + q4;
+            const int r = warp * 16 + i4 * 4 + (lane >> 3), c4 = ch * (CK / 4) + (lane & 7);
             const long long row = tile * TR + r;
             dst[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (tile < ntiles && row < rows) dst[i4] = *reinterpret_cast<const float4*>(dpre + (size_t)row * G + c4 * 4);
@@ -145,6 +157,7 @@ lstm_dx_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ u,
 
     int g = 0;                                            // chunk counter across tiles (stage ring position)
     int tdone = 0;                                        // tiles completed by this CTA (tile-done parity)
+    DXP_INIT
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tdone) {
 #pragma unroll
         for (int ch = 0; ch < NCH; ++ch, ++g) {
@@ -155,23 +168,31 @@ lstm_dx_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ u,
             for (int i4 = 0; i4 < 4; ++i4) cd[i4] = dv[ch % RING][i4];
             if (ch + AHEAD < NCH) issue_loads(dv[(ch + AHEAD) % RING], tile, ch + AHEAD);
             else issue_loads(dv[(ch + AHEAD) % RING], tile + gridDim.x, ch + AHEAD - NCH);
+#ifdef B200RL_DXPROF
+            if (cd[0].x == 1234.5f || cd[1].x == 1234.5f || cd[2].x == 1234.5f || cd[3].x == 1234.5f) acc_bt += 1.f;
+            DXP(8);
+#endif
             if (use >= 1) tc::mbar_wait(&empty[buf], (uint32_t)((use - 1) & 1));
+            DXP(9);
 #pragma unroll
             for (int i4 = 0; i4 < 4; ++i4) {
-                const int r8 = warp * 2 + (i4 & 1), c4l = (i4 >> 1) * 4 + q4;
+                const int r = warp * 16 + i4 * 4 + (lane >> 3), c4l = lane & 7;
                 float4 hi, lo;
                 tc::split_tf32(cd[i4].x, hi.x, lo.x); tc::split_tf32(cd[i4].y, hi.y, lo.y);
                 tc::split_tf32(cd[i4].z, hi.z, lo.z); tc::split_tf32(cd[i4].w, hi.w, lo.w);
-                const int o = r_in * 16 + r8 * D_SBO + c4l * D_LBO;
+                const int o = (r & 7) * 16 + (r >> 3) * D_SBO + c4l * D_LBO;
                 *reinterpret_cast<float4*>(D_hi + o) = hi;
                 *reinterpret_cast<float4*>(D_lo + o) = lo;
             }
             tc::fence_async_smem();
-            tc::mbar_arrive(&full[buf]);
+            tc::mbar_arrive_warp(&full[buf]);
+            DXP(10);
         }
         // ---- epilogue of this tile
+        DXP(0);
         tc::mbar_wait(tile_done, (uint32_t)(tdone & 1));
         tc::fence_after_sync();
+        DXP(1);
         {
             const int r = 32 * (warp & 3) + lane, c0 = (warp >> 2) * 32;         // row, first of 32 columns
             const long long row = tile * TR + r;
@@ -187,6 +208,10 @@ lstm_dx_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ u,
             float uq[FMAX];                                   // this row's torso inputs, loaded once
 #pragma unroll
             for (int q = 0; q < FMAX; ++q) uq[q] = (ok && q < Fin) ? __ldg(ur + q) : 0.f;
+#ifdef B200RL_DXPROF
+            if (uq[0] == 1234.5f) dxv[0] = 0.f;
+            DXP(2);
+#endif
 #pragma unroll 4
             for (int i = 0; i < 32; ++i) {
                 const int k = c0 + i;
@@ -201,8 +226,10 @@ lstm_dx_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ u,
             }
         }
         tc::fence_before_sync();
-        tc::mbar_arrive(tmem_free);                        // accumulator drained: the issuer may start the next tile
+        tc::mbar_arrive_warp(tmem_free);                        // accumulator drained: the issuer may start the next tile
+        DXP(3);
         tc::named_bar_sync(1, NP);
+        DXP(4);
         {
             float sb = 0.f;
 #pragma unroll 4
@@ -214,6 +241,7 @@ lstm_dx_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ u,
             }
             acc_bt += sb;
         }
+        DXP(5);
         if (du != nullptr && tid < TR) {
             const long long row = tile * TR + tid;
             if (row < rows)
@@ -223,7 +251,9 @@ lstm_dx_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ u,
                     du[(size_t)row * Fin + q] = s;
                 }
         }
+        DXP(6);
         tc::named_bar_sync(1, NP);                         // S / Us (stage memory) free for the next tile
+        DXP(7);
     }
     // ---- combine the four row quarters and write this CTA's slab entries
     float* red = reinterpret_cast<float*>(stage0);         // [4][64][Fin+1]

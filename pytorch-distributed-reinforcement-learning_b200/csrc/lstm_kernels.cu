@@ -569,11 +569,16 @@ head_fwd_kernel(const float* __restrict__ h, const float* __restrict__ W, const 
 }
 
 // ======================================================================= backward (serial)
-constexpr int BS = 32;       // backward D_T row stride: 128-byte aligned rows -> one wavefront per LDS.128
-// shared (floats): WhT[256][64] | DT[2][256][BS] | WhS[NH][64] | dHd[2][32][NH]
+// The CTA is two independent halves of 128 threads x 16 sequences (as the recurrent forward): the halves
+// share the read-only W_hh / W_head tiles and synchronise only with themselves (named barriers), so one
+// half's cell phase (MUFU, global loads/stores) overlaps the other's dh GEMM (FFMA2 + LDS).
+// shared (floats): WhT[256][64] | DT[half][2][256*16] | WhS[NH][64] | dHd[half][2][16][NH] | Rp[half][4][16*64]
 static inline size_t bwd_smem_bytes(int NH) {
-    return sizeof(float) * (size_t)(G * H + 2 * G * BS + NH * H + 2 * TM * NH + 4 + 4 * TM * H);
+    return sizeof(float) * (size_t)(G * H + 2 * 2 * G * HM + NH * H + 2 * 2 * HM * NH + 4 + 2 * 4 * HM * H);
 }
+// D tile address of gate column p (16 rows each): neighbouring units j, j+1 (p differs by 4) land in
+// different 64-byte halves of a 128-byte line, so a quarter-warp's cell-phase stores are conflict-free
+__device__ __forceinline__ int bwd_daddr(int p) { return (p >> 1) * 32 + (((p & 1) ^ ((p >> 2) & 1)) * HM); }
 
 __global__ void __launch_bounds__(NT, 1)
 lstm_bwd_kernel(const float* __restrict__ dhead, const float* __restrict__ W_head,
@@ -581,39 +586,42 @@ lstm_bwd_kernel(const float* __restrict__ dhead, const float* __restrict__ W_hea
                 const float* __restrict__ c_sav, const float* __restrict__ cx0,
                 int B, int T, int NH) {
     B200RL_DYN_SMEM(float, smem);
-    float* WhT = smem;                       // WhT[p*64 + k] = W_hh[n(p)][k],  p = j*4+g, n = g*64+j
-    float* DT = WhT + G * H;                 // DT[buf][p*BS + r]
-    float* WhS = DT + 2 * G * BS;            // WhS[c*64 + k]
-    float* dHd = WhS + NH * H;               // dHd[buf][r*NH + c]
-    float* Rp = dHd + 2 * TM * NH + ((4 - ((2 * TM * NH) & 3)) & 3);   // Rp[slice][row*64 + k]: split-K partial sums (16-byte aligned)
-    const int tid = threadIdx.x;
-    const MapR m;
-    // dh GEMM ownership: K (the 256 gate columns) is split 4 ways over warp pairs; within a slice a thread owns
-    // 4 rows x 8 k: 12 shared-memory wavefronts per 32 FMA instead of 6 per 8 (the kernel is wavefront-bound)
-    const int gs = tid >> 6, grg = tid & 7, gk0 = (((tid >> 5) & 1) * 4 + ((tid & 31) >> 3)) * 8;
+    const int tid = threadIdx.x, hf = tid >> 7, ht = tid & 127, lane = tid & 31, hw = ht >> 5;
+    const int nD = HM * NH;
+    float* WhT = smem;                                   // WhT[p*64 + k] = W_hh[n(p)][k],  p = j*4+g, n = g*64+j
+    float* DT = WhT + G * H + hf * 2 * G * HM;           // DT[buf][daddr(p) + r]
+    float* WhS = WhT + G * H + 2 * 2 * G * HM;           // WhS[c*64 + k]
+    float* dHd = WhS + NH * H + hf * 2 * nD;             // dHd[buf][r*NH + c]
+    float* Rp = WhS + NH * H + 2 * 2 * nD;
+    Rp += ((4 - ((NH * H + 2 * 2 * nD) & 3)) & 3) + hf * 4 * HM * H;   // Rp[slice][row*64 + k']: split-K partial sums (16-byte aligned)
+    // cell ownership: 4 rows x 2 units
+    const int r0 = (lane & 3) * 4, j0 = hw * 8 + (lane >> 2), j1 = j0 + 32;
+    // dh GEMM ownership: K (the 256 gate columns) is split over the half's 4 warps; within a slice a thread owns
+    // 4 rows x 8 k: 12 shared-memory wavefronts per 32 FMA (the kernel is wavefront-bound)
+    const int gs = hw, grg = lane & 3, kq = lane >> 2, gk0 = kq * 8;
     {
         const int n = tid, g = n >> 6, j = n & 63, p = j * 4 + g;
         for (int k4 = 0; k4 < H; k4 += 4) st4(WhT + p * H + k4, ld4(W_hh + (size_t)n * H + k4));
         for (int i = tid; i < NH * H; i += NT) WhS[i] = W_head[i];
     }
+    __syncthreads();
     const int ntiles = (B + TM - 1) / TM;
-    const int nD = TM * NH;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int b0 = tile * TM;
-        __syncthreads();
+        const int b0 = tile * TM + hf * HM;
+        tc::named_bar_sync(1 + hf, 128);
         int brow[4]; bool bok[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { int b = b0 + m.r0 + i; bok[i] = b < B; brow[i] = bok[i] ? b : B - 1; }
+        for (int i = 0; i < 4; ++i) { int b = b0 + r0 + i; bok[i] = b < B; brow[i] = bok[i] ? b : B - 1; }
         // software pipeline (global latency must never sit on the per-step critical path):
         // registers hold gates_t, c_t, c_{t-1} for the step being processed; the loads of
         // gates_{t-1} and c_{t-2} are issued at the top of step t and first used one full step
         // later; the dhead tile of step t-2 is loaded at step t and parked in shared memory
         // at the end of step t-1.
-        constexpr int NPF = (TM * B200RL_MAX_HEADS + NT - 1) / NT;
+        constexpr int NPF = (HM * B200RL_MAX_HEADS + 127) / 128;
         auto load_dhead = [&](int t, float (&dst)[NPF]) {
 #pragma unroll
             for (int e = 0; e < NPF; ++e) {
-                int i = e * NT + tid;
+                int i = e * 128 + ht;
                 if (i < nD) {
                     int r = i / NH, c = i % NH; int b = b0 + r < B ? b0 + r : B - 1;
                     dst[e] = __ldg(dhead + ((size_t)b * T + t) * NH + c);
@@ -624,7 +632,7 @@ lstm_bwd_kernel(const float* __restrict__ dhead, const float* __restrict__ W_hea
             float* Hd = dHd + (t & 1) * nD;
 #pragma unroll
             for (int e = 0; e < NPF; ++e) {
-                int i = e * NT + tid;
+                int i = e * 128 + ht;
                 if (i < nD) Hd[i] = src[e];
             }
         };
@@ -641,17 +649,17 @@ lstm_bwd_kernel(const float* __restrict__ dhead, const float* __restrict__ W_hea
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
-                const int j = jj ? m.j1 : m.j0;
+                const int j = jj ? j1 : j0;
                 const size_t o = ((size_t)brow[i] * T + (T - 1)) * H + j;
                 dc[i][jj] = 0.f; dhr[i][jj] = 0.f;
                 ccur[i][jj] = c_sav[o];
                 cprev[i][jj] = T > 1 ? c_sav[o - H] : cx0[(size_t)brow[i] * H + j];
                 gcur[i][jj] = ld4(gates + o * 4);
             }
-        __syncthreads();
+        tc::named_bar_sync(1 + hf, 128);
 
         for (int t = T - 1; t >= 0; --t) {
-            float* Dc = DT + (t & 1) * G * BS;
+            float* Dc = DT + (t & 1) * G * HM;
             // (a) issue loads whose first use is one full step away
             float4 gnx[4][2]; float cpp[4][2];
             float dh_new[NPF];
@@ -659,7 +667,7 @@ lstm_bwd_kernel(const float* __restrict__ dhead, const float* __restrict__ W_hea
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int jj = 0; jj < 2; ++jj) {
-                    const int j = jj ? m.j1 : m.j0;
+                    const int j = jj ? j1 : j0;
                     gnx[i][jj] = make_float4(0.f, 0.f, 0.f, 0.f);
                     cpp[i][jj] = 0.f;
                     if (t > 0) gnx[i][jj] = ld4(gates + (((size_t)brow[i] * T + (t - 1)) * H + j) * 4);
@@ -674,9 +682,9 @@ lstm_bwd_kernel(const float* __restrict__ dhead, const float* __restrict__ W_hea
             for (int i = 0; i < 4; ++i) {
 #pragma unroll
                 for (int jj = 0; jj < 2; ++jj) {
-                    const int j = jj ? m.j1 : m.j0;
+                    const int j = jj ? j1 : j0;
                     float dh = dhr[i][jj];
-                    for (int c = 0; c < NH; ++c) dh = fmaf(dH[(m.r0 + i) * NH + c], WhS[c * H + j], dh);
+                    for (int c = 0; c < NH; ++c) dh = fmaf(dH[(r0 + i) * NH + c], WhS[c * H + j], dh);
                     const float4 gt = gcur[i][jj];          // i, f, g, o (post-activation)
                     const float tc = tanh_(ccur[i][jj]);
                     const float d_o = dh * tc;
@@ -691,16 +699,16 @@ lstm_bwd_kernel(const float* __restrict__ dhead, const float* __restrict__ W_hea
             // r-minor tile for the dh GEMM: one float4 (4 rows) per gate column
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
-                float* d = Dc + ((jj ? m.j1 : m.j0) * 4) * BS + m.r0;
-                st4(d + 0 * BS, make_float4(dp[0][jj].x, dp[1][jj].x, dp[2][jj].x, dp[3][jj].x));
-                st4(d + 1 * BS, make_float4(dp[0][jj].y, dp[1][jj].y, dp[2][jj].y, dp[3][jj].y));
-                st4(d + 2 * BS, make_float4(dp[0][jj].z, dp[1][jj].z, dp[2][jj].z, dp[3][jj].z));
-                st4(d + 3 * BS, make_float4(dp[0][jj].w, dp[1][jj].w, dp[2][jj].w, dp[3][jj].w));
+                const int p0 = (jj ? j1 : j0) * 4;
+                st4(Dc + bwd_daddr(p0 + 0) + r0, make_float4(dp[0][jj].x, dp[1][jj].x, dp[2][jj].x, dp[3][jj].x));
+                st4(Dc + bwd_daddr(p0 + 1) + r0, make_float4(dp[0][jj].y, dp[1][jj].y, dp[2][jj].y, dp[3][jj].y));
+                st4(Dc + bwd_daddr(p0 + 2) + r0, make_float4(dp[0][jj].z, dp[1][jj].z, dp[2][jj].z, dp[3][jj].z));
+                st4(Dc + bwd_daddr(p0 + 3) + r0, make_float4(dp[0][jj].w, dp[1][jj].w, dp[2][jj].w, dp[3][jj].w));
             }
             // (d) park the dhead tile of step t-1 (loaded a step ago); visible after the barrier
             if (t > 0) park_dhead(t - 1, dh_next);
-            __syncthreads();
-            // (c) dh_rec[r][k] = sum_p dpre[r][p] W_hh[n(p)][k]        (32 x 64 x 256 per CTA)
+            tc::named_bar_sync(1 + hf, 128);
+            // (c) dh_rec[r][k] = sum_p dpre[r][p] W_hh[n(p)][k]        (16 x 64 x 256 per half)
             if (t > 0) {
                 f2 acc[4][4];
 #pragma unroll
@@ -710,7 +718,7 @@ lstm_bwd_kernel(const float* __restrict__ dhead, const float* __restrict__ W_hea
 #pragma unroll 4
                 for (int pp = 0; pp < G / 4; ++pp) {
                     const int p = gs * (G / 4) + pp;
-                    const float4 d = ld4(Dc + p * BS + grg * 4);
+                    const float4 d = ld4(Dc + bwd_daddr(p) + grg * 4);
                     f2 w0, w1, w2, w3;
                     f2_ld2(WhT + p * H + gk0, w0, w1);
                     f2_ld2(WhT + p * H + gk0 + 4, w2, w3);
@@ -721,23 +729,28 @@ lstm_bwd_kernel(const float* __restrict__ dhead, const float* __restrict__ W_hea
                         f2_fma(acc[i][2], dv[i], w2); f2_fma(acc[i][3], dv[i], w3);
                     }
                 }
-                float* Rs = Rp + gs * TM * H;
+                // exchange through Rp, 16-byte granules XOR-swizzled by the row group and written in swapped order by
+                // odd k-octets: both the stores here and the scalar reads below are bank-conflict-free (unswizzled,
+                // this exchange was 41 % of all shared-memory wavefronts, ncu r1g)
+                float* Rs = Rp + gs * HM * H;
+                const bool odd = kq & 1;
+                const int oa = (gk0 + (odd ? 4 : 0)) ^ (grg << 3), ob = (gk0 + (odd ? 0 : 4)) ^ (grg << 3);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    // columns XOR-swizzled by the row group (16-byte granules): without it the eight row groups of a
-                    // quarter-warp hit one bank group on both sides of the exchange (ncu r1g: 41 % of all wavefronts)
                     float* dst = Rs + (grg * 4 + i) * H;
-                    st4(dst + (gk0 ^ (grg << 2)), make_float4(f2_lo(acc[i][0]), f2_hi(acc[i][0]), f2_lo(acc[i][1]), f2_hi(acc[i][1])));
-                    st4(dst + ((gk0 + 4) ^ (grg << 2)), make_float4(f2_lo(acc[i][2]), f2_hi(acc[i][2]), f2_lo(acc[i][3]), f2_hi(acc[i][3])));
+                    const float4 lo4 = make_float4(f2_lo(acc[i][0]), f2_hi(acc[i][0]), f2_lo(acc[i][1]), f2_hi(acc[i][1]));
+                    const float4 hi4 = make_float4(f2_lo(acc[i][2]), f2_hi(acc[i][2]), f2_lo(acc[i][3]), f2_hi(acc[i][3]));
+                    st4(dst + oa, odd ? hi4 : lo4);
+                    st4(dst + ob, odd ? lo4 : hi4);
                 }
-                __syncthreads();
+                tc::named_bar_sync(1 + hf, 128);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
                     for (int sl = 0; sl < 4; ++sl) {
-                        s0 += Rp[sl * TM * H + (m.r0 + i) * H + (m.j0 ^ m.r0)];       // r0 = 4 * row group
-                        s1 += Rp[sl * TM * H + (m.r0 + i) * H + (m.j1 ^ m.r0)];
+                        s0 += Rp[sl * HM * H + (r0 + i) * H + (j0 ^ (r0 << 1))];       // r0 << 1 = row group << 3
+                        s1 += Rp[sl * HM * H + (r0 + i) * H + (j1 ^ (r0 << 1))];
                     }
                     dhr[i][0] = s0; dhr[i][1] = s1;
                 }

@@ -65,9 +65,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
 }
+// One arrival per WARP (barrier count = participating warps): 32 per-thread arrivals on one mbarrier serialise
+// (measured: 256 arrivals cost ~1.3K cycles per stage in lstm_dx_tc, tools/dx_prof.cu).  Every lane must have
+// executed its own proxy fence before the call.
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
 // barrier among a subset of the CTA's warps (id 1..15; `nthreads` a multiple of 32)
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+#ifdef B200RL_PROBE_NOFENCE      // timing experiment only (tools/dx_prof.cu): results are not valid without the fence
+__device__ __forceinline__ void fence_async_smem() {}
+#else
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -130,6 +141,10 @@ inline void mbar_arrive(uint64_t* bar) {
     uint32_t pending = (uint32_t)(v & 0xffff) - 1, count = (uint32_t)((v >> 16) & 0xffff), phase = (uint32_t)((v >> 32) & 1);
     if (pending == 0) { pending = count; phase ^= 1; }
     *bar = (uint64_t)pending | ((uint64_t)count << 16) | ((uint64_t)phase << 32);
+}
+inline void mbar_arrive_warp(uint64_t* bar) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
 }
 inline void mbar_wait(uint64_t* bar, uint32_t parity) {
     for (;;) {

@@ -14,15 +14,16 @@
 // are split on the fly, v = hi + lo with hi, lo exactly representable in TF32, and three
 // MMAs are issued per K-step: hi*hi + hi*lo + lo*hi (the dropped lo*lo term is ~2^-22).
 //
-// Data path per stage (16 rows = 2 K-steps of 8): all 256 threads load fp32 rows from HBM
-// (16-byte loads, 2 full sectors per row segment), recompute x, split hi/lo and scatter the
-// values with 4-byte stores into the canonical no-swizzle K-major UMMA layout, where the
-// contraction index (the row r) is the fast one:
+// Data path per stage (16 rows = 2 K-steps of 8): all 256 threads load fp32 rows from HBM --
+// a quarter-warp takes one full 128-byte line of a row, a warp 4 rows (requests that touch half
+// lines of 8 rows ran at 2.3 TB/s: the SM's outstanding-request budget, not bytes, was the limit,
+// tools/dx_prof.cu) -- recompute x, split hi/lo and scatter the values with 4-byte stores into the
+// canonical no-swizzle K-major UMMA layout, where the contraction index (the row r) is the fast one:
 //     elem(mn, r) at (mn%8)*16 + (mn/8)*SBO + (r%4)*4 + (r/4)*LBO        [bytes]
 // (measured on B200: kind::tf32 with MN-major descriptors returns zeros, K-major is exact
 // -- tools/tc_probe.cu -- so the tile is transposed on the way into shared memory).
-// LBO = 144 B and SBO = 672 B are chosen = 16 B / 32 B modulo 128 B, which makes the 32 lanes
-// of every scatter store hit 32 distinct banks.
+// SBO = 528 B (= 16 B modulo 128 B) makes the 32 lanes of every scatter store (4 rows x 8 float4
+// columns, one element each) hit 32 distinct banks.
 //
 // Warp-specialised pipeline (no CTA-wide barrier inside the loop): warps 0-7 are PRODUCERS
 // (load / split / scatter a stage, fence.proxy.async, arrive on full[stage]); warp 8 is the MMA
@@ -38,19 +39,19 @@ namespace b200rl {
 namespace wtc {
 constexpr int H = 64, G = 256, KC = 128, NP = 256, NT = NP + 32;   // producers + issuer warp
 constexpr int SR = 16;                          // rows per stage (2 MMA K-steps of 8)
-constexpr int NSTAGE = 3;
-constexpr int LBO = 144;                        // K direction: next core matrix (4 rows)      = 16 B mod 128 B
-constexpr int SBO = 672;                        // MN direction: next group of 8 mn (4 core matrices + skew) = 32 B mod 128 B
-constexpr int A_TILE = (KC / 8) * SBO;          // 10752
-constexpr int D_TILE = (G / 8) * SBO;           // 21504
-constexpr int STAGE = 2 * A_TILE + 2 * D_TILE;  // A_hi | A_lo | D_hi | D_lo = 64512 B
+constexpr int NSTAGE = 4;
+constexpr int LBO = 128;                        // K direction: next core matrix (4 rows)
+constexpr int SBO = 528;                        // MN direction: next group of 8 mn (4 core matrices + 16 B skew) = 16 B mod 128 B
+constexpr int A_TILE = (KC / 8) * SBO;          // 8448
+constexpr int D_TILE = (G / 8) * SBO;           // 16896
+constexpr int STAGE = 2 * A_TILE + 2 * D_TILE;  // A_hi | A_lo | D_hi | D_lo = 50688 B
 constexpr int MAXF = 32;
 static_assert((SR / 4 - 1) * LBO + 128 <= SBO, "core matrices of one mn-group must fit below SBO");
 __device__ __forceinline__ int koff(int mn, int r) { return (mn & 7) * 16 + (mn >> 3) * SBO + (r & 3) * 4 + (r >> 2) * LBO; }
 }  // namespace wtc
 
 static inline size_t wgrad_tc_smem_bytes(int Fin) {
-    return wtc::NSTAGE * (size_t)wtc::STAGE + sizeof(float) * (size_t)(Fin * wtc::H + wtc::H) + 64;
+    return wtc::NSTAGE * (size_t)wtc::STAGE + sizeof(float) * (size_t)(Fin * wtc::H + wtc::H) + 96;
 }
 
 __global__ void __launch_bounds__(wtc::NT, 1)
@@ -70,12 +71,12 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool producer = warp < NP / 32;
-    const int r_in = lane & 7, q4 = lane >> 3;                       // row inside a core matrix, float4 column
+    const int rq = lane >> 3, cq = lane & 7;                         // row inside a group of 4, float4 inside a 128-byte line
 
     for (int i = tid; i < Fin * H; i += NT) { int q = i / H, j = i % H; WtS[i] = Wt[j * Fin + q]; }
     if (tid < H) bts[tid] = bt[tid];
     if (tid == 0) {
-        for (int i = 0; i < NSTAGE; ++i) { tc::mbar_init(&full[i], NP); tc::mbar_init(&empty[i], 1); }
+        for (int i = 0; i < NSTAGE; ++i) { tc::mbar_init(&full[i], NP / 32); tc::mbar_init(&empty[i], 1); }
         tc::mbar_init(done, 1);
         tc::fence_mbar_init();
     }
@@ -88,8 +89,7 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
 
     const long long rows = (long long)B * T;
     const long long nstages = (rows + SR - 1) / SR;
-    float4 dbacc[2];
-    dbacc[0] = make_float4(0.f, 0.f, 0.f, 0.f); dbacc[1] = dbacc[0];
+    float4 dbacc = make_float4(0.f, 0.f, 0.f, 0.f);               // bias gradient of gate columns (warp*8 + cq)*4 .. +3
 
     // Register-staged loads: a ring of 4 register sets; the HBM reads of stage i+3 are issued
     // before stage i is split and scattered, so their latency overlaps three stages of work.
@@ -101,14 +101,13 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
         const bool live = stg < nstages;
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) {
-            const int r8 = i4 & 1, hh = i4 >> 1;
-            const int c4 = (warp * 2 + hh) * 4 + q4;
-            const long long row = row0 + r8 * 8 + r_in;
+            const int c4 = warp * 8 + cq;
+            const long long row = row0 + i4 * 4 + rq;
             R.d[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (live && row < rows) R.d[i4] = *reinterpret_cast<const float4*>(dpre + (size_t)row * G + c4 * 4);
         }
-        const int c4 = (warp >> 1) * 4 + q4;
-        const long long row = row0 + (warp & 1) * 8 + r_in;
+        const int c4 = (warp & 1) * 8 + cq;
+        const long long row = row0 + (warp >> 1) * 4 + rq;
         R.h = make_float4(0.f, 0.f, 0.f, 0.f);
         R.ok = live && row < rows;
 #pragma unroll
@@ -132,14 +131,13 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
         const long long row0 = st * SR;
         if (use >= 1) tc::mbar_wait(&empty[buf], (uint32_t)((use - 1) & 1));  // MMAs of the previous use of this buffer are done
 
-        // ---- D tile: 16 rows x 64 float4.  Thread: rows r8*8 + r_in (r8 = 0,1), float4 columns c4(hh) (hh = 0,1)
+        // ---- D tile: 16 rows x 64 float4.  Thread: rows i4*4 + rq, float4 column warp*8 + cq
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) {
-            const int r8 = i4 & 1, hh = i4 >> 1;
-            const int c4 = (warp * 2 + hh) * 4 + q4;
-            const int r = r8 * 8 + r_in;
+            const int c4 = warp * 8 + cq;
+            const int r = i4 * 4 + rq;
             const float4 v = R.d[i4];
-            dbacc[hh].x += v.x; dbacc[hh].y += v.y; dbacc[hh].z += v.z; dbacc[hh].w += v.w;
+            dbacc.x += v.x; dbacc.y += v.y; dbacc.z += v.z; dbacc.w += v.w;
             const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -150,9 +148,9 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
                 *reinterpret_cast<float*>(D_lo + o) = lo;
             }
         }
-        // ---- A tile: [x_t (k<64) | h_{t-1} (k>=64)], 16 float4 each per row; thread: row (warp&1)*8 + r_in
+        // ---- A tile: [x_t (k<64) | h_{t-1} (k>=64)], 16 float4 each per row; thread: row (warp>>1)*4 + rq
         {
-            const int r = (warp & 1) * 8 + r_in, c4 = (warp >> 1) * 4 + q4;              // c4 in 0..15
+            const int r = (warp >> 1) * 4 + rq, c4 = (warp & 1) * 8 + cq;                // c4 in 0..15
             const long long row = row0 + r;
             float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
             const float4 hv = R.h;
@@ -191,14 +189,14 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
             }
         }
         tc::fence_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
-        tc::mbar_arrive(&full[buf]);
+        tc::mbar_arrive_warp(&full[buf]);
         ++it;
     };
 
     if (producer) {
         const long long g = gridDim.x;
         long long st = blockIdx.x;
-        issue_loads(ring[0], st); issue_loads(ring[1], st + g); issue_loads(ring[2], st + 2 * g);
+        issue_loads(ring[0], st); issue_loads(ring[1], st + g); issue_loads(ring[2], st + 2 * g);   // (ring depth 4 = NSTAGE)
         while (st < nstages) {
             issue_loads(ring[3], st + 3 * g); process(ring[0], st); st += g; if (st >= nstages) break;
             issue_loads(ring[0], st + 3 * g); process(ring[1], st); st += g; if (st >= nstages) break;
@@ -254,17 +252,16 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
             }
         }
     }
-    // ---- bias gradient: reduce the 8 row-lanes that share a float4 column
+    // ---- bias gradient: reduce the 4 row-lanes that share a float4 column
+    {
+        float4 s = dbacc;
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-        float4 s = dbacc[hh];
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
+        for (int o = 8; o < 32; o <<= 1) {
             s.x += __shfl_xor_sync(kFull, s.x, o); s.y += __shfl_xor_sync(kFull, s.y, o);
             s.z += __shfl_xor_sync(kFull, s.z, o); s.w += __shfl_xor_sync(kFull, s.w, o);
         }
-        if (r_in == 0) {
-            const int c4 = (warp * 2 + hh) * 4 + q4;       // p = c4*4 + g  ->  j = c4, n = g*64 + c4
+        if (rq == 0) {
+            const int c4 = warp * 8 + cq;                  // p = c4*4 + g  ->  j = c4, n = g*64 + c4
             const float v[4] = {s.x, s.y, s.z, s.w};
 #pragma unroll
             for (int g = 0; g < 4; ++g) { out[off_bih + g * H + c4] = v[g]; out[off_bhh + g * H + c4] = v[g]; }

@@ -73,8 +73,8 @@ lstm_xproj_tc_kernel(const float* __restrict__ u, const float* __restrict__ Wt, 
     if (tid < H) bts[tid] = bt[tid];
     if (tid < G) { const int p = tid, n = (p & 3) * 64 + (p >> 2); bsum[p] = b_ih[n] + b_hh[n]; }
     if (tid == 0) {
-        tc::mbar_init(a_full, NP); tc::mbar_init(a_empty, 1);
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_done[i], 1); tc::mbar_init(&acc_free[i], NP); }
+        tc::mbar_init(a_full, NP / 32); tc::mbar_init(a_empty, 1);
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_done[i], 1); tc::mbar_init(&acc_free[i], NP / 32); }
         tc::fence_mbar_init();
     }
     if (warp == NP / 32) tc::tmem_alloc(tmem_slot, 512);
@@ -140,7 +140,7 @@ lstm_xproj_tc_kernel(const float* __restrict__ u, const float* __restrict__ Wt, 
                 *reinterpret_cast<float4*>(A_lo + o) = lo;
             }
             tc::fence_async_smem();
-            tc::mbar_arrive(a_full);
+            tc::mbar_arrive_warp(a_full);
         };
         float* P = patch + warp * 32 * SST;
         auto epilogue = [&](long long tile, int n) {
@@ -173,7 +173,7 @@ lstm_xproj_tc_kernel(const float* __restrict__ u, const float* __restrict__ Wt, 
                 }
             }
             tc::fence_before_sync();
-            tc::mbar_arrive(&acc_free[acc]);
+            tc::mbar_arrive_warp(&acc_free[acc]);
         };
         int n = 0;
         long long prev = -1;
