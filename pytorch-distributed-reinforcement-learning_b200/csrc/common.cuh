@@ -90,6 +90,24 @@ __device__ __forceinline__ void f2_ld2(const float* p, f2& a, f2& b) { const ulo
 #endif
 }  // namespace b200rl
 
+namespace b200rl {
+// sigmoid / tanh for the LSTM cell: sigm(x) = rcp(1 + ex2(-x log2 e)) on the two MUFU approximations (ex2: 2 ulp,
+// rcp: 1 ulp; absolute error ~1e-7, far inside the rtol 1e-4 parity bar), tanh(x) = 2 sigm(2x) - 1.  Four / five
+// instructions: expf + __fdividef cost ~14 with their range handling, and the cell phase of the recurrent
+// kernels is issue-bound on exactly these (tools/fwd_prof.cu).  Saturation is exact: ex2 -> inf gives rcp -> 0.
+#ifdef B200RL_EMUL
+inline float ex2_approx(float x) { return exp2f(x); }
+inline float rcp_approx(float x) { return 1.0f / x; }
+#else
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#endif
+__device__ __forceinline__ float sigm(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh_(float x) { return fmaf(2.0f, rcp_approx(1.0f + ex2_approx(-2.8853900817779268f * x)), -1.0f); }
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+}  // namespace b200rl
+
 // Error plumbing shared by the C-ABI entry points.
 namespace b200rl {
 int set_error(const char* fmt, ...);

@@ -58,13 +58,6 @@ struct MapJ {
     }
 };
 
-// sigmoid / tanh for the cell: expf + approximate reciprocal (~2 ulp), tanh(x) = 2*sigmoid(2x) - 1
-// (absolute error ~1e-7, far inside the rtol 1e-4 parity bar; avoids tanhf's branchy slow path).
-__device__ __forceinline__ float sigm(float x) { return __fdividef(1.0f, 1.0f + expf(-x)); }
-__device__ __forceinline__ float tanh_(float x) { return fmaf(2.0f, sigm(2.0f * x), -1.0f); }
-
-__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
 // =============================================================================== forward
 // shared (floats): Wp[128][256] | AT[2][128][32] | bsum[256] | bt[64] | WtS[Fin][64] | U[2][32][Fin]
@@ -1026,12 +1019,17 @@ extern "C" int b200rl_lstm_fwd(const float* u, const float* hx0, const float* cx
                                int B, int T, int Fin, int variant, void* stream) {
     B200RL_REQUIRE(B >= 1 && T >= 1, "lstm_fwd: bad shape B=%d T=%d", B, T);
     B200RL_REQUIRE(Fin >= 1 && Fin <= MAXF, "lstm_fwd: Fin=%d out of range [1,%d]", Fin, MAXF);
-    B200RL_REQUIRE(variant >= 0 && variant <= 2, "lstm_fwd: unknown variant %d", variant);
+    B200RL_REQUIRE(variant >= 0 && variant <= 3, "lstm_fwd: unknown variant %d", variant);
     const int ntiles = (B + TM - 1) / TM;
     const int grid = ntiles < sm_count() ? ntiles : sm_count();
+    if (variant == 3) {
+        // input projection AND the recurrent GEMM on tcgen05
+        if (launch_xproj_tc(u, Wt, bt, W_ih, b_ih, b_hh, gates, B, T, Fin, 0, sm_count(), stream)) return 1;
+        return launch_fwd_tc(gates, hx0, cx0, W_hh, c, h, B, T, sm_count(), stream);
+    }
     if (variant == 2) {
         // input projection on tcgen05 for all (b,t), staged in the (not yet written) `gates` buffer
-        if (launch_xproj_tc(u, Wt, bt, W_ih, b_ih, b_hh, gates, B, T, Fin, sm_count(), stream)) return 1;
+        if (launch_xproj_tc(u, Wt, bt, W_ih, b_ih, b_hh, gates, B, T, Fin, 0, sm_count(), stream)) return 1;
         const size_t smx = fwdx_smem_bytes();
         if (set_smem(lstm_fwdx_kernel, smx, "lstm_fwd(recurrent)")) return 1;
         B200RL_LAUNCH(lstm_fwdx_kernel, grid, NT, smx, stream, gates, hx0, cx0, W_hh, c, h, B, T);

@@ -100,6 +100,16 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, SmemDesc a, SmemDesc b
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// D[tmem] (+)= A[tmem] . B[smem]^T : the A tile (M = 128 lanes x K = 8 columns, one 32-bit cell per tf32 element)
+// is read from tensor memory, so only B crosses the 128 B/clk shared-memory port
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, SmemDesc b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
+}
 // arrive on `bar` once every MMA issued so far by this thread has completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -121,6 +131,30 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 32; ++i) r[i] = __uint_as_float(u[i]);
+}
+// 16 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
+    uint32_t u[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+          "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
+}
+// store 16 consecutive columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+        ::"r"(taddr), "r"(__float_as_uint(r[0])), "r"(__float_as_uint(r[1])), "r"(__float_as_uint(r[2])), "r"(__float_as_uint(r[3])),
+          "r"(__float_as_uint(r[4])), "r"(__float_as_uint(r[5])), "r"(__float_as_uint(r[6])), "r"(__float_as_uint(r[7])),
+          "r"(__float_as_uint(r[8])), "r"(__float_as_uint(r[9])), "r"(__float_as_uint(r[10])), "r"(__float_as_uint(r[11])),
+          "r"(__float_as_uint(r[12])), "r"(__float_as_uint(r[13])), "r"(__float_as_uint(r[14])), "r"(__float_as_uint(r[15]))
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ uint32_t tmem_addr(uint32_t base, int lane, int col) { return base + ((uint32_t)lane << 16) + (uint32_t)col; }
 
@@ -178,9 +212,28 @@ inline void mma_tf32(uint32_t d_tmem, SmemDesc a, SmemDesc b, uint32_t idesc, ui
             t.d[m][d_tmem + n] = s;
         }
 }
+inline void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, SmemDesc b, uint32_t idesc, uint32_t accumulate) {
+    const int M = (int)((idesc >> 24) & 31) << 4, N = (int)((idesc >> 17) & 63) << 3;
+    const bool bmn = (idesc >> 16) & 1;
+    EmulTmem& t = emul_tmem();
+    for (int m = 0; m < M; ++m)
+        for (int n = 0; n < N; ++n) {
+            float s = accumulate ? t.d[m][d_tmem + n] : 0.f;
+            for (int k = 0; k < 8; ++k) s += __uint_as_float(__float_as_uint(t.d[m][a_tmem + k]) & kTf32Mask) * emul_elem(b, bmn, n, k);
+            t.d[m][d_tmem + n] = s;
+        }
+}
+inline void tmem_st16(uint32_t taddr, const float (&r)[16]) {
+    const int lane = (int)(taddr >> 16), col = (int)(taddr & 0xffff);
+    for (int i = 0; i < 16; ++i) emul_tmem().d[lane][col + i] = r[i];
+}
 inline void tmem_ld32(uint32_t taddr, float (&r)[32]) {
     const int lane = (int)(taddr >> 16), col = (int)(taddr & 0xffff);
     for (int i = 0; i < 32; ++i) r[i] = emul_tmem().d[lane][col + i];
+}
+inline void tmem_ld16(uint32_t taddr, float (&r)[16]) {
+    const int lane = (int)(taddr >> 16), col = (int)(taddr & 0xffff);
+    for (int i = 0; i < 16; ++i) r[i] = emul_tmem().d[lane][col + i];
 }
 inline uint32_t tmem_addr(uint32_t base, int lane, int col) { return base + ((uint32_t)lane << 16) + (uint32_t)col; }
 #endif

@@ -42,7 +42,7 @@ template <int FMAX>
 __global__ void __launch_bounds__(xpk::NT, 1)
 lstm_xproj_tc_kernel(const float* __restrict__ u, const float* __restrict__ Wt, const float* __restrict__ bt,
                      const float* __restrict__ W_ih, const float* __restrict__ b_ih, const float* __restrict__ b_hh,
-                     float* __restrict__ xproj, long long rows, int Fin) {
+                     float* __restrict__ xproj, long long rows, int Fin, int igfo) {
     using namespace xpk;
     B200RL_DYN_SMEM(unsigned char, smem);
     unsigned char* W_hi = smem;
@@ -62,7 +62,8 @@ lstm_xproj_tc_kernel(const float* __restrict__ u, const float* __restrict__ Wt, 
 
     for (int i = tid; i < G * H; i += NT) {          // elem(p, k) = W_ih[n(p)][k], one core matrix (8 p x 4 k) per warp store
         const int k = ((i >> 5) & 15) * 4 + (i & 3), p = (i >> 9) * 8 + ((i >> 2) & 7);
-        const float w = W_ih[(size_t)((p & 3) * 64 + (p >> 2)) * H + k];
+        const int gate = igfo ? ((p & 1) * 2 + ((p >> 1) & 1)) : (p & 3);          // slot -> gate: (i,g,f,o) or (i,f,g,o)
+        const float w = W_ih[(size_t)(gate * 64 + (p >> 2)) * H + k];
         float hi, lo;
         tc::split_tf32(w, hi, lo);
         const int o = (p & 7) * 16 + (p >> 3) * W_SBO + (k & 3) * 4 + (k >> 2) * W_LBO;
@@ -71,7 +72,7 @@ lstm_xproj_tc_kernel(const float* __restrict__ u, const float* __restrict__ Wt, 
     }
     for (int i = tid; i < Fin * H; i += NT) { int q = i / H, k = i % H; WtS[i] = Wt[k * Fin + q]; }
     if (tid < H) bts[tid] = bt[tid];
-    if (tid < G) { const int p = tid, n = (p & 3) * 64 + (p >> 2); bsum[p] = b_ih[n] + b_hh[n]; }
+    if (tid < G) { const int p = tid, gate = igfo ? ((p & 1) * 2 + ((p >> 1) & 1)) : (p & 3), n = gate * 64 + (p >> 2); bsum[p] = b_ih[n] + b_hh[n]; }
     if (tid == 0) {
         tc::mbar_init(a_full, NP / 32); tc::mbar_init(a_empty, 1);
         for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_done[i], 1); tc::mbar_init(&acc_free[i], NP / 32); }
@@ -192,7 +193,7 @@ lstm_xproj_tc_kernel(const float* __restrict__ u, const float* __restrict__ Wt, 
 }
 
 int launch_xproj_tc(const float* u, const float* Wt, const float* bt, const float* W_ih, const float* b_ih, const float* b_hh,
-                    float* xproj, int B, int T, int Fin, int sms, void* stream) {
+                    float* xproj, int B, int T, int Fin, int igfo, int sms, void* stream) {
     B200RL_REQUIRE(Fin >= 1 && Fin <= xpk::MAXF, "lstm_fwd(xproj): Fin=%d out of range", Fin);
     const long long rows = (long long)B * T;
     const long long ntiles = (rows + xpk::TR - 1) / xpk::TR;
@@ -209,13 +210,13 @@ int launch_xproj_tc(const float* u, const float* Wt, const float* bt, const floa
 #endif
     if (Fin <= 4) {
         B200RL_XPROJ_ATTR(4)
-        B200RL_LAUNCH(lstm_xproj_tc_kernel<4>, grid, xpk::NT, smem, stream, u, Wt, bt, W_ih, b_ih, b_hh, xproj, rows, Fin);
+        B200RL_LAUNCH(lstm_xproj_tc_kernel<4>, grid, xpk::NT, smem, stream, u, Wt, bt, W_ih, b_ih, b_hh, xproj, rows, Fin, igfo);
     } else if (Fin <= 8) {
         B200RL_XPROJ_ATTR(8)
-        B200RL_LAUNCH(lstm_xproj_tc_kernel<8>, grid, xpk::NT, smem, stream, u, Wt, bt, W_ih, b_ih, b_hh, xproj, rows, Fin);
+        B200RL_LAUNCH(lstm_xproj_tc_kernel<8>, grid, xpk::NT, smem, stream, u, Wt, bt, W_ih, b_ih, b_hh, xproj, rows, Fin, igfo);
     } else {
         B200RL_XPROJ_ATTR(32)
-        B200RL_LAUNCH(lstm_xproj_tc_kernel<32>, grid, xpk::NT, smem, stream, u, Wt, bt, W_ih, b_ih, b_hh, xproj, rows, Fin);
+        B200RL_LAUNCH(lstm_xproj_tc_kernel<32>, grid, xpk::NT, smem, stream, u, Wt, bt, W_ih, b_ih, b_hh, xproj, rows, Fin, igfo);
     }
 #undef B200RL_XPROJ_ATTR
     return check_launch("lstm_fwd(xproj)");

@@ -44,6 +44,22 @@ def test_forward_matches_reference(backend, name):
     _close(logits.cpu(), g["fwd/logits"], what="logits")
 
 
+@pytest.mark.parametrize("variant", [0, 2, 3])
+def test_forward_kernel_variants_agree_with_reference(backend, variant, monkeypatch):
+    """Every forward kernel generation stays selectable (B200RL_FWD_VARIANT) and parity-green: 0 = FFMA with
+    the projection in the loop, 2 = tcgen05 projection + FFMA recurrence, 3 = tcgen05 projection + tcgen05
+    recurrence (default)."""
+    from b200rl import ops as O
+    ops, dev = backend
+    monkeypatch.setattr(O, "FWD_VARIANT", variant)
+    g = load_golden("ppo_small")
+    model = _model(g, None, dev)
+    b = golden_batch(g, 0, dev)
+    logits, logp, ent, value = model.actor.forward(b["obs"], (b["hx"], b["cx"]), b["act"], ops=ops)
+    _close(value.cpu(), g["fwd/value"], what="value")
+    _close(logits.cpu(), g["fwd/logits"], what="logits")
+
+
 CASES = [("ppo_small", "PPO"), ("impala_small", "IMPALA"), ("ppo_continuous_small", "PPO-Continuous"),
          ("ppo_repo_default", "PPO"), ("impala_mid", "IMPALA"), ("ppo_cfg1", "PPO")]
 
