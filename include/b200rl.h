@@ -81,19 +81,24 @@ int b200rl_head_fwd(const float* h, const float* W_head, const float* b_head,
                     float* head_out, long long rows, int NH, void* stream);
 
 /* BPTT, serial part: consumes dhead (B,T,NH) = dLoss/dhead_out and OVERWRITES `gates`
- * in place with dLoss/d(gate pre-activations) (same (B,T,H,4) layout).               */
-int b200rl_lstm_bwd(const float* dhead, const float* W_head, const float* W_hh,
-                    float* gates, const float* c, const float* cx0,
+ * in place with dLoss/d(gate pre-activations) (same (B,T,H,4) layout).
+ * `variant` 0: FFMA kernel (W_ih, dx unused, may be NULL).
+ * `variant` 1: tcgen05 kernel; also writes dx (B,T,H) = dLoss/d(torso output, before its
+ *              ReLU mask) = dpre . W_ih, which lstm_wgrad variant 3 consumes.          */
+int b200rl_lstm_bwd(const float* dhead, const float* W_head, const float* W_hh, const float* W_ih,
+                    float* gates, const float* c, const float* cx0, float* dx,
                     int B, int T, int NH, int variant, void* stream);
 
 /* BPTT, parallel part: weight gradients as `nparts` partial slabs of `P` floats each
- * (partials[part*P + off_*]); also the torso-input gradient du (B,T,Fin) if non-NULL. */
+ * (partials[part*P + off_*]); also the torso-input gradient du (B,T,Fin) if non-NULL.
+ * `variant` 0: FFMA; 1: tcgen05 dW + tcgen05 dx; 2: tcgen05 dW + FFMA rest;
+ *           3: tcgen05 dW + torso gradients from `dx` (see lstm_bwd variant 1; du must be NULL, Fin <= 8). */
 int b200rl_lstm_wgrad(const float* dpre, const float* h, const float* hx0, const float* u,
                       const float* dhead, const float* Wt, const float* bt, const float* W_ih,
                       float* partials, int nparts, long long P,
                       long long off_Wt, long long off_bt, long long off_Wih, long long off_Whh,
                       long long off_bih, long long off_bhh, long long off_Whead, long long off_bhead,
-                      float* du, int B, int T, int Fin, int NH, int variant, void* stream);
+                      float* du, const float* dx, int B, int T, int Fin, int NH, int variant, void* stream);
 
 /* grad[i] = sum_part partials[part*P + i]                                             */
 int b200rl_reduce_partials(const float* partials, float* grad, int nparts, long long P, void* stream);

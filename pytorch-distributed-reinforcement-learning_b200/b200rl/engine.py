@@ -111,7 +111,7 @@ class OnPolicyEngine:
             scale = 1.0 / self.world
         ops.clip_rmsprop(self.flat, self.grad, self.sq_avg, L.P, scale, hp["max_grad_norm"], hp["lr"],
                          0.99, 1e-5, self.grad_norm)
-        self.n_launches += 8 + {0: 0, 1: 2, 2: 1}[self.wgrad_variant] + (1 if _ops.FWD_VARIANT == 2 else 0)
+        self.n_launches += 8 + {0: 0, 1: 2, 2: 1}[self.wgrad_variant] + (1 if _ops.FWD_VARIANT >= 2 else 0)
 
     # -------------------------------------------------------------------- scalars
     def losses(self):
@@ -200,7 +200,7 @@ class VMPOEngine(OnPolicyEngine):
         lib.call("b200rl_vmpo_dual_step", ptr(self.duals), ptr(self.dual_sq), ptr(self.scalars), ptr(self.losses_dev),
                  hp["coef_eta"], float(coef_alpha), hp["lr"], 0.99, 1e-5, N, float(k * (T - 1)),
                  hp["policy_loss_coef"], hp["value_loss_coef"], st)
-        self.n_launches += 12 + {0: 0, 1: 2, 2: 1}[self.wgrad_variant] + (1 if _ops.FWD_VARIANT == 2 else 0)
+        self.n_launches += 12 + {0: 0, 1: 2, 2: 1}[self.wgrad_variant] + (1 if _ops.FWD_VARIANT >= 2 else 0)
 
     def losses(self):
         v = self.losses_dev.cpu().tolist()

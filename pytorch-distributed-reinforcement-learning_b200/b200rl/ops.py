@@ -14,7 +14,9 @@ H = 64
 # kernel (W_hh resident in tensor memory), 2 = tcgen05 input projection + FFMA recurrent kernel (K=64),
 # 1 = 16-warp split-K FFMA, 0 = 8-warp FFMA with the projection in the loop
 FWD_VARIANT = int(os.environ.get("B200RL_FWD_VARIANT", "3"))
-BWD_VARIANT = int(os.environ.get("B200RL_BWD_VARIANT", "0"))
+# backward 1 = tcgen05 BPTT kernel (also emits dx = dpre . W_ih, so the weight-gradient stage skips that GEMM),
+# 0 = FFMA kernel
+BWD_VARIANT = int(os.environ.get("B200RL_BWD_VARIANT", "1"))
 
 
 class Ops:
@@ -147,12 +149,19 @@ def _head_fwd(self, L, flat, h, head_out):
     self.lib.call("b200rl_head_fwd", ptr(h), v("W_head"), v("b_head"), ptr(head_out), rows, L.NH, self._stream(dev))
 
 
-def _lstm_bwd(self, L, flat, dhead, ws, cx0):
+def _lstm_bwd(self, L, flat, dhead, ws, cx0, variant=None):
     dev = self._chk(flat, dhead, ws["gates"], ws["c"], cx0)
     B, T = dhead.shape[0], dhead.shape[1]
+    variant = BWD_VARIANT if variant is None else variant
     v = lambda k: ptr(flat) + 4 * L.off[k][0]
-    self.lib.call("b200rl_lstm_bwd", ptr(dhead), v("W_head"), v("W_hh"), ptr(ws["gates"]), ptr(ws["c"]), ptr(cx0),
-                  B, T, L.NH, 0, self._stream(dev))
+    dx = None
+    if variant == 1:
+        dx = ws.get("dx")
+        if dx is None or dx.shape[:2] != (B, T):
+            dx = ws["dx"] = torch.empty(B, T, H, device=dhead.device)
+    ws["dx_fresh"] = variant == 1                 # lstm_wgrad may take the torso gradients from ws["dx"]
+    self.lib.call("b200rl_lstm_bwd", ptr(dhead), v("W_head"), v("W_hh"), v("W_ih"), ptr(ws["gates"]), ptr(ws["c"]), ptr(cx0),
+                  ptr(dx), B, T, L.NH, variant, self._stream(dev))
 
 
 def _lstm_wgrad(self, L, flat, ws, hx0, u, dhead, partials, du=None, variant=0):
@@ -160,12 +169,15 @@ def _lstm_wgrad(self, L, flat, ws, hx0, u, dhead, partials, du=None, variant=0):
     B, T, Fin = u.shape
     nparts = partials.shape[0]
     assert partials.shape[1] == L.P
+    dx = None
+    if variant == 1 and ws.get("dx_fresh") and du is None and Fin <= 8:
+        variant, dx = 3, ws["dx"]
     v = lambda k: ptr(flat) + 4 * L.off[k][0]
     o = lambda k: L.off[k][0]
     self.lib.call("b200rl_lstm_wgrad", ptr(ws["gates"]), ptr(ws["h"]), ptr(hx0), ptr(u), ptr(dhead),
                   v("Wt"), v("bt"), v("W_ih"), ptr(partials), nparts, L.P,
                   o("Wt"), o("bt"), o("W_ih"), o("W_hh"), o("b_ih"), o("b_hh"), o("W_head"), o("b_head"),
-                  ptr(du), B, T, Fin, L.NH, variant, self._stream(dev))
+                  ptr(du), ptr(dx), B, T, Fin, L.NH, variant, self._stream(dev))
 
 
 def _reduce_partials(self, partials, grad):

@@ -1,0 +1,278 @@
+// Serial half of the LSTM backward (BPTT) on tcgen05 (sm_100a).
+//
+// Per step t = T-1 .. 0 (autograd of nn.LSTMCell looped over T, networks/models.py:71-75, replayed by
+// loss.backward(), ppo/learning.py:92):
+//   dh   = dh_rec + dhead_t . W_head                         tc = tanh(c_t)
+//   d_o  = dh tc ;  dct = dh o (1 - tc^2) + dc ;  d_i = dct g ;  d_g = dct i ;  d_f = dct c_{t-1} ;  dc = dct f
+//   dpre = (d_i i(1-i), d_f f(1-f), d_g (1-g^2), d_o o(1-o))                    -> `gates`, in place
+//   dh_rec[r][k] = sum_p dpre[r][p] W_hh[n(p)][k]           dx[r][k] = sum_p dpre[r][p] W_ih[n(p)][k]
+//
+// The two GEMMs of a step are ONE tcgen05 accumulation with the weights as M:
+//   D[128 x 32] = [W_hh^T ; W_ih^T][128 x 256] . dpre_t^T[256 x 32]     (lanes 0-63: dh_rec, lanes 64-127: dx)
+// so the torso gradient's GEMM (a separate 537 MB pass over dpre before) rides along for free.
+// 3xTF32: A_hi lives in tensor memory (256 columns); A_lo for k < 192 too (192 columns), the last 64 k
+// in shared memory (32 KB, SS-form MMAs); dpre (B operand, hi/lo, K-major) is rewritten every step by the
+// cell phase.  Two issuer warps split K (two accumulators, summed by the readers): 96 MMAs per step.
+//
+// Cell phase: TMEM lanes are bound to the warp's quarter, so dh_rec (lanes 0-63) is only visible to warps
+// with id % 4 in {0, 1} -- and those share two of the four SM sub-partitions.  The work is therefore split:
+//   HELPER warps (id % 4 in {2, 3}; same unit and sequences as their partner) own everything that does not
+//   depend on dh: the global loads of the saved activations, tanh(c_t), dhead . W_head and the products
+//   P_o = tc o(1-o), Q = o(1-tc^2), P_i = g i(1-i), P_f = c_{t-1} f(1-f), P_g = i(1-g^2), f -- computed for
+//   step t-1 WHILE the tensor core runs step t, and handed over through shared memory; they also drain the
+//   dx lanes of the accumulator to `dx`.
+//   CRITICAL warps (id % 4 in {0, 1}) wait for the accumulator, then need 7 flops per cell:
+//   dh = D + dhW ; d_o' = dh P_o ; dct = dh Q + dc ; (dct P_i, dct P_f, dct P_g) ; dc = dct f,
+//   store dpre (global + B operand hi/lo) and hand the step to the issuers.
+#include "common.cuh"
+#include "tc05.cuh"
+#include "launchers.cuh"
+
+namespace b200rl {
+
+namespace btk {
+constexpr int H = 64, G = 256, TB = 32, NC = 512, NT = NC + 64;    // 8 critical + 8 helper warps, 2 MMA issuer warps
+constexpr int B_LBO = 144, B_SBO = 9216;                            // B: 64 core matrices along K, 16-byte skew -> conflict-free 16-byte stores
+constexpr int B_BYTES = (TB / 8) * B_SBO;                           // 36864 per hi / lo
+static_assert(63 * B_LBO + 128 <= B_SBO, "core matrices of one 8-row group must fit below SBO");
+constexpr int KS = 192;                                             // A_lo: k < KS in tensor memory, k >= KS in shared memory
+constexpr int AL_LBO = 128, AL_SBO = ((G - KS) / 4) * 128;          // 2048
+constexpr int AL_BYTES = (128 / 8) * AL_SBO;                        // 32768
+constexpr int TM_D0 = 0, TM_D1 = 32, TM_AH = 64, TM_AL = TM_AH + G, TM_COLS = 512;
+static_assert(TM_AL + KS <= TM_COLS, "tensor memory budget");
+constexpr int NCOEF = 7;                                            // dhW, P_o, Q, P_i, P_f, P_g, f
+constexpr int CELLS = TB * H;
+}  // namespace btk
+
+static inline size_t bwdt_smem_bytes(int NH) {
+    return 2 * (size_t)btk::B_BYTES + btk::AL_BYTES + sizeof(float) * (size_t)(btk::NCOEF * btk::CELLS + NH * btk::H) + 64;
+}
+
+__global__ void __launch_bounds__(btk::NT, 1)
+lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_head, const float* __restrict__ W_hh,
+                 const float* __restrict__ W_ih, float* gates, const float* __restrict__ c_sav,
+                 const float* __restrict__ cx0, float* __restrict__ dx, int B, int T, int NH) {
+    using namespace btk;
+    B200RL_DYN_SMEM(unsigned char, smem);
+    unsigned char* B_hi = smem;
+    unsigned char* B_lo = smem + B_BYTES;
+    unsigned char* ALs = smem + 2 * B_BYTES;
+    float* COEF = reinterpret_cast<float*>(ALs + AL_BYTES);          // COEF[(k*8 + pair)*256 + i*32 + lane]
+    float* WhS = COEF + NCOEF * CELLS;                               // WhS[c*64 + j]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(WhS + NH * H);
+    uint64_t* b_full = bars, *acc_done = bars + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool cellw = warp < NC / 32;
+    const int q = warp & 3, cg = (warp >> 2) & 3;                   // TMEM lane quarter, group of 8 sequences
+
+    for (int i = tid; i < NH * H; i += NT) WhS[i] = W_head[i];
+    if (tid == 0) {
+        tc::mbar_init(b_full, NC / 32); tc::mbar_init(acc_done, 2);
+        tc::fence_mbar_init();
+    }
+    if (warp == NC / 32) tc::tmem_alloc(tmem_slot, TM_COLS);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+#ifdef B200RL_EMUL
+    const int my_lane = 32 * q + lane;
+#else
+    const int my_lane = 32 * q;
+#endif
+    // one-time: A[m][p] = W_hh[n(p)][m] (m < 64) | W_ih[n(p)][m-64], n(p) = (p&3)*64 + (p>>2); thread = row m (its TMEM
+    // lane), warp (q, cg) fills columns p in [64 cg, 64 cg + 64)
+    if (cellw) {
+        const int m = 32 * q + lane;
+        const float* wsrc = (m < H ? W_hh : W_ih) + (m & (H - 1));
+        for (int k0 = 0; k0 < 64; k0 += 16) {
+            float hi[16], lo[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const int p = cg * 64 + k0 + e, n = (p & 3) * H + (p >> 2);
+                tc::split_tf32(wsrc[(size_t)n * H], hi[e], lo[e]);
+            }
+            const int p0 = cg * 64 + k0;
+            tc::tmem_st16(tc::tmem_addr(tmem, my_lane, TM_AH + p0), hi);
+            if (p0 < KS) {
+                tc::tmem_st16(tc::tmem_addr(tmem, my_lane, TM_AL + p0), lo);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const int pp = p0 + e - KS;
+                    *reinterpret_cast<float*>(ALs + (m & 7) * 16 + (m >> 3) * AL_SBO + (pp & 3) * 4 + (pp >> 2) * AL_LBO) = lo[e];
+                }
+            }
+        }
+    }
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t idesc = tc::make_idesc_tf32(128, TB, false, false);
+    const int ntiles = (B + TB - 1) / TB;
+
+    if (!cellw) {
+        if (lane == 0) {
+            const int ii = warp - NC / 32;                           // K half: k-steps [16 ii, 16 ii + 16) into accumulator ii
+            const uint32_t D = tmem + (ii ? TM_D1 : TM_D0);
+            uint32_t n = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int t = 0; t < T; ++t, ++n) {
+                    tc::mbar_wait(b_full, n & 1);                    // dpre_t operand written, accumulators drained
+                    tc::fence_after_sync();
+#pragma unroll
+                    for (int s0 = 0; s0 < 16; ++s0) {
+                        const int s = ii * 16 + s0, p0 = s * 8;
+                        const tc::SmemDesc bh = tc::make_desc(B_hi + s * 2 * B_LBO, B_LBO, B_SBO);
+                        const tc::SmemDesc bl = tc::make_desc(B_lo + s * 2 * B_LBO, B_LBO, B_SBO);
+                        tc::mma_tf32_ts(D, tmem + TM_AH + p0, bh, idesc, s0 > 0 ? 1u : 0u);
+                        tc::mma_tf32_ts(D, tmem + TM_AH + p0, bl, idesc, 1u);
+                        if (p0 < KS) tc::mma_tf32_ts(D, tmem + TM_AL + p0, bh, idesc, 1u);
+                        else tc::mma_tf32(D, tc::make_desc(ALs + ((p0 - KS) >> 2) * AL_LBO, AL_LBO, AL_SBO), bh, idesc, 1u);
+                    }
+                    tc::mma_commit(acc_done);
+                }
+            }
+        }
+    } else {
+        const bool helper = q >= 2;
+        const int j = (q & 1) * 32 + lane;                           // LSTM unit (critical / helper) = dx column (helper, TMEM side)
+        const int pair = (q & 1) * 4 + cg;
+        float* CO = COEF + pair * 256 + lane;                        // + (k*8)*256 + i*32
+        uint32_t nb = 0;                                             // accumulator batches waited for so far
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int b0 = tile * TB + cg * 8;
+            auto seq = [&](int i) { const int b = b0 + i; return b < B ? b : B - 1; };
+            auto rowof = [&](int i) { return (unsigned)seq(i) * (unsigned)T; };   // B*T < 2^31 (checked by the launcher)
+            if (helper) {
+                float4 gcur[8]; float ccur[8], cprev[8];
+                auto load_step = [&](int t) {                        // saved activations of step t and c_{t-1}
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const size_t o = (size_t)(rowof(i) + t) * H + j;
+                        gcur[i] = ld4(gates + o * 4);
+                        cprev[i] = t > 0 ? c_sav[o - H] : cx0[(size_t)seq(i) * H + j];
+                    }
+                };
+                auto coefs = [&](int t) {                            // everything of step t that does not need dh
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float* dhr = dhead + (size_t)(rowof(i) + t) * NH;
+                        float dhw = 0.f;
+                        for (int c = 0; c < NH; ++c) dhw = fmaf(__ldg(dhr + c), WhS[c * H + j], dhw);
+                        const float4 g4 = gcur[i];                   // i, f, g, o (post-activation)
+                        const float tch = tanh_(ccur[i]);
+                        float* co = CO + i * 32;
+                        co[0 * 2048] = dhw;
+                        co[1 * 2048] = tch * g4.w * (1.f - g4.w);
+                        co[2 * 2048] = g4.w * (1.f - tch * tch);
+                        co[3 * 2048] = g4.z * g4.x * (1.f - g4.x);
+                        co[4 * 2048] = cprev[i] * g4.y * (1.f - g4.y);
+                        co[5 * 2048] = g4.x * (1.f - g4.z * g4.z);
+                        co[6 * 2048] = g4.y;
+                    }
+                };
+#pragma unroll
+                for (int i = 0; i < 8; ++i) ccur[i] = c_sav[(size_t)(rowof(i) + T - 1) * H + j];
+                load_step(T - 1);
+                coefs(T - 1);
+                for (int t = T - 1; t >= 0; --t) {
+                    // next step's inputs: c_{t-1} becomes c_t, loads fly during this step's hand-over
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) ccur[i] = cprev[i];
+                    if (t > 0) load_step(t - 1);
+                    if (t < T - 1) {                                 // drain dx_{t+1} (lanes 64..127 of both accumulators)
+                        tc::mbar_wait(acc_done, nb & 1); ++nb;
+                        tc::fence_after_sync();
+                        float d0[8], d1[8];
+                        tc::tmem_ld8(tc::tmem_addr(tmem, my_lane, TM_D0 + cg * 8), d0);
+                        tc::tmem_ld8(tc::tmem_addr(tmem, my_lane, TM_D1 + cg * 8), d1);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (b0 + i < B) dx[(size_t)(rowof(i) + t + 1) * H + j] = d0[i] + d1[i];
+                        tc::fence_before_sync();
+                    }
+                    tc::mbar_arrive_warp(b_full);                    // (nothing to write: this warp's share of "accumulators drained")
+                    tc::named_bar_sync(1 + pair, 64);                // coefficients of step t are in shared memory
+                    tc::named_bar_sync(1 + pair, 64);                // ... and have been read
+                    if (t > 0) coefs(t - 1);
+                }
+                tc::mbar_wait(acc_done, nb & 1); ++nb;               // dx_0
+                tc::fence_after_sync();
+                {
+                    float d0[8], d1[8];
+                    tc::tmem_ld8(tc::tmem_addr(tmem, my_lane, TM_D0 + cg * 8), d0);
+                    tc::tmem_ld8(tc::tmem_addr(tmem, my_lane, TM_D1 + cg * 8), d1);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (b0 + i < B) dx[(size_t)rowof(i) * H + j] = d0[i] + d1[i];
+                    tc::fence_before_sync();
+                }
+            } else {
+                float dc[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dc[i] = 0.f;
+                for (int t = T - 1; t >= 0; --t) {
+                    float d0[8], d1[8];
+                    if (t < T - 1) {
+                        tc::mbar_wait(acc_done, nb & 1); ++nb;
+                        tc::fence_after_sync();
+                        tc::tmem_ld8(tc::tmem_addr(tmem, my_lane, TM_D0 + cg * 8), d0);
+                        tc::tmem_ld8(tc::tmem_addr(tmem, my_lane, TM_D1 + cg * 8), d1);
+                        tc::fence_before_sync();
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { d0[i] = 0.f; d1[i] = 0.f; }
+                    }
+                    tc::named_bar_sync(1 + pair, 64);
+                    float cf[8][NCOEF];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int k = 0; k < NCOEF; ++k) cf[i][k] = CO[k * 2048 + i * 32];
+                    tc::named_bar_sync(1 + pair, 64);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float dh = d0[i] + d1[i] + cf[i][0];
+                        const float dct = fmaf(dh, cf[i][2], dc[i]);
+                        const float4 dp = make_float4(dct * cf[i][3], dct * cf[i][4], dct * cf[i][5], dh * cf[i][1]);
+                        dc[i] = dct * cf[i][6];
+                        if (b0 + i < B) st4(gates + ((size_t)(rowof(i) + t) * H + j) * 4, dp);
+                        float4 hi, lo;
+                        tc::split_tf32(dp.x, hi.x, lo.x); tc::split_tf32(dp.y, hi.y, lo.y);
+                        tc::split_tf32(dp.z, hi.z, lo.z); tc::split_tf32(dp.w, hi.w, lo.w);
+                        const int r = cg * 8 + i;
+                        const int ob = (r & 7) * 16 + (r >> 3) * B_SBO + j * B_LBO;
+                        *reinterpret_cast<float4*>(B_hi + ob) = hi;
+                        *reinterpret_cast<float4*>(B_lo + ob) = lo;
+                    }
+                    tc::fence_async_smem();
+                    tc::mbar_arrive_warp(b_full);
+                }
+                tc::mbar_wait(acc_done, nb & 1); ++nb;               // batch of step 0 (dx_0): keeps the phase count in step
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == NC / 32) tc::tmem_dealloc(tmem, TM_COLS);
+}
+
+int launch_bwd_tc(const float* dhead, const float* W_head, const float* W_hh, const float* W_ih, float* gates,
+                  const float* c, const float* cx0, float* dx, int B, int T, int NH, int sms, void* stream) {
+    B200RL_REQUIRE((long long)B * T < (1LL << 31), "lstm_bwd(tc): B*T must be below 2^31");
+    B200RL_REQUIRE(dx != nullptr && W_ih != nullptr, "lstm_bwd(tc): needs W_ih and the dx workspace");
+    const int ntiles = (B + btk::TB - 1) / btk::TB;
+    const size_t smem = bwdt_smem_bytes(NH);
+#ifndef B200RL_EMUL
+    cudaError_t e = cudaFuncSetAttribute(lstm_bwdt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error("lstm_bwd(tc): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+#endif
+    B200RL_LAUNCH(lstm_bwdt_kernel, ntiles < sms ? ntiles : sms, btk::NT, smem, stream, dhead, W_head, W_hh, W_ih, gates, c, cx0, dx, B, T, NH);
+    return check_launch("lstm_bwd(tc)");
+}
+
+}  // namespace b200rl

@@ -340,6 +340,68 @@ head_grad_kernel(const float* __restrict__ h, const float* __restrict__ dhead, f
     }
 }
 
+// --------------------------------------------------------------------------- torso gradients from a stored dx
+// When the backward kernel already produced dx = dpre . W_ih (bwd_tc.cu fuses that GEMM into the recurrent one),
+// what is left is a bandwidth-bound pass over dx (256 B per row): ReLU mask (x recomputed from u), dbt, dWt.
+// 1024 threads: 16 threads x float4 per row, 64 rows per CTA pass.
+template <int FMAX, int TG_T>                      // (8 torso inputs need more registers: half the threads)
+__global__ void __launch_bounds__(TG_T)
+torso_grad_kernel(const float* __restrict__ dxg, const float* __restrict__ u, const float* __restrict__ Wt,
+                  const float* __restrict__ bt, float* __restrict__ partials, long long P, long long off_Wt, long long off_bt,
+                  long long rows, int Fin) {
+    B200RL_DYN_SMEM(float, smem);                     // red[32 warps][(Fin+1) * 64]
+    const int tid = threadIdx.x, c4 = tid & 15, part = tid >> 4, lane = tid & 31, warp = tid >> 5;
+    float4 w[FMAX];                                   // Wt[4 c4 + e][q], e = x,y,z,w
+#pragma unroll
+    for (int q = 0; q < FMAX; ++q)
+        w[q] = q < Fin ? make_float4(Wt[(c4 * 4 + 0) * Fin + q], Wt[(c4 * 4 + 1) * Fin + q], Wt[(c4 * 4 + 2) * Fin + q], Wt[(c4 * 4 + 3) * Fin + q])
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 b4 = *reinterpret_cast<const float4*>(bt + c4 * 4);
+    float4 ab = make_float4(0.f, 0.f, 0.f, 0.f), aw[FMAX];
+#pragma unroll
+    for (int q = 0; q < FMAX; ++q) aw[q] = ab;
+#pragma unroll 2
+    for (long long r = (long long)blockIdx.x * (TG_T / 16) + part; r < rows; r += (long long)gridDim.x * (TG_T / 16)) {
+        const float4 d = *reinterpret_cast<const float4*>(dxg + (size_t)r * 64 + c4 * 4);
+        float uq[FMAX];
+#pragma unroll
+        for (int q = 0; q < FMAX; ++q) uq[q] = q < Fin ? __ldg(u + (size_t)r * Fin + q) : 0.f;
+        float4 x = b4;
+#pragma unroll
+        for (int q = 0; q < FMAX; ++q) { x.x = fmaf(uq[q], w[q].x, x.x); x.y = fmaf(uq[q], w[q].y, x.y); x.z = fmaf(uq[q], w[q].z, x.z); x.w = fmaf(uq[q], w[q].w, x.w); }
+        const float4 sv = make_float4(x.x > 0.f ? d.x : 0.f, x.y > 0.f ? d.y : 0.f, x.z > 0.f ? d.z : 0.f, x.w > 0.f ? d.w : 0.f);
+        ab.x += sv.x; ab.y += sv.y; ab.z += sv.z; ab.w += sv.w;
+#pragma unroll
+        for (int q = 0; q < FMAX; ++q) {
+            aw[q].x = fmaf(sv.x, uq[q], aw[q].x); aw[q].y = fmaf(sv.y, uq[q], aw[q].y);
+            aw[q].z = fmaf(sv.z, uq[q], aw[q].z); aw[q].w = fmaf(sv.w, uq[q], aw[q].w);
+        }
+    }
+    // the two row lanes of a warp, then the 32 warps through shared memory
+    auto fold = [&](float4& v) {
+        v.x += __shfl_xor_sync(kFull, v.x, 16); v.y += __shfl_xor_sync(kFull, v.y, 16);
+        v.z += __shfl_xor_sync(kFull, v.z, 16); v.w += __shfl_xor_sync(kFull, v.w, 16);
+    };
+    fold(ab);
+#pragma unroll
+    for (int q = 0; q < FMAX; ++q) fold(aw[q]);
+    const int RW = (Fin + 1) * 64;
+    if (lane < 16) {
+        float* d = smem + warp * RW;
+        *reinterpret_cast<float4*>(d + Fin * 64 + c4 * 4) = ab;
+#pragma unroll
+        for (int q = 0; q < FMAX; ++q) if (q < Fin) *reinterpret_cast<float4*>(d + q * 64 + c4 * 4) = aw[q];
+    }
+    __syncthreads();
+    float* out = partials + (size_t)blockIdx.x * P;
+    for (int i = tid; i < RW; i += TG_T) {
+        float sum = 0.f;
+        for (int wv = 0; wv < TG_T / 32; ++wv) sum += smem[wv * RW + i];
+        const int q = i >> 6, jj = i & 63;
+        if (q == Fin) out[off_bt + jj] = sum; else out[off_Wt + (size_t)jj * Fin + q] = sum;
+    }
+}
+
 template <typename K>
 static int dx_set_smem(K kern, size_t smem) {
 #ifndef B200RL_EMUL
@@ -367,6 +429,30 @@ int launch_dx_tc(const float* dpre, const float* u, const float* W_ih, const flo
     else B200RL_DX_LAUNCH(32);
 #undef B200RL_DX_LAUNCH
     if (check_launch("lstm_wgrad(dx tc)")) return 1;
+    const size_t hsm = sizeof(float) * HG_G * (HG_R * 65 + HG_R * B200RL_MAX_HEADS);
+    if (dx_set_smem(head_grad_kernel, hsm)) return 1;
+    B200RL_LAUNCH(head_grad_kernel, nparts, 256 * HG_G, hsm, stream, h, dhead, partials, P, off_Whead, off_bhead, rows, NH);
+    return check_launch("lstm_wgrad(head grad)");
+}
+
+int launch_torso_from_dx(const float* dx, const float* u, const float* Wt, const float* bt,
+                         const float* h, const float* dhead, float* partials, int nparts, long long P,
+                         long long off_Wt, long long off_bt, long long off_Whead, long long off_bhead,
+                         int B, int T, int Fin, int NH, void* stream) {
+    B200RL_REQUIRE(Fin >= 1 && Fin <= 8, "lstm_wgrad(torso from dx): Fin=%d out of range [1,8]", Fin);
+    const long long rows = (long long)B * T;
+    if (Fin <= 4) {
+        const size_t tsm = sizeof(float) * (size_t)(1024 / 32) * (Fin + 1) * 64;
+        auto kern = torso_grad_kernel<4, 1024>;
+        if (dx_set_smem(kern, tsm)) return 1;
+        B200RL_LAUNCH(kern, nparts, 1024, tsm, stream, dx, u, Wt, bt, partials, P, off_Wt, off_bt, rows, Fin);
+    } else {
+        const size_t tsm = sizeof(float) * (size_t)(512 / 32) * (Fin + 1) * 64;
+        auto kern = torso_grad_kernel<8, 512>;
+        if (dx_set_smem(kern, tsm)) return 1;
+        B200RL_LAUNCH(kern, nparts, 512, tsm, stream, dx, u, Wt, bt, partials, P, off_Wt, off_bt, rows, Fin);
+    }
+    if (check_launch("lstm_wgrad(torso from dx)")) return 1;
     const size_t hsm = sizeof(float) * HG_G * (HG_R * 65 + HG_R * B200RL_MAX_HEADS);
     if (dx_set_smem(head_grad_kernel, hsm)) return 1;
     B200RL_LAUNCH(head_grad_kernel, nparts, 256 * HG_G, hsm, stream, h, dhead, partials, P, off_Whead, off_bhead, rows, NH);

@@ -18,4 +18,12 @@ int launch_xproj_tc(const float* u, const float* Wt, const float* bt, const floa
 // fwd_tc.cu: recurrent LSTM forward with the per-step GEMM on tcgen05; xg = xproj (i,g,f,o) in, saved activations out
 int launch_fwd_tc(float* xg, const float* hx0, const float* cx0, const float* W_hh, float* c, float* h,
                   int B, int T, int sms, void* stream);
+// dx_tc.cu: torso gradients from a stored dx (written by bwd_tc.cu) + head gradients
+int launch_torso_from_dx(const float* dx, const float* u, const float* Wt, const float* bt,
+                         const float* h, const float* dhead, float* partials, int nparts, long long P,
+                         long long off_Wt, long long off_bt, long long off_Whead, long long off_bhead,
+                         int B, int T, int Fin, int NH, void* stream);
+// bwd_tc.cu: serial BPTT with dh_rec and dx = dpre . W_ih as one tcgen05 accumulation per step
+int launch_bwd_tc(const float* dhead, const float* W_head, const float* W_hh, const float* W_ih, float* gates,
+                  const float* c, const float* cx0, float* dx, int B, int T, int NH, int sms, void* stream);
 }  // namespace b200rl

@@ -1056,12 +1056,13 @@ extern "C" int b200rl_head_fwd(const float* h, const float* W_head, const float*
     return check_launch("head_fwd");
 }
 
-extern "C" int b200rl_lstm_bwd(const float* dhead, const float* W_head, const float* W_hh,
-                               float* gates, const float* c, const float* cx0,
+extern "C" int b200rl_lstm_bwd(const float* dhead, const float* W_head, const float* W_hh, const float* W_ih,
+                               float* gates, const float* c, const float* cx0, float* dx,
                                int B, int T, int NH, int variant, void* stream) {
     B200RL_REQUIRE(B >= 1 && T >= 1, "lstm_bwd: bad shape B=%d T=%d", B, T);
     B200RL_REQUIRE(NH >= 1 && NH <= B200RL_MAX_HEADS, "lstm_bwd: NH=%d out of range", NH);
-    B200RL_REQUIRE(variant == 0, "lstm_bwd: unknown variant %d", variant);
+    B200RL_REQUIRE(variant == 0 || variant == 1, "lstm_bwd: unknown variant %d", variant);
+    if (variant == 1) return launch_bwd_tc(dhead, W_head, W_hh, W_ih, gates, c, cx0, dx, B, T, NH, sm_count(), stream);
     const size_t smem = bwd_smem_bytes(NH);
     if (set_smem(lstm_bwd_kernel, smem, "lstm_bwd")) return 1;
     const int ntiles = (B + TM - 1) / TM;
@@ -1075,14 +1076,21 @@ extern "C" int b200rl_lstm_wgrad(const float* dpre, const float* h, const float*
                                  float* partials, int nparts, long long P,
                                  long long off_Wt, long long off_bt, long long off_Wih, long long off_Whh,
                                  long long off_bih, long long off_bhh, long long off_Whead, long long off_bhead,
-                                 float* du, int B, int T, int Fin, int NH, int variant, void* stream) {
+                                 float* du, const float* dx, int B, int T, int Fin, int NH, int variant, void* stream) {
     B200RL_REQUIRE(B >= 1 && T >= 1, "lstm_wgrad: bad shape B=%d T=%d", B, T);
     B200RL_REQUIRE(Fin >= 1 && Fin <= MAXF && NH >= 1 && NH <= B200RL_MAX_HEADS, "lstm_wgrad: Fin=%d NH=%d out of range", Fin, NH);
     B200RL_REQUIRE(H * Fin <= WG_E * NT && NH * H <= WG_E * NT, "lstm_wgrad: head/torso too wide");
-    B200RL_REQUIRE(variant >= 0 && variant <= 2, "lstm_wgrad: unknown variant %d", variant);
+    B200RL_REQUIRE(variant >= 0 && variant <= 3, "lstm_wgrad: unknown variant %d", variant);
     B200RL_REQUIRE(nparts >= 1, "lstm_wgrad: nparts=%d", nparts);
     B200RL_REQUIRE((off_Wih % 4) == 0 && (off_Whh % 4) == 0 && (P % 4) == 0, "lstm_wgrad: W_ih/W_hh offsets and P must be multiples of 4 floats");
     const size_t smem = wgrad_smem_bytes(Fin, NH);
+    if (variant == 3) {
+        // dx was already produced by lstm_bwd variant 1: tcgen05 dW + a bandwidth-bound torso pass over dx
+        B200RL_REQUIRE(dx != nullptr && du == nullptr, "lstm_wgrad: variant 3 needs dx (from lstm_bwd variant 1) and does not produce du");
+        B200RL_REQUIRE((long long)nparts * 32 <= (long long)B * T + 31, "lstm_wgrad: nparts=%d exceeds the number of 32-row stages", nparts);
+        if (launch_wgrad_tc(dpre, h, hx0, u, Wt, bt, partials, nparts, P, off_Wih, off_Whh, off_bih, off_bhh, B, T, Fin, stream)) return 1;
+        return launch_torso_from_dx(dx, u, Wt, bt, h, dhead, partials, nparts, P, off_Wt, off_bt, off_Whead, off_bhead, B, T, Fin, NH, stream);
+    }
     if (variant == 1) {
         // tensor-core path: dW_ih / dW_hh / db (wgrad_tc.cu) and dx -> torso grads (dx_tc.cu) on tcgen05
         B200RL_REQUIRE((long long)nparts * 32 <= (long long)B * T + 31, "lstm_wgrad: nparts=%d exceeds the number of 32-row stages", nparts);

@@ -60,6 +60,26 @@ def test_forward_kernel_variants_agree_with_reference(backend, variant, monkeypa
     _close(logits.cpu(), g["fwd/logits"], what="logits")
 
 
+@pytest.mark.parametrize("bwd_variant,wgrad_variant", [(0, 0), (0, 1), (1, 1)])
+def test_backward_kernel_variants_agree_with_oracle(backend, bwd_variant, wgrad_variant, monkeypatch):
+    """Backward generations stay selectable and parity-green: FFMA BPTT + FFMA weight gradients (0, 0), FFMA BPTT +
+    tcgen05 dW / dx (0, 1), tcgen05 BPTT with the dx GEMM fused + tcgen05 dW + torso pass over dx (1, 1; default)."""
+    from b200rl import ops as O
+    from b200rl.engine import OnPolicyEngine
+    ops, dev = backend
+    monkeypatch.setattr(O, "BWD_VARIANT", bwd_variant)
+    monkeypatch.setenv("B200RL_WGRAD_VARIANT", str(wgrad_variant))
+    g = load_golden("ppo_small")
+    model = _model(g, "PPO", dev)
+    eng = OnPolicyEngine(model.actor, "PPO", oracle.DEFAULT_HYPER, ops=ops)
+    orc = oracle.OracleLearner("PPO", golden_sd(g, "sd0"))
+    for i in range(2):
+        r = orc.update(golden_batch(g, i))
+        eng.update(golden_batch(g, i, dev))
+        _close(_flat_sd_order(model.actor, eng.grad), r["grad"], rtol=1e-3, atol=2e-5 * max(1.0, float(r["grad"].abs().max())), what="grad")
+        _close(_flat_sd_order(model.actor, eng.flat), g[f"out/params/{i}"], what=f"params[{i}]", **PARAMS)
+
+
 CASES = [("ppo_small", "PPO"), ("impala_small", "IMPALA"), ("ppo_continuous_small", "PPO-Continuous"),
          ("ppo_repo_default", "PPO"), ("impala_mid", "IMPALA"), ("ppo_cfg1", "PPO")]
 
