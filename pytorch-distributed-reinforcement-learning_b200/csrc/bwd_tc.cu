@@ -30,6 +30,16 @@
 
 namespace b200rl {
 
+// phase timeline for tools/bwd_prof.cu (never compiled into the product library)
+#ifdef B200RL_BWDPROF
+__device__ unsigned long long g_bwdprof[24];
+#define BWP_INIT unsigned long long bwp_prev = clock64();
+#define BWP(i, who) do { if (tid == (who)) { unsigned long long now_ = clock64(); atomicAdd(&g_bwdprof[i], now_ - bwp_prev); bwp_prev = now_; } } while (0)
+#else
+#define BWP_INIT
+#define BWP(i, who) do { } while (0)
+#endif
+
 namespace btk {
 constexpr int H = 64, G = 256, TB = 32, NC = 512, NT = NC + 64;    // 8 critical + 8 helper warps, 2 MMA issuer warps
 constexpr int B_LBO = 144, B_SBO = 9216;                            // B: 64 core matrices along K, 16-byte skew -> conflict-free 16-byte stores
@@ -45,7 +55,7 @@ constexpr int CELLS = TB * H;
 }  // namespace btk
 
 static inline size_t bwdt_smem_bytes(int NH) {
-    return 2 * (size_t)btk::B_BYTES + btk::AL_BYTES + sizeof(float) * (size_t)(btk::NCOEF * btk::CELLS + NH * btk::H) + 64;
+    return 2 * (size_t)btk::B_BYTES + btk::AL_BYTES + sizeof(float) * (size_t)(btk::NCOEF * btk::CELLS + NH * btk::H + 8 * 8 * NH) + 64;
 }
 
 __global__ void __launch_bounds__(btk::NT, 1)
@@ -59,7 +69,8 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
     unsigned char* ALs = smem + 2 * B_BYTES;
     float* COEF = reinterpret_cast<float*>(ALs + AL_BYTES);          // COEF[(k*8 + pair)*256 + i*32 + lane]
     float* WhS = COEF + NCOEF * CELLS;                               // WhS[c*64 + j]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(WhS + NH * H);
+    float* DHS = WhS + NH * H;                                       // DHS[helper pair][8 sequences * NH]: dhead rows of the step being prepared
+    uint64_t* bars = reinterpret_cast<uint64_t*>(DHS + 8 * 8 * NH);           // (256 NH bytes: 8-byte aligned)
     uint64_t* b_full = bars, *acc_done = bars + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
 
@@ -119,10 +130,13 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
             const int ii = warp - NC / 32;                           // K half: k-steps [16 ii, 16 ii + 16) into accumulator ii
             const uint32_t D = tmem + (ii ? TM_D1 : TM_D0);
             uint32_t n = 0;
+            BWP_INIT
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int t = 0; t < T; ++t, ++n) {
+                    BWP(16, NC);
                     tc::mbar_wait(b_full, n & 1);                    // dpre_t operand written, accumulators drained
                     tc::fence_after_sync();
+                    BWP(17, NC);
 #pragma unroll
                     for (int s0 = 0; s0 < 16; ++s0) {
                         const int s = ii * 16 + s0, p0 = s * 8;
@@ -134,6 +148,7 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                         else tc::mma_tf32(D, tc::make_desc(ALs + ((p0 - KS) >> 2) * AL_LBO, AL_LBO, AL_SBO), bh, idesc, 1u);
                     }
                     tc::mma_commit(acc_done);
+                    BWP(18, NC);
                 }
             }
         }
@@ -143,6 +158,7 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
         const int pair = (q & 1) * 4 + cg;
         float* CO = COEF + pair * 256 + lane;                        // + (k*8)*256 + i*32
         uint32_t nb = 0;                                             // accumulator batches waited for so far
+        BWP_INIT
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int b0 = tile * TB + cg * 8;
             auto seq = [&](int i) { const int b = b0 + i; return b < B ? b : B - 1; };
@@ -157,12 +173,21 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                         cprev[i] = t > 0 ? c_sav[o - H] : cx0[(size_t)seq(i) * H + j];
                     }
                 };
+                float* dhs = DHS + pair * 8 * NH;
+                auto fetch_dhead = [&](int t) {                      // asynchronous: lands in shared memory, no registers held
+                    __syncwarp();                                    // the previous step's values have been consumed by every lane
+                    for (int e = lane; e < 8 * NH; e += 32) {
+                        const int i = e / NH, c = e - i * NH;
+                        cp_async4(dhs + e, dhead + (size_t)(rowof(i) + t) * NH + c);
+                    }
+                };
                 auto coefs = [&](int t) {                            // everything of step t that does not need dh
+                    cp_async_wait_all();
+                    __syncwarp();
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const float* dhr = dhead + (size_t)(rowof(i) + t) * NH;
                         float dhw = 0.f;
-                        for (int c = 0; c < NH; ++c) dhw = fmaf(__ldg(dhr + c), WhS[c * H + j], dhw);
+                        for (int c = 0; c < NH; ++c) dhw = fmaf(dhs[i * NH + c], WhS[c * H + j], dhw);
                         const float4 g4 = gcur[i];                   // i, f, g, o (post-activation)
                         const float tch = tanh_(ccur[i]);
                         float* co = CO + i * 32;
@@ -178,15 +203,19 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
 #pragma unroll
                 for (int i = 0; i < 8; ++i) ccur[i] = c_sav[(size_t)(rowof(i) + T - 1) * H + j];
                 load_step(T - 1);
+                fetch_dhead(T - 1);
                 coefs(T - 1);
                 for (int t = T - 1; t >= 0; --t) {
+                    BWP(8, 64);
                     // next step's inputs: c_{t-1} becomes c_t, loads fly during this step's hand-over
 #pragma unroll
                     for (int i = 0; i < 8; ++i) ccur[i] = cprev[i];
-                    if (t > 0) load_step(t - 1);
+                    if (t > 0) { load_step(t - 1); fetch_dhead(t - 1); }
+                    tc::named_bar_sync(1 + pair, 64);                // coefficients of step t (written one step ago) are in shared memory
                     if (t < T - 1) {                                 // drain dx_{t+1} (lanes 64..127 of both accumulators)
                         tc::mbar_wait(acc_done, nb & 1); ++nb;
                         tc::fence_after_sync();
+                        BWP(9, 64);
                         float d0[8], d1[8];
                         tc::tmem_ld8(tc::tmem_addr(tmem, my_lane, TM_D0 + cg * 8), d0);
                         tc::tmem_ld8(tc::tmem_addr(tmem, my_lane, TM_D1 + cg * 8), d1);
@@ -195,10 +224,12 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                             if (b0 + i < B) dx[(size_t)(rowof(i) + t + 1) * H + j] = d0[i] + d1[i];
                         tc::fence_before_sync();
                     }
+                    BWP(10, 64);
                     tc::mbar_arrive_warp(b_full);                    // (nothing to write: this warp's share of "accumulators drained")
-                    tc::named_bar_sync(1 + pair, 64);                // coefficients of step t are in shared memory
-                    tc::named_bar_sync(1 + pair, 64);                // ... and have been read
+                    tc::named_bar_sync(1 + pair, 64);                // ... and have been read: the slots are free for step t-1
+                    BWP(11, 64);
                     if (t > 0) coefs(t - 1);
+                    BWP(12, 64);
                 }
                 tc::mbar_wait(acc_done, nb & 1); ++nb;               // dx_0
                 tc::fence_after_sync();
@@ -217,9 +248,11 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                 for (int i = 0; i < 8; ++i) dc[i] = 0.f;
                 for (int t = T - 1; t >= 0; --t) {
                     float d0[8], d1[8];
+                    BWP(0, 0);
                     if (t < T - 1) {
                         tc::mbar_wait(acc_done, nb & 1); ++nb;
                         tc::fence_after_sync();
+                        BWP(1, 0);
                         tc::tmem_ld8(tc::tmem_addr(tmem, my_lane, TM_D0 + cg * 8), d0);
                         tc::tmem_ld8(tc::tmem_addr(tmem, my_lane, TM_D1 + cg * 8), d1);
                         tc::fence_before_sync();
@@ -227,13 +260,16 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
 #pragma unroll
                         for (int i = 0; i < 8; ++i) { d0[i] = 0.f; d1[i] = 0.f; }
                     }
+                    BWP(2, 0);
                     tc::named_bar_sync(1 + pair, 64);
+                    BWP(3, 0);
                     float cf[8][NCOEF];
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
 #pragma unroll
                         for (int k = 0; k < NCOEF; ++k) cf[i][k] = CO[k * 2048 + i * 32];
                     tc::named_bar_sync(1 + pair, 64);
+                    BWP(4, 0);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float dh = d0[i] + d1[i] + cf[i][0];
@@ -249,8 +285,10 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                         *reinterpret_cast<float4*>(B_hi + ob) = hi;
                         *reinterpret_cast<float4*>(B_lo + ob) = lo;
                     }
+                    BWP(5, 0);
                     tc::fence_async_smem();
                     tc::mbar_arrive_warp(b_full);
+                    BWP(6, 0);
                 }
                 tc::mbar_wait(acc_done, nb & 1); ++nb;               // batch of step 0 (dx_0): keeps the phase count in step
             }

@@ -108,6 +108,19 @@ __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 }  // namespace b200rl
 
+namespace b200rl {
+// 4-byte asynchronous global -> shared copy (LDGSTS): no destination register, completion via cp_async_wait_all()
+#ifdef B200RL_EMUL
+inline void cp_async4(float* dst_smem, const float* src) { *dst_smem = *src; }
+inline void cp_async_wait_all() {}
+#else
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#endif
+}  // namespace b200rl
+
 // Error plumbing shared by the C-ABI entry points.
 namespace b200rl {
 int set_error(const char* fmt, ...);

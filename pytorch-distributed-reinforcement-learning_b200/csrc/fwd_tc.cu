@@ -16,12 +16,12 @@
 // memory every MMA pulled 4 KB of weights through the 128 B/clk port (240 KB = 1.9K cycles per step,
 // measured with tools/fwd_prof.cu); from TMEM only the 1 KB B slices cross it.
 //
-// Cell phase, 8 warps: TMEM lane l of tile X holds gate i (l < 64) or f (l >= 64) of unit l % 64, tile Y
-// holds g or o, and a warp can only read its own lane quarter -- so warps 0,1 (and 4,5) see (i, g) of
-// 32 units each and warps 2,3 (6,7) see (f, o) of the same units; warps 0-3 take sequences 0-15,
-// warps 4-7 sequences 16-31.  Each thread reads its two gate rows for 16 sequences, hands the raw sums
-// of 8 of them to its partner thread (same unit, other gate pair) through shared memory and gets the
-// partner's for the other 8, then owns 8 complete cells: add xproj, four activations, c, h, saved
+// Cell phase, 16 warps: TMEM lane l of tile X holds gate i (l < 64) or f (l >= 64) of unit l % 64, tile Y
+// holds g or o, and a warp can only read its own lane quarter -- so warps with id % 4 in {0, 1} see (i, g)
+// of 32 units each and id % 4 in {2, 3} see (f, o) of the same units; warps 4g .. 4g+3 take sequences
+// 8g .. 8g+7.  Each thread reads its two gate rows for 8 sequences, hands the raw sums of 4 of them to
+// its partner thread (same unit, other gate pair) through shared memory and gets the partner's for the
+// other 4, then owns 4 complete cells: add xproj, four activations, c, h, saved
 // activations, next B operand.  Global accesses are 128-byte (c, h) or 512-byte (xproj in, gates out)
 // contiguous per warp and row, each byte touched by exactly one thread.
 //
@@ -47,11 +47,15 @@ __device__ unsigned long long g_fwdprof[16];
 #endif
 
 namespace ftk {
-constexpr int H = 64, G = 256, TB = 32, NC = 256, NT = NC + 64;   // 8 cell warps + 2 MMA issuer warps
+constexpr int H = 64, G = 256, TB = 32;
+constexpr int NG = 4;                                      // sequence groups: 4 cell warps (one per TMEM lane quarter) each
+constexpr int RW = TB / NG, CT = RW / 2;                   // sequences a warp reads / cells a thread owns
+constexpr int NC = NG * 128, NT = NC + 64;                 // cell warps + 2 MMA issuer warps
 constexpr int TM_D = 0, TM_A = 64, TM_COLS = 512;          // TMEM columns: D tiles X|Y at 0..63 ; A at 64 + (mt*2 + lo)*64 + k
 constexpr int B_LBO = 144, B_SBO = 2304;                   // B: 16 core matrices along K, 16-byte skew -> conflict-free 4-byte scatter
 constexpr int B_BYTES = (TB / 8) * B_SBO;                  // 9216 per hi / lo
-constexpr int EXF = 4 * 2 * 16 * 32;                       // swap buffer: [pair][direction][slot][lane] floats
+constexpr int EXF = 2 * NG * 2 * RW * 32;                  // swap buffer: [pair][direction][slot][lane] floats
+static_assert(RW == 8, "the cell phase reads 8 accumulator columns per tile (tmem_ld8)");
 static_assert(15 * B_LBO + 128 <= B_SBO, "core matrices of one 8-row group must fit below SBO");
 }  // namespace ftk
 
@@ -83,7 +87,7 @@ lstm_fwdt_kernel(float* xg, const float* __restrict__ hx0, const float* __restri
     const uint32_t tmem = *tmem_slot;
     // one-time: W_hh (PyTorch row order n = g*64 + j) -> TF32 hi/lo in TMEM: warps 0-3 fill tile 0, warps 4-7 tile 1,
     // thread = row n (its own TMEM lane), 16 columns per store
-    if (compute) {
+    if (warp < 8) {
         const int mt = warp >> 2, m = 32 * (warp & 3) + lane;
         const float* wrow = W_hh + (size_t)(mt * 128 + m) * H;
 #ifdef B200RL_EMUL
@@ -135,14 +139,14 @@ lstm_fwdt_kernel(float* xg, const float* __restrict__ hx0, const float* __restri
             }
         }
     } else {
-        const int q = warp & 3, ch = warp >> 2;                // TMEM lane quarter, sequence half
+        const int q = warp & 3, ch = warp >> 2;                // TMEM lane quarter, sequence group
         const bool fo = q >= 2;                                // false: gates (i, g) ; true: gates (f, o)
         const int j = (q & 1) * 32 + lane;                     // unit
         const int pair = (q & 1) + 2 * ch;
-        float* EXs = EX + pair * 1024 + (fo ? 512 : 0);        // my outgoing slots [slot][lane]
-        const float* EXr = EX + pair * 1024 + (fo ? 0 : 512);  // the partner's
-        const int rbase = ch * 16;                             // the 16 sequences this warp activates
-        const int mine = fo ? 8 : 0;                           // the 8 of them this thread finishes (the other 8 go to the partner)
+        float* EXs = EX + pair * (2 * RW * 32) + (fo ? RW * 32 : 0);        // my outgoing slots [slot][lane]
+        const float* EXr = EX + pair * (2 * RW * 32) + (fo ? 0 : RW * 32);  // the partner's
+        const int rbase = ch * RW;                             // the RW sequences this warp reads from tensor memory
+        const int mine = fo ? CT : 0;                          // the CT of them this thread finishes (the others go to the partner)
 #ifdef B200RL_EMUL
         const int addr_lane = 32 * q + lane;
 #else
@@ -157,9 +161,9 @@ lstm_fwdt_kernel(float* xg, const float* __restrict__ hx0, const float* __restri
             // rowof(i) + t ; sequences past B are clamped for loads and masked for stores
             auto seq = [&](int i) { const int b = b0 + rbase + mine + i; return b < B ? b : B - 1; };
             auto rowof = [&](int i) { return (unsigned)seq(i) * (unsigned)T; };       // B*T < 2^31 (checked by the launcher)
-            float cst[8];
+            float cst[CT];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < CT; ++i) {
                 const size_t b = (size_t)seq(i);
                 cst[i] = cx0[b * H + j];
                 float hi, lo;
@@ -168,9 +172,9 @@ lstm_fwdt_kernel(float* xg, const float* __restrict__ hx0, const float* __restri
                 *reinterpret_cast<float*>(B_hi + ob) = hi;
                 *reinterpret_cast<float*>(B_lo + ob) = lo;
             }
-            float4 xq[8];                                      // xproj of my cells, one step ahead
+            float4 xq[CT];                                     // xproj of my cells, one step ahead
 #pragma unroll
-            for (int i = 0; i < 8; ++i) xq[i] = ld4(xg + ((size_t)rowof(i) * H + j) * 4);
+            for (int i = 0; i < CT; ++i) xq[i] = ld4(xg + ((size_t)rowof(i) * H + j) * 4);
             tc::fence_async_smem();
             tc::fence_before_sync();
             tc::mbar_arrive_warp(b_full);
@@ -180,22 +184,22 @@ lstm_fwdt_kernel(float* xg, const float* __restrict__ hx0, const float* __restri
                 tc::mbar_wait(acc_done, n & 1);
                 tc::fence_after_sync();
                 FWP(1, 0);
-                float xa[16], xb[16];
-                tc::tmem_ld16(tc::tmem_addr(tmem, addr_lane, TM_D + rbase), xa);       // gate i (or f) of unit j, 16 sequences
-                tc::tmem_ld16(tc::tmem_addr(tmem, addr_lane, TM_D + TB + rbase), xb);  // gate g (or o)
+                float xa[RW], xb[RW];
+                tc::tmem_ld8(tc::tmem_addr(tmem, addr_lane, TM_D + rbase), xa);        // gate i (or f) of unit j, RW sequences
+                tc::tmem_ld8(tc::tmem_addr(tmem, addr_lane, TM_D + TB + rbase), xb);   // gate g (or o)
                 FWP(2, 0);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { EXs[(2 * i) * 32 + lane] = fo ? xa[i] : xa[8 + i]; EXs[(2 * i + 1) * 32 + lane] = fo ? xb[i] : xb[8 + i]; }
+                for (int i = 0; i < CT; ++i) { EXs[(2 * i) * 32 + lane] = fo ? xa[i] : xa[CT + i]; EXs[(2 * i + 1) * 32 + lane] = fo ? xb[i] : xb[CT + i]; }
                 FWP(3, 0);
                 tc::named_bar_sync(1 + pair, 64);
                 FWP(4, 0);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < CT; ++i) {
                     const float pa = EXr[(2 * i) * 32 + lane], pb = EXr[(2 * i + 1) * 32 + lane];
                     const float4 x = xq[i];
                     if (t + 1 < T) xq[i] = ld4(xg + ((size_t)(rowof(i) + t + 1) * H + j) * 4);
-                    const float ig = sigm((fo ? pa : xa[i]) + x.x), fg = sigm((fo ? xa[8 + i] : pa) + x.y);
-                    const float gg = tanh_((fo ? pb : xb[i]) + x.z), og = sigm((fo ? xb[8 + i] : pb) + x.w);
+                    const float ig = sigm((fo ? pa : xa[i]) + x.x), fg = sigm((fo ? xa[CT + i] : pa) + x.y);
+                    const float gg = tanh_((fo ? pb : xb[i]) + x.z), og = sigm((fo ? xb[CT + i] : pb) + x.w);
                     const float cn = fmaf(fg, cst[i], ig * gg);
                     const float hh = og * tanh_(cn);
                     cst[i] = cn;

@@ -1,0 +1,40 @@
+// Phase timeline of lstm_bwdt_kernel (dev tool): cycles per timestep seen by a critical thread, a helper thread and an MMA issuer.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DB200RL_BWDPROF \
+//     -I pytorch-distributed-reinforcement-learning_b200/csrc -I include tools/bwd_prof.cu -o tools/_build/bwd_prof
+#include <cstdarg>
+#include <cstdio>
+#include "common.cuh"
+namespace b200rl {
+int set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vfprintf(stderr, fmt, ap); va_end(ap); fputc('\n', stderr); return 1; }
+int check_launch(const char* what) { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) return set_error("%s: %s", what, cudaGetErrorString(e)); return 0; }
+}
+#include "bwd_tc.cu"
+using namespace b200rl;
+int main() {
+    const int B = 4096, T = 128, NH = 3;
+    const long long rows = (long long)B * T;
+    float *gates, *c, *cx0, *Whh, *Wih, *Whead, *dhead, *dx;
+    cudaMalloc(&gates, rows * 256 * 4); cudaMalloc(&c, rows * 64 * 4); cudaMalloc(&cx0, B * 64 * 4); cudaMalloc(&Whh, 256 * 64 * 4);
+    cudaMalloc(&Wih, 256 * 64 * 4); cudaMalloc(&Whead, NH * 64 * 4); cudaMalloc(&dhead, rows * NH * 4); cudaMalloc(&dx, rows * 64 * 4);
+    cudaMemset(gates, 0, rows * 256 * 4); cudaMemset(c, 0, rows * 64 * 4); cudaMemset(cx0, 0, B * 64 * 4); cudaMemset(Whh, 0, 256 * 64 * 4);
+    cudaMemset(Wih, 0, 256 * 64 * 4); cudaMemset(Whead, 0, NH * 64 * 4); cudaMemset(dhead, 0, rows * NH * 4);
+    for (int it = 0; it < 2; ++it) launch_bwd_tc(dhead, Whead, Whh, Wih, gates, c, cx0, dx, B, T, NH, 148, 0);
+    cudaDeviceSynchronize();
+    unsigned long long z[24] = {0};
+    cudaMemcpyToSymbol(g_bwdprof, z, sizeof(z));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    launch_bwd_tc(dhead, Whead, Whh, Wih, gates, c, cx0, dx, B, T, NH, 148, 0);
+    cudaEventRecord(e1);
+    cudaDeviceSynchronize();
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    cudaMemcpyFromSymbol(z, g_bwdprof, sizeof(z));
+    const double steps = (B / 32.0) * T;
+    printf("bwd_tc %.3f ms; cycles/step critical thread: loop top %.0f | wait acc_done %.0f | tmem ld %.0f | wait coefs %.0f | read coefs + bar %.0f | 8 cells %.0f | fence+arrive %.0f\n",
+           ms, z[0] / steps, z[1] / steps, z[2] / steps, z[3] / steps, z[4] / steps, z[5] / steps, z[6] / steps);
+    printf("   helper: loop top %.0f | issue loads + wait acc_done %.0f | drain dx %.0f | arrive + 2 pair barriers %.0f | coefs(t-1) %.0f\n",
+           z[8] / steps, z[9] / steps, z[10] / steps, z[11] / steps, z[12] / steps);
+    printf("   issuer: loop top %.0f | wait b_full %.0f | issue 48 MMAs + commit %.0f\n", z[16] / steps, z[17] / steps, z[18] / steps);
+    printf("%s\n", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
