@@ -355,8 +355,8 @@ def main():
             "lstm_fwd": 4 * (bt_ * (F + 6 * H) + 2 * B * H + L.P),
             "head_fwd": 4 * (bt_ * (H + L.NH)),
             "ppo_head": 4 * (bt_ * (2 * L.NH + 4)),
-            "lstm_bwd": 4 * (bt_ * (4 * H + H + L.NH + 4 * H) + B * H),
-            "lstm_wgrad": 4 * (bt_ * (4 * H + H + F + L.NH) + eng.nparts * L.P),
+            "lstm_bwd": 4 * (bt_ * (4 * H + H + L.NH + 4 * H + H) + B * H),          # + dx (B,T,H) written by the tcgen05 BPTT kernel
+            "lstm_wgrad": 4 * (bt_ * (4 * H + H + H + F + L.NH) + eng.nparts * L.P),    # dpre, h, dx, u, dhead
             "reduce_partials": 4 * (eng.nparts * L.P + L.P),
             "clip_rmsprop": 4 * 6 * L.P,
         }
@@ -370,7 +370,9 @@ def main():
         out["roofline"] = {
             "kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
             "traffic": load_traffic(dom), "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes[dom],
-            "note": "fp32 FFMA kernel: the binding pipe is FP32/shared-memory, not HBM; see fp32 block and DESIGN.md",
+            "note": "persistent recurrent kernel (per-step tcgen05 GEMM + cell phase, 128 dependent steps): bound by the per-step "
+                    "serial latency (MMA issue ~31-44 cycles per M128xN32xK8 tf32 MMA, MUFU-bound cell phase), not by HBM; "
+                    "`fp32` = algorithmic flop rate vs the FP32 FFMA peak for scale (the GEMMs run as 3xTF32 on tcgen05); see DESIGN.md 4",
             "fp32": {"achieved_tflops": algo_flop.get(dom, 0) / (kms[dom] * 1e-3) / 1e12, "peak_tflops": fp32_peak,
                      "frac": algo_flop.get(dom, 0) / (kms[dom] * 1e-3) / 1e12 / fp32_peak},
         }

@@ -526,7 +526,8 @@ lstm_fwd16_kernel(const float* __restrict__ u, const float* __restrict__ hx0, co
 }
 
 // ============================================================================== head_fwd
-// head_out[row][c] = b[c] + sum_k h[row][k] W[c][k];   128 rows per CTA, staged through smem.
+// head_out[row][c] = b[c] + sum_k h[row][k] W[c][k];   128 rows per CTA pass, staged through smem; the next pass's
+// rows are already in flight (registers) while this one is reduced.
 constexpr int HR = 128;
 __global__ void __launch_bounds__(HR)
 head_fwd_kernel(const float* __restrict__ h, const float* __restrict__ W, const float* __restrict__ b,
@@ -538,17 +539,29 @@ head_fwd_kernel(const float* __restrict__ h, const float* __restrict__ W, const 
     for (int i = tid; i < NH * H; i += HR) Ws[i] = W[i];
     if (tid < NH) bs[tid] = b[tid];
     const long long nblk = (rows + HR - 1) / HR;
+    constexpr int NV = HR * H / 4 / HR;                   // float4 per thread per pass (16)
+    float4 pv[NV];
+    auto fetch = [&](long long blk) {
+        const long long r0 = blk * HR;
+#pragma unroll
+        for (int it = 0; it < NV; ++it) {
+            const int idx = it * HR + tid, r = idx >> 4, c4 = idx & 15;
+            pv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (blk < nblk && r0 + r < rows) pv[it] = ld4(h + (size_t)(r0 + r) * H + c4 * 4);
+        }
+    };
+    fetch(blockIdx.x);
     for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
         const long long r0 = blk * HR;
         __syncthreads();
-        for (int it = 0; it < HR * H / 4 / HR; ++it) {
-            int idx = it * HR + tid, r = idx >> 4, c4 = idx & 15;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r0 + r < rows) v = ld4(h + (size_t)(r0 + r) * H + c4 * 4);
+#pragma unroll
+        for (int it = 0; it < NV; ++it) {
+            const int idx = it * HR + tid, r = idx >> 4, c4 = idx & 15;
             float* d = Ht + r * (H + 1) + c4 * 4;
-            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            d[0] = pv[it].x; d[1] = pv[it].y; d[2] = pv[it].z; d[3] = pv[it].w;
         }
         __syncthreads();
+        fetch(blk + gridDim.x);
         if (r0 + tid < rows) {
             const float* hr = Ht + tid * (H + 1);
             for (int c = 0; c < NH; ++c) {
