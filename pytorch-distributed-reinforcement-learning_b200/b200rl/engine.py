@@ -114,11 +114,7 @@ class OnPolicyEngine:
         self.n_launches += 8 + {0: 0, 1: 2, 2: 1}[self.wgrad_variant] + (1 if _ops.FWD_VARIANT >= 2 else 0)
 
     # -------------------------------------------------------------------- scalars
-    def losses(self):
-        """Host copy of the loss scalars of the LAST update (synchronises).  Keys follow
-        the reference's `detached_losses` (ppo/learning.py:83-88); `ratio` is reduced to
-        (min, max, mean) instead of shipping the (B,T-1,1) tensor to the host."""
-        B, T = self._shape
+    def _reduced_scalars(self):
         s = self.scalars
         if self.world > 1:
             s = s.clone()
@@ -127,7 +123,10 @@ class OnPolicyEngine:
             sums = s[:4].clone()
             torch.distributed.all_reduce(sums, group=self.pg)
             s = torch.cat([sums, torch.stack([-mm[0], mm[1]]), s[6:]])
-        v = s.cpu().tolist()
+        return s
+
+    def _losses_from(self, v, grad_norm):
+        B, T = self._shape
         N = float(B * (T - 1) * self.world)
         hp = self.hp
         pol, val, ent = v[0] / N, v[1] / N, v[2] / N
@@ -135,8 +134,44 @@ class OnPolicyEngine:
             "policy-loss": pol, "value-loss": val, "policy-entropy": ent,
             "loss": hp["policy_loss_coef"] * pol + hp["value_loss_coef"] * val - hp["entropy_coef"] * ent,
             "ratio-min": v[4], "ratio-max": v[5], "ratio-avg": v[3] / N,
-            "grad-norm": float(self.grad_norm.item()),
+            "grad-norm": grad_norm,
         }
+
+    def losses(self):
+        """Host copy of the loss scalars of the LAST update (synchronises).  Keys follow
+        the reference's `detached_losses` (ppo/learning.py:83-88); `ratio` is reduced to
+        (min, max, mean) instead of shipping the (B,T-1,1) tensor to the host."""
+        return self._losses_from(self._reduced_scalars().cpu().tolist(), float(self.grad_norm.item()))
+
+    # ---------------------------------------------------------- stream-ordered snapshot
+    def snapshot_async(self, with_losses=True):
+        """Enqueue, behind the update just issued, the device->pinned-host copies of everything the host consumes per
+        iteration (flat parameters for `pub_model`, loss scalars, gradient norm) and return a handle; nothing blocks.
+        `snapshot_wait(handle)` later returns (host_flat, losses-or-None).  Two slots alternate, so a handle stays valid
+        until the snapshot after the next one is taken."""
+        if not hasattr(self, "_snap"):
+            pin = self.device.type == "cuda"
+            self._snap = [dict(flat=torch.empty(self.flat.shape, dtype=torch.float32, pin_memory=pin),
+                               sc=torch.empty(8, dtype=torch.float64, pin_memory=pin),
+                               gn=torch.empty(1, dtype=torch.float32, pin_memory=pin)) for _ in range(2)]
+            self._snap_i = 0
+        self._snap_i ^= 1
+        b = self._snap[self._snap_i]
+        b["flat"].copy_(self.flat.detach(), non_blocking=True)
+        if with_losses:
+            b["sc"].copy_(self._reduced_scalars(), non_blocking=True)
+            b["gn"].copy_(self.grad_norm, non_blocking=True)
+        ev = None
+        if self.device.type == "cuda":
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+        return (b, ev, with_losses)
+
+    def snapshot_wait(self, handle):
+        b, ev, with_losses = handle
+        if ev is not None:
+            ev.synchronize()
+        return b["flat"], (self._losses_from(b["sc"].tolist(), float(b["gn"][0])) if with_losses else None)
 
 
 class VMPOEngine(OnPolicyEngine):

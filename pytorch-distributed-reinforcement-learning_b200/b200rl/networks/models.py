@@ -107,6 +107,11 @@ class _FlatNet(nn.Module):
         from collections import OrderedDict
         return OrderedDict((n, v.clone()) for n, v in self.views_of(host).items())
 
+    def state_dict_from_flat(self, host_flat):
+        """`state_dict()`-shaped clones cut out of a host copy of the flat buffer (see engine.snapshot_async)."""
+        from collections import OrderedDict
+        return OrderedDict((n, v.clone()) for n, v in self.views_of(host_flat).items())
+
     def flat_parameters(self):
         """The flat buffer (re-flattened first if something, e.g. unpickling, re-homed the views)."""
         L = self._layout

@@ -78,3 +78,36 @@ def test_learning_coroutine_matches_reference(backend, name, algo, tmp_path):
     # checkpoint written at idx 0 under the reference's file name, loadable, reference keys
     ck = torch.load(tmp_path / f"{algo}_0.pt", weights_only=False)
     assert list(ck.actor.state_dict().keys()) == ref_keys
+
+
+@pytest.mark.gpu
+def test_host_stager_prefetch_is_consumed_and_buffers_rotate():
+    """`prefetch(*batch)` followed by `stager(*batch)` must hand out the prefetched device tensors (no second H2D), and a
+    buffer set must not be overwritten while the previous batch may still be read."""
+    from b200rl.utils.utils import HostStager
+    dev = torch.device("cuda:0")
+    st = HostStager(dev)
+    B, T, f = 8, 4, 3
+    g = torch.Generator().manual_seed(0)
+
+    def host_batch():
+        return (torch.randn(B, T, f, generator=g).pin_memory(), torch.randn(B, T, 1, generator=g).pin_memory(),
+                torch.randn(B, T, 1, generator=g).pin_memory(), torch.randn(B, T, 2, generator=g).pin_memory(),
+                torch.randn(B, T, 1, generator=g).pin_memory(), torch.randn(B, T, 1, generator=g).pin_memory(),
+                torch.randn(B, T, 5, generator=g), torch.randn(B, T, 5, generator=g))       # hx, cx as (B, T, H), pageable
+
+    batches = [host_batch() for _ in range(4)]
+    d0 = st(*batches[0])                                  # first batch: synchronous path
+    assert st.prefetch_hits == 0
+    for i in range(1, 4):
+        st.prefetch(*batches[i])
+        keep = [t.clone() for t in d0 if t is not None]   # what the "update" of the previous batch reads
+        d1 = st(*batches[i])
+        assert st.prefetch_hits == i
+        torch.cuda.synchronize()
+        for a, b in zip(keep, [t for t in d0 if t is not None]):
+            torch.testing.assert_close(a, b, rtol=0, atol=0)          # the previous set was not clobbered by the prefetch
+        for j, (h, d) in enumerate(zip(batches[i], d1)):
+            want = h[:, 0] if j >= 6 else h
+            torch.testing.assert_close(d.cpu(), want, rtol=0, atol=0)
+        d0 = d1
