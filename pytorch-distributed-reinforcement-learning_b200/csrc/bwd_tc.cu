@@ -21,7 +21,8 @@
 //   P_o = tc o(1-o), Q = o(1-tc^2), P_i = g i(1-i), P_f = c_{t-1} f(1-f), P_g = i(1-g^2), f -- computed for
 //   step t-1 WHILE the tensor core runs step t, and handed over through shared memory; they also drain the
 //   dx lanes of the accumulator to `dx`.
-//   CRITICAL warps (id % 4 in {0, 1}) wait for the accumulator, then need 7 flops per cell:
+//   CRITICAL warps (id % 4 in {0, 1}) wait for the accumulator and publish dh_rec of half of their cells to the
+//   partner; then BOTH threads of a pair finish four cells each with 7 flops per cell:
 //   dh = D + dhW ; d_o' = dh P_o ; dct = dh Q + dc ; (dct P_i, dct P_f, dct P_g) ; dc = dct f,
 //   store dpre (global + B operand hi/lo) and hand the step to the issuers.
 #include "common.cuh"
@@ -55,7 +56,7 @@ constexpr int CELLS = TB * H;
 }  // namespace btk
 
 static inline size_t bwdt_smem_bytes(int NH) {
-    return 2 * (size_t)btk::B_BYTES + btk::AL_BYTES + sizeof(float) * (size_t)(btk::NCOEF * btk::CELLS + NH * btk::H + 8 * 8 * NH) + 64;
+    return 2 * (size_t)btk::B_BYTES + btk::AL_BYTES + sizeof(float) * (size_t)(btk::NCOEF * btk::CELLS + NH * btk::H + 8 * 8 * NH + 8 * 4 * 32) + 64;
 }
 
 __global__ void __launch_bounds__(btk::NT, 1)
@@ -70,7 +71,8 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
     float* COEF = reinterpret_cast<float*>(ALs + AL_BYTES);          // COEF[(k*8 + pair)*256 + i*32 + lane]
     float* WhS = COEF + NCOEF * CELLS;                               // WhS[c*64 + j]
     float* DHS = WhS + NH * H;                                       // DHS[helper pair][8 sequences * NH]: dhead rows of the step being prepared
-    uint64_t* bars = reinterpret_cast<uint64_t*>(DHS + 8 * 8 * NH);           // (256 NH bytes: 8-byte aligned)
+    float* DHX = DHS + 8 * 8 * NH;                                   // DHX[pair][4][lane]: dh_rec of the cells the helper finishes
+    uint64_t* bars = reinterpret_cast<uint64_t*>(DHX + 8 * 4 * 32);           // (8-byte aligned)
     uint64_t* b_full = bars, *acc_done = bars + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
 
@@ -157,12 +159,36 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
         const int j = (q & 1) * 32 + lane;                           // LSTM unit (critical / helper) = dx column (helper, TMEM side)
         const int pair = (q & 1) * 4 + cg;
         float* CO = COEF + pair * 256 + lane;                        // + (k*8)*256 + i*32
+        float* DX = DHX + pair * 128 + lane;                         // + i*32
         uint32_t nb = 0;                                             // accumulator batches waited for so far
         BWP_INIT
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int b0 = tile * TB + cg * 8;
             auto seq = [&](int i) { const int b = b0 + i; return b < B ? b : B - 1; };
             auto rowof = [&](int i) { return (unsigned)seq(i) * (unsigned)T; };   // B*T < 2^31 (checked by the launcher)
+            // the dh-dependent tail of the cell backward for cells i0 .. i0+3 of (unit j, this sequence group): 7 flops per
+            // cell from the prepared coefficients, dpre to global memory and to the B operand (hi / lo)
+            auto cell_phase = [&](int t, int i0, const float (&dh4)[4], float (&dc)[4]) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int ii = i0 + i;
+                    float cf[NCOEF];
+#pragma unroll
+                    for (int k = 0; k < NCOEF; ++k) cf[k] = CO[k * 2048 + ii * 32];
+                    const float dh = dh4[i] + cf[0];
+                    const float dct = fmaf(dh, cf[2], dc[i]);
+                    const float4 dp = make_float4(dct * cf[3], dct * cf[4], dct * cf[5], dh * cf[1]);
+                    dc[i] = dct * cf[6];
+                    if (b0 + ii < B) st4(gates + ((size_t)(rowof(ii) + t) * H + j) * 4, dp);
+                    float4 hi, lo;
+                    tc::split_tf32(dp.x, hi.x, lo.x); tc::split_tf32(dp.y, hi.y, lo.y);
+                    tc::split_tf32(dp.z, hi.z, lo.z); tc::split_tf32(dp.w, hi.w, lo.w);
+                    const int r = cg * 8 + ii;
+                    const int ob = (r & 7) * 16 + (r >> 3) * B_SBO + j * B_LBO;
+                    *reinterpret_cast<float4*>(B_hi + ob) = hi;
+                    *reinterpret_cast<float4*>(B_lo + ob) = lo;
+                }
+            };
             if (helper) {
                 float4 gcur[8]; float ccur[8], cprev[8];
                 auto load_step = [&](int t) {                        // saved activations of step t and c_{t-1}
@@ -184,14 +210,27 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                 auto coefs = [&](int t) {                            // everything of step t that does not need dh
                     cp_async_wait_all();
                     __syncwarp();
+                    BWP(13, 64);
+#ifdef B200RL_BWDPROF
+                    if (gcur[0].x == 1234.5f && cprev[7] == 1234.5f && gcur[7].w == 1234.5f) ccur[0] = 0.f;   // force the prefetched loads to have landed
+                    BWP(14, 64);
+#endif
+                    // dhead . W_head with the head index outermost: ONE runtime loop with eight independent FMA chains inside (the
+                    // per-cell form compiled to a branchy unroll cascade per cell that kept the eight cells from overlapping: 4.2K cycles)
+                    float dhw[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dhw[i] = 0.f;
+                    for (int c = 0; c < NH; ++c) {
+                        const float w = WhS[c * H + j];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) dhw[i] = fmaf(dhs[i * NH + c], w, dhw[i]);
+                    }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        float dhw = 0.f;
-                        for (int c = 0; c < NH; ++c) dhw = fmaf(dhs[i * NH + c], WhS[c * H + j], dhw);
                         const float4 g4 = gcur[i];                   // i, f, g, o (post-activation)
                         const float tch = tanh_(ccur[i]);
                         float* co = CO + i * 32;
-                        co[0 * 2048] = dhw;
+                        co[0 * 2048] = dhw[i];
                         co[1 * 2048] = tch * g4.w * (1.f - g4.w);
                         co[2 * 2048] = g4.w * (1.f - tch * tch);
                         co[3 * 2048] = g4.z * g4.x * (1.f - g4.x);
@@ -205,14 +244,17 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                 load_step(T - 1);
                 fetch_dhead(T - 1);
                 coefs(T - 1);
+                float dc[4];                                         // cells 4..7 of this (unit, sequence group) are finished here
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dc[i] = 0.f;
                 for (int t = T - 1; t >= 0; --t) {
                     BWP(8, 64);
                     // next step's inputs: c_{t-1} becomes c_t, loads fly during this step's hand-over
 #pragma unroll
                     for (int i = 0; i < 8; ++i) ccur[i] = cprev[i];
                     if (t > 0) { load_step(t - 1); fetch_dhead(t - 1); }
-                    tc::named_bar_sync(1 + pair, 64);                // coefficients of step t (written one step ago) are in shared memory
-                    if (t < T - 1) {                                 // drain dx_{t+1} (lanes 64..127 of both accumulators)
+                    float dxs[8];                                    // dx_{t+1}: lanes 64..127 of both accumulators
+                    if (t < T - 1) {
                         tc::mbar_wait(acc_done, nb & 1); ++nb;
                         tc::fence_after_sync();
                         BWP(9, 64);
@@ -220,14 +262,24 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                         tc::tmem_ld8(tc::tmem_addr(tmem, my_lane, TM_D0 + cg * 8), d0);
                         tc::tmem_ld8(tc::tmem_addr(tmem, my_lane, TM_D1 + cg * 8), d1);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            if (b0 + i < B) dx[(size_t)(rowof(i) + t + 1) * H + j] = d0[i] + d1[i];
+                        for (int i = 0; i < 8; ++i) dxs[i] = d0[i] + d1[i];
                         tc::fence_before_sync();
                     }
+                    tc::named_bar_sync(1 + pair, 64);                // the critical thread has published dh_rec of my cells
                     BWP(10, 64);
-                    tc::mbar_arrive_warp(b_full);                    // (nothing to write: this warp's share of "accumulators drained")
-                    tc::named_bar_sync(1 + pair, 64);                // ... and have been read: the slots are free for step t-1
+                    float dh4[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) dh4[i] = DX[i * 32];
+                    cell_phase(t, 4, dh4, dc);
+                    tc::fence_async_smem();
+                    tc::mbar_arrive_warp(b_full);
+                    tc::named_bar_sync(1 + pair, 64);                // both threads have read their coefficients: the slots are free for step t-1
                     BWP(11, 64);
+                    if (t < T - 1) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (b0 + i < B) dx[(size_t)(rowof(i) + t + 1) * H + j] = dxs[i];
+                    }
                     if (t > 0) coefs(t - 1);
                     BWP(12, 64);
                 }
@@ -243,51 +295,37 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                     tc::fence_before_sync();
                 }
             } else {
-                float dc[8];
+                float dc[4];                                         // cells 0..3
 #pragma unroll
-                for (int i = 0; i < 8; ++i) dc[i] = 0.f;
+                for (int i = 0; i < 4; ++i) dc[i] = 0.f;
                 for (int t = T - 1; t >= 0; --t) {
-                    float d0[8], d1[8];
+                    float dhr[8];
                     BWP(0, 0);
                     if (t < T - 1) {
                         tc::mbar_wait(acc_done, nb & 1); ++nb;
                         tc::fence_after_sync();
                         BWP(1, 0);
+                        float d0[8], d1[8];
                         tc::tmem_ld8(tc::tmem_addr(tmem, my_lane, TM_D0 + cg * 8), d0);
                         tc::tmem_ld8(tc::tmem_addr(tmem, my_lane, TM_D1 + cg * 8), d1);
                         tc::fence_before_sync();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) dhr[i] = d0[i] + d1[i];
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) { d0[i] = 0.f; d1[i] = 0.f; }
+                        for (int i = 0; i < 8; ++i) dhr[i] = 0.f;
                     }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) DX[i * 32] = dhr[4 + i];
                     BWP(2, 0);
                     tc::named_bar_sync(1 + pair, 64);
                     BWP(3, 0);
-                    float cf[8][NCOEF];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-#pragma unroll
-                        for (int k = 0; k < NCOEF; ++k) cf[i][k] = CO[k * 2048 + i * 32];
-                    tc::named_bar_sync(1 + pair, 64);
-                    BWP(4, 0);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float dh = d0[i] + d1[i] + cf[i][0];
-                        const float dct = fmaf(dh, cf[i][2], dc[i]);
-                        const float4 dp = make_float4(dct * cf[i][3], dct * cf[i][4], dct * cf[i][5], dh * cf[i][1]);
-                        dc[i] = dct * cf[i][6];
-                        if (b0 + i < B) st4(gates + ((size_t)(rowof(i) + t) * H + j) * 4, dp);
-                        float4 hi, lo;
-                        tc::split_tf32(dp.x, hi.x, lo.x); tc::split_tf32(dp.y, hi.y, lo.y);
-                        tc::split_tf32(dp.z, hi.z, lo.z); tc::split_tf32(dp.w, hi.w, lo.w);
-                        const int r = cg * 8 + i;
-                        const int ob = (r & 7) * 16 + (r >> 3) * B_SBO + j * B_LBO;
-                        *reinterpret_cast<float4*>(B_hi + ob) = hi;
-                        *reinterpret_cast<float4*>(B_lo + ob) = lo;
-                    }
+                    const float dh4[4] = {dhr[0], dhr[1], dhr[2], dhr[3]};
+                    cell_phase(t, 0, dh4, dc);
                     BWP(5, 0);
                     tc::fence_async_smem();
                     tc::mbar_arrive_warp(b_full);
+                    tc::named_bar_sync(1 + pair, 64);
                     BWP(6, 0);
                 }
                 tc::mbar_wait(acc_done, nb & 1); ++nb;               // batch of step 0 (dx_0): keeps the phase count in step

@@ -19,9 +19,16 @@ __device__ __forceinline__ float grad_norm_and_coef(const float* grad, long long
     __shared__ double scratch[32];
     __shared__ float coef_s;
     double s = 0.0;
-    for (long long i = threadIdx.x; i < n; i += kOptThreads) {
-        const double g = (double)(grad[i] * grad_scale * (mask ? mask[i] : 1.0f));
-        s += g * g;
+    // 8 loads in flight per thread: the CTA is alone on the device, so latency, not bandwidth, is what there is to hide
+    for (long long i0 = threadIdx.x; i0 < n; i0 += 8LL * kOptThreads) {
+        float g[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const long long i = i0 + (long long)e * kOptThreads;
+            g[e] = i < n ? grad[i] * grad_scale * (mask ? mask[i] : 1.0f) : 0.0f;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s += (double)g[e] * (double)g[e];
     }
     const double tot = block_sum(s, scratch);
     if (threadIdx.x == 0) {
@@ -40,12 +47,24 @@ clip_rmsprop_kernel(float* __restrict__ param, float* __restrict__ grad, float* 
                     long long n, float grad_scale, float max_norm, float lr, float alpha, float eps,
                     float* norm_out) {
     const float coef = grad_norm_and_coef(grad, n, grad_scale, max_norm, norm_out);
-    for (long long i = threadIdx.x; i < n; i += kOptThreads) {
-        const float g = grad[i] * grad_scale * coef;
-        grad[i] = g;                                        // .grad is left clipped, as in torch
-        const float v = sq[i] * alpha + (1.0f - alpha) * g * g;
-        sq[i] = v;
-        param[i] = param[i] - lr * (g / (sqrtf(v) + eps));
+    for (long long i0 = threadIdx.x; i0 < n; i0 += 4LL * kOptThreads) {
+        float g[4], q[4], w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const long long i = i0 + (long long)e * kOptThreads;
+            if (i < n) { g[e] = grad[i]; q[e] = sq[i]; w[e] = param[i]; }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const long long i = i0 + (long long)e * kOptThreads;
+            if (i < n) {
+                const float gg = g[e] * grad_scale * coef;
+                grad[i] = gg;                                   // .grad is left clipped, as in torch
+                const float v = q[e] * alpha + (1.0f - alpha) * gg * gg;
+                sq[i] = v;
+                param[i] = w[e] - lr * (gg / (sqrtf(v) + eps));
+            }
+        }
     }
 }
 
@@ -58,13 +77,25 @@ clip_adam_kernel(float* __restrict__ param, float* __restrict__ grad, float* __r
     const double bc2 = 1.0 - pow((double)beta2, (double)step);
     const float step_size = (float)((double)lr / bc1);
     const float rsq_bc2 = (float)(1.0 / sqrt(bc2));
-    for (long long i = threadIdx.x; i < n; i += kOptThreads) {
-        const float g = grad[i] * grad_scale * coef * (mask ? mask[i] : 1.0f);
-        grad[i] = g;
-        const float mi = m[i] * beta1 + (1.0f - beta1) * g;
-        const float vi = v[i] * beta2 + (1.0f - beta2) * g * g;
-        m[i] = mi; v[i] = vi;
-        param[i] = param[i] - step_size * (mi / (sqrtf(vi) * rsq_bc2 + eps));
+    for (long long i0 = threadIdx.x; i0 < n; i0 += 4LL * kOptThreads) {
+        float g[4], m0[4], v0[4], w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const long long i = i0 + (long long)e * kOptThreads;
+            if (i < n) { g[e] = grad[i] * (mask ? mask[i] : 1.0f); m0[e] = m[i]; v0[e] = v[i]; w[e] = param[i]; }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const long long i = i0 + (long long)e * kOptThreads;
+            if (i < n) {
+                const float gg = g[e] * grad_scale * coef;
+                grad[i] = gg;
+                const float mi = m0[e] * beta1 + (1.0f - beta1) * gg;
+                const float vi = v0[e] * beta2 + (1.0f - beta2) * gg * gg;
+                m[i] = mi; v[i] = vi;
+                param[i] = w[e] - step_size * (mi / (sqrtf(vi) * rsq_bc2 + eps));
+            }
+        }
     }
 }
 

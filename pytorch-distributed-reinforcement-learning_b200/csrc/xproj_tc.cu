@@ -154,7 +154,7 @@ lstm_xproj_tc_kernel(const float* __restrict__ u, const float* __restrict__ Wt, 
 #else
             const int addr_lane = rbase;
 #endif
-            const int wr = lane >> 4, wc = lane & 15;                                // store role: 2 rows x 16 columns per instruction
+            const int wr = lane >> 4, wc = lane & 15;                                // store role: 2 rows (16 apart) x 16 columns per instruction
             for (int c0 = c_base; c0 < c_base + 128; c0 += 32) {
                 float v[32];
                 tc::tmem_ld32(tc::tmem_addr(tmem, addr_lane, acc * G + c0), v);
@@ -167,9 +167,9 @@ lstm_xproj_tc_kernel(const float* __restrict__ u, const float* __restrict__ Wt, 
                     const int col = c0 + hseg * SC + wc;
                     const float bias = bsum[col];
 #pragma unroll 8
-                    for (int rr = 0; rr < 32; rr += 2) {
-                        const long long row = tile * TR + rbase + rr + wr;
-                        if (row < rows) xproj[(size_t)row * G + col] = P[(rr + wr) * SST + wc] + bias;
+                    for (int rr = 0; rr < 16; ++rr) {                       // rows rr and rr+16: 16 x 17 = 16 (mod 32) banks apart
+                        const long long row = tile * TR + rbase + rr + 16 * wr;
+                        if (row < rows) xproj[(size_t)row * G + col] = P[(rr + 16 * wr) * SST + wc] + bias;
                     }
                 }
             }
