@@ -65,7 +65,8 @@ class OnPolicyEngine:
         self.head_out = torch.empty(B, T, L.NH, device=dev)
         self.dhead = torch.empty(B, T, L.NH, device=dev)
         nchunks = (B * T + 31) // 32
-        self.nparts = max(1, min(_sm_count(dev, self.ops), nchunks))
+        # one partial-gradient slab per CTA of the weight-gradient stage; wgrad_tc runs two CTAs per SM
+        self.nparts = max(1, min(2 * _sm_count(dev, self.ops), nchunks))
         self.partials = torch.zeros(self.nparts, L.P, device=dev)   # pad slots stay zero
         self._shape = (B, T)
 

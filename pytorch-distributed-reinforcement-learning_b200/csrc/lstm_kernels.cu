@@ -1097,18 +1097,21 @@ extern "C" int b200rl_lstm_wgrad(const float* dpre, const float* h, const float*
     B200RL_REQUIRE(nparts >= 1, "lstm_wgrad: nparts=%d", nparts);
     B200RL_REQUIRE((off_Wih % 4) == 0 && (off_Whh % 4) == 0 && (P % 4) == 0, "lstm_wgrad: W_ih/W_hh offsets and P must be multiples of 4 floats");
     const size_t smem = wgrad_smem_bytes(Fin, NH);
+    // wgrad_tc runs two CTAs per SM and takes every slab; the other kernels of the stage fill an SM with one CTA and use the
+    // first sm_count slabs (their entries in the remaining slabs stay zero, as allocated)
+    const int np_misc = nparts < sm_count() ? nparts : sm_count();
     if (variant == 3) {
         // dx was already produced by lstm_bwd variant 1: tcgen05 dW + a bandwidth-bound torso pass over dx
         B200RL_REQUIRE(dx != nullptr && du == nullptr, "lstm_wgrad: variant 3 needs dx (from lstm_bwd variant 1) and does not produce du");
         B200RL_REQUIRE((long long)nparts * 32 <= (long long)B * T + 31, "lstm_wgrad: nparts=%d exceeds the number of 32-row stages", nparts);
         if (launch_wgrad_tc(dpre, h, hx0, u, Wt, bt, partials, nparts, P, off_Wih, off_Whh, off_bih, off_bhh, B, T, Fin, stream)) return 1;
-        return launch_torso_from_dx(dx, u, Wt, bt, h, dhead, partials, nparts, P, off_Wt, off_bt, off_Whead, off_bhead, B, T, Fin, NH, stream);
+        return launch_torso_from_dx(dx, u, Wt, bt, h, dhead, partials, np_misc, P, off_Wt, off_bt, off_Whead, off_bhead, B, T, Fin, NH, stream);
     }
     if (variant == 1) {
         // tensor-core path: dW_ih / dW_hh / db (wgrad_tc.cu) and dx -> torso grads (dx_tc.cu) on tcgen05
         B200RL_REQUIRE((long long)nparts * 32 <= (long long)B * T + 31, "lstm_wgrad: nparts=%d exceeds the number of 32-row stages", nparts);
         if (launch_wgrad_tc(dpre, h, hx0, u, Wt, bt, partials, nparts, P, off_Wih, off_Whh, off_bih, off_bhh, B, T, Fin, stream)) return 1;
-        return launch_dx_tc(dpre, u, W_ih, Wt, bt, h, dhead, partials, nparts, P, off_Wt, off_bt, off_Whead, off_bhead,
+        return launch_dx_tc(dpre, u, W_ih, Wt, bt, h, dhead, partials, np_misc, P, off_Wt, off_bt, off_Whead, off_bhead,
                             du, B, T, Fin, NH, stream);
     }
     if (variant == 2) {   // tcgen05 dW + FFMA remainder (kept for A/B measurements)

@@ -39,7 +39,7 @@ namespace b200rl {
 namespace wtc {
 constexpr int H = 64, G = 256, KC = 128, NP = 256, NT = NP + 32;   // producers + issuer warp
 constexpr int SR = 16;                          // rows per stage (2 MMA K-steps of 8)
-constexpr int NSTAGE = 4;
+constexpr int NSTAGE = 2;                         // two CTAs per SM (2 x 101 KB of stages, 2 x 256 TMEM columns): 4 producer warps per sub-partition
 constexpr int LBO = 128;                        // K direction: next core matrix (4 rows)
 constexpr int SBO = 528;                        // MN direction: next group of 8 mn (4 core matrices + 16 B skew) = 16 B mod 128 B
 constexpr int A_TILE = (KC / 8) * SBO;          // 8448
@@ -54,7 +54,7 @@ static inline size_t wgrad_tc_smem_bytes(int Fin) {
     return wtc::NSTAGE * (size_t)wtc::STAGE + sizeof(float) * (size_t)(Fin * wtc::H + wtc::H) + 96;
 }
 
-__global__ void __launch_bounds__(wtc::NT, 1)
+__global__ void __launch_bounds__(wtc::NT, 2)
 lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h, const float* __restrict__ hx0,
                      const float* __restrict__ u, const float* __restrict__ Wt, const float* __restrict__ bt,
                      float* __restrict__ partials, long long P,
@@ -91,11 +91,11 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
     const long long nstages = (rows + SR - 1) / SR;
     float4 dbacc = make_float4(0.f, 0.f, 0.f, 0.f);               // bias gradient of gate columns (warp*8 + cq)*4 .. +3
 
-    // Register-staged loads: a ring of 4 register sets; the HBM reads of stage i+3 are issued
-    // before stage i is split and scattered, so their latency overlaps three stages of work.
+    // Register-staged loads: two register sets; the HBM reads of the CTA's next stage are issued before the current one
+    // is split and scattered (the co-resident second CTA keeps another stage in flight on the same SM).
     constexpr int UP = 4;                           // torso inputs prefetched in registers when Fin <= UP
     struct StageRegs { float4 d[4]; float4 h; float u[UP]; bool ok; };
-    StageRegs ring[4];
+    StageRegs ring[2];
     auto issue_loads = [&](StageRegs& R, long long stg) {
         const long long row0 = stg * SR;
         const bool live = stg < nstages;
@@ -196,12 +196,10 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
     if (producer) {
         const long long g = gridDim.x;
         long long st = blockIdx.x;
-        issue_loads(ring[0], st); issue_loads(ring[1], st + g); issue_loads(ring[2], st + 2 * g);   // (ring depth 4 = NSTAGE)
+        issue_loads(ring[0], st);
         while (st < nstages) {
-            issue_loads(ring[3], st + 3 * g); process(ring[0], st); st += g; if (st >= nstages) break;
-            issue_loads(ring[0], st + 3 * g); process(ring[1], st); st += g; if (st >= nstages) break;
-            issue_loads(ring[1], st + 3 * g); process(ring[2], st); st += g; if (st >= nstages) break;
-            issue_loads(ring[2], st + 3 * g); process(ring[3], st); st += g;
+            issue_loads(ring[1], st + g); process(ring[0], st); st += g; if (st >= nstages) break;
+            issue_loads(ring[0], st + g); process(ring[1], st); st += g;
         }
     } else if (lane == 0) {
         // ---- MMA issuer: stage descriptors differ only in their start address (low 14 bits, 16-byte units)
