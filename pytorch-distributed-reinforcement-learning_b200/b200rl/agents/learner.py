@@ -237,7 +237,8 @@ class LearnerSeperate(LearnerBase):
         self.critic = self.model.critic
         self.target_critic = self.critic                      # aliasing, as in the reference (learner.py:358)
         cont = bool(getattr(self.actor, "continuous", False))
-        self.engine = SACEngine(self.model, hyper_from_args(self.args), cont, ops=self._ops, separate_target=separate_target)
+        self.engine = SACEngine(self.model, hyper_from_args(self.args), cont, ops=self._ops, separate_target=separate_target,
+                                process_group=self.process_group)
         self.target_entropy = self.args.action_space
         self.to_gpu.skip = {"logits", "log_prob"}
         self._latched = False

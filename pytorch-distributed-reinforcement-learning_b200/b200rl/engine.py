@@ -255,10 +255,15 @@ class SACEngine:
     SURVEY.md A.6-8), so the "target" forward is the critic forward and `soft_update` is
     theta <- (1-tau) theta + tau theta; `separate_target=True` keeps a real copy instead."""
 
-    def __init__(self, model, hyper, continuous, ops=None, separate_target=False, tau=0.005):
+    def __init__(self, model, hyper, continuous, ops=None, separate_target=False, tau=0.005, process_group=None):
         self.ops = ops or _ops.default()
         self.hp = dict(hyper)
         self.cont = continuous
+        # data parallel: the replay batch is sharded over ranks (equal shards); every loss is a mean over the batch, so the
+        # actor / twin-critic gradients and the temperature statistics are summed over ranks and scaled by 1/world
+        # (three small all-reduces per update: actor grad, the alpha statistics, critic grad)
+        self.pg = process_group
+        self.world = 1 if process_group is None else torch.distributed.get_world_size(process_group)
         self.actor, self.twin = model.actor, model.critic
         self.q = [self.twin.q1, self.twin.q2]
         self.fa = self.actor.flat_parameters()
@@ -352,8 +357,9 @@ class SACEngine:
             lib.call("b200rl_sac_actor_head", ptr(self.hoa), ptr(self.Q[0]), ptr(self.Q[1]), ptr(self.alpha_state),
                      ptr(self.dhoa), ptr(self.scalars), B, T, A, st)
             self._net_bwd(La, self.fa, 0, uo, hx, cx, self.wsa, self.dhoa, self.pa, self.ga)
-            ops.clip_adam(self.fa, self.ga, self.ma, self.va, La.P, 1.0, mg, lr, self.step, norm_out=self.norm_a)
-            lib.call("b200rl_sac_alpha_step", ptr(self.alpha_state), ptr(self.scalars), ptr(self.alpha_out), N, float(A), lr, self.step, st)
+            sc = self._reduce_actor()
+            ops.clip_adam(self.fa, self.ga, self.ma, self.va, La.P, 1.0 / self.world, mg, lr, self.step, norm_out=self.norm_a)
+            lib.call("b200rl_sac_alpha_step", ptr(self.alpha_state), ptr(sc), ptr(self.alpha_out), N * self.world, float(A), lr, self.step, st)
             self._net_fwd(La, self.fa, 0, uo, hx, cx, self.wsa, self.hoa)            # updated actor
             if self.separate_target:
                 for i in range(2):
@@ -378,8 +384,9 @@ class SACEngine:
             lib.call("b200rl_sac_cont_actor_grad", ptr(self.hoa), ptr(eps1), ptr(self.a_pol), ptr(self.logp), ptr(self.du[0]), ptr(self.du[1]),
                      ptr(self.alpha_state), ptr(self.dhoa), ptr(self.scalars), B, T, A, f, st)
             self._net_bwd(La, self.fa, 0, uo, hx, cx, self.wsa, self.dhoa, self.pa, self.ga)
-            ops.clip_adam(self.fa, self.ga, self.ma, self.va, La.P, 1.0, mg, lr, self.step, norm_out=self.norm_a)
-            lib.call("b200rl_sac_alpha_step", ptr(self.alpha_state), ptr(self.scalars), ptr(self.alpha_out), N * A, float(A), lr, self.step, st)
+            sc = self._reduce_actor()
+            ops.clip_adam(self.fa, self.ga, self.ma, self.va, La.P, 1.0 / self.world, mg, lr, self.step, norm_out=self.norm_a)
+            lib.call("b200rl_sac_alpha_step", ptr(self.alpha_state), ptr(sc), ptr(self.alpha_out), N * A * self.world, float(A), lr, self.step, st)
             self._net_fwd(La, self.fa, 0, uo, hx, cx, self.wsa, self.hoa)            # updated actor, fresh noise
             lib.call("b200rl_sac_cont_sample", ptr(self.hoa), ptr(eps2), ptr(self.a_pol), ptr(self.logp), B, T, A, st)
             u2 = torch.cat([uo, self.a_pol], -1)
@@ -394,13 +401,29 @@ class SACEngine:
             for i in range(2):
                 self._net_bwd(Lq, self.fq, i * Pq, u3, hx, cx, self.wsq[i], self.dQ[i], self.pq[i], self.gq[i * Pq:(i + 1) * Pq])
             pol_den = N * A
-        ops.clip_adam(self.fq, self.gq, self.mq, self.vq, 2 * Pq, 1.0, mg, lr, self.step, norm_out=self.norm_q, mask=self.qmask)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.gq, group=self.pg)
+        ops.clip_adam(self.fq, self.gq, self.mq, self.vq, 2 * Pq, 1.0 / self.world, mg, lr, self.step, norm_out=self.norm_q, mask=self.qmask)
         ops.soft_update_flat(self.fq, self.ftq, self.tau)
-        self._pol_den, self._N = pol_den, N
+        self._pol_den, self._N = pol_den * self.world, N * self.world
         self.n_launches += 1
 
+    def _reduce_actor(self):
+        """Sum the actor gradient and the running loss / temperature statistics over ranks; returns the statistics the
+        temperature step reads (a reduced copy: `self.scalars` keeps accumulating local sums for the critic loss)."""
+        if self.world == 1:
+            return self.scalars
+        torch.distributed.all_reduce(self.ga, group=self.pg)
+        sc = self.scalars.clone()
+        torch.distributed.all_reduce(sc, group=self.pg)
+        return sc
+
     def losses(self):
-        s = self.scalars.cpu().tolist()
+        sc = self.scalars
+        if self.world > 1:
+            sc = sc.clone()
+            torch.distributed.all_reduce(sc, group=self.pg)
+        s = sc.cpu().tolist()
         ao = self.alpha_out.cpu().tolist()
         pol, val = s[0] / self._pol_den, s[1] / self._N
         return {"policy-loss": pol, "value-loss": val, "loss_alpha": ao[0], "alpha": ao[1],

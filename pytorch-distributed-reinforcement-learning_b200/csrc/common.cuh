@@ -104,6 +104,19 @@ __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.
 #endif
 __device__ __forceinline__ float sigm(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float tanh_(float x) { return fmaf(2.0f, rcp_approx(1.0f + ex2_approx(-2.8853900817779268f * x)), -1.0f); }
+// Two activations on THREE MUFU instead of four: with a = e^-x, b = e^-y one reciprocal r = 1/((1+a)(1+b)) serves both,
+// sigm(x) = r (1+b), sigm(y) = r (1+a); with b = e^-2y instead, tanh(y) = r (1+a)(1-b).  Inputs are clamped at -30 (sigm(-30) = 9e-14, and the
+// product of the two exponentials stays far below FLT_MAX); the cell phase of the tcgen05 forward is MUFU-bound.
+__device__ __forceinline__ void sigm_sigm(float x, float y, float& sx, float& sy) {
+    const float a = ex2_approx(-1.4426950408889634f * fmaxf(x, -30.0f)), b = ex2_approx(-1.4426950408889634f * fmaxf(y, -30.0f));
+    const float pa = 1.0f + a, pb = 1.0f + b, r = rcp_approx(pa * pb);
+    sx = r * pb; sy = r * pa;
+}
+__device__ __forceinline__ void sigm_tanh(float x, float y, float& sx, float& ty) {
+    const float a = ex2_approx(-1.4426950408889634f * fmaxf(x, -30.0f)), b = ex2_approx(-2.8853900817779268f * fmaxf(y, -15.0f));
+    const float pa = 1.0f + a, pb = 1.0f + b, r = rcp_approx(pa * pb);
+    sx = r * pb; ty = (r * pa) * (1.0f - b);
+}
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 }  // namespace b200rl

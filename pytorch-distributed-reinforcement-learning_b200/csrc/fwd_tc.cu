@@ -198,8 +198,9 @@ lstm_fwdt_kernel(float* xg, const float* __restrict__ hx0, const float* __restri
                     const float pa = EXr[(2 * i) * 32 + lane], pb = EXr[(2 * i + 1) * 32 + lane];
                     const float4 x = xq[i];
                     if (t + 1 < T) xq[i] = ld4(xg + ((size_t)(rowof(i) + t + 1) * H + j) * 4);
-                    const float ig = sigm((fo ? pa : xa[i]) + x.x), fg = sigm((fo ? xa[CT + i] : pa) + x.y);
-                    const float gg = tanh_((fo ? pb : xb[i]) + x.z), og = sigm((fo ? xb[CT + i] : pb) + x.w);
+                    float ig, fg, gg, og;                                   // 8 MUFU per cell: (i, g) and (f, o) share a reciprocal each, tanh(c) takes two
+                    sigm_tanh((fo ? pa : xa[i]) + x.x, (fo ? pb : xb[i]) + x.z, ig, gg);
+                    sigm_sigm((fo ? xa[CT + i] : pa) + x.y, (fo ? xb[CT + i] : pb) + x.w, fg, og);
                     const float cn = fmaf(fg, cst[i], ig * gg);
                     const float hh = og * tanh_(cn);
                     cst[i] = cn;

@@ -1,5 +1,5 @@
 """Data-parallel learner: B sharded over ranks, one all-reduce of the flat gradient (PPO / IMPALA),
-all-gather of the advantage matrix + global top-k (V-MPO).  world_size=2 with gloo on CPU drives the
+all-gather of the advantage matrix + global top-k (V-MPO), actor / critic / temperature reductions (SAC).  world_size=2 with gloo on CPU drives the
 host logic through the test-only emulated kernels; the same check runs over NCCL when >= 2 GPUs exist."""
 import os
 import socket
@@ -99,3 +99,64 @@ def test_dp2_nccl_equals_full_batch(algo, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     _run(algo, "nccl", 64, 16, tmp_path)
+
+
+# ------------------------------------------------------------------------------------------------ SAC / SAC-Continuous
+def _sac_setup(cont, B, T):
+    from collections import OrderedDict
+    from b200rl.networks import models as M
+    from b200rl.synth import make_rollouts
+    f, A = (5, 2) if cont else (4, 3)
+    torch.manual_seed(3)
+    model = (M.MlpLSTMSeperateContinuous(f, A, T, 64, act_dim=A) if cont else M.MlpLSTMSeperate(f, A, T, 64))
+    pa = OrderedDict((k, v.clone()) for k, v in model.actor.state_dict().items())
+    pc = OrderedDict((k, v.clone()) for k, v in model.critic.state_dict().items())
+    batches = [make_rollouts(B, T, f, A, continuous=cont, batch_index=i, **({"act_dim": A} if cont else {})) for i in range(2)]
+    g = torch.Generator().manual_seed(11)
+    noise = [[torch.randn(B, T, A, generator=g), torch.randn(B, T, A, generator=g)] for _ in range(2)] if cont else [None, None]
+    return model, pa, pc, batches, noise
+
+
+def _sac_worker(rank, world, port, cont, B, T, out_path):
+    for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import oracle
+    from b200rl import native, ops as O
+    from b200rl.engine import SACEngine
+    lib = native.Lib(os.path.join(ROOT, "tests", "emul", "_build", "libb200rl_emul.so"), emulated=True)
+    ops = O.Ops(lib, allow_cpu=True)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    model, _, _, batches, noise = _sac_setup(cont, B, T)
+    eng = SACEngine(model, oracle.DEFAULT_HYPER, cont, ops=ops, process_group=dist.group.WORLD)
+    sh = B // world
+    cut = lambda t: t[rank * sh:(rank + 1) * sh].contiguous()
+    for b, nz in zip(batches, noise):
+        eng.update({k: cut(v) for k, v in b.items()}, noise=None if nz is None else [cut(e) for e in nz])
+    L = eng.losses()
+    if rank == 0:
+        np.savez(out_path, actor=torch.cat([v.reshape(-1) for v in model.actor.state_dict().values()]).numpy(),
+                 critic=torch.cat([v.reshape(-1) for v in model.critic.state_dict().values()]).numpy(),
+                 loss=L["loss"], log_alpha=L["log_alpha"])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cont", [False, True])
+def test_sac_dp2_gloo_equals_full_batch(cont, tmp_path):
+    """Two ranks on half the replay batch each == one learner on the whole batch (actor, twin critics, temperature)."""
+    import oracle
+    from conftest import _emul_ops
+    _emul_ops()
+    B, T = 8, 5
+    out = str(tmp_path / "dp_sac.npz")
+    mp.spawn(_sac_worker, args=(2, _free_port(), cont, B, T, out), nprocs=2, join=True)
+    got = np.load(out)
+    _, pa, pc, batches, noise = _sac_setup(cont, B, T)
+    orc = oracle.OracleLearner("SAC-Continuous" if cont else "SAC", {"actor": pa, "critic": pc})
+    for b, nz in zip(batches, noise):
+        r = orc.update(b, noise=nz) if cont else orc.update(b)
+    np.testing.assert_allclose(got["loss"], float(r["loss"]), rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(got["log_alpha"], float(r["log_alpha"]), rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(got["actor"], r["actor_params"].numpy(), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(got["critic"], r["critic_params"].numpy(), rtol=1e-4, atol=1e-6)
