@@ -12,7 +12,11 @@
 // so the torso gradient's GEMM (a separate 537 MB pass over dpre before) rides along for free.
 // 3xTF32: A_hi lives in tensor memory (256 columns); A_lo for k < 192 too (192 columns), the last 64 k
 // in shared memory (32 KB, SS-form MMAs); dpre (B operand, hi/lo, K-major) is rewritten every step by the
-// cell phase.  Two issuer warps split K (two accumulators, summed by the readers): 96 MMAs per step.
+// cell phase.  96 MMAs per step; one thread gets a small tcgen05.mma out only every ~60-120 cycles while issues from
+// different threads overlap (tools/tc_probe3.cu), so TWO issuer warps split K into halves with an accumulator each and
+// the readers sum the partials.  Measured alternatives (tools/bwd_prof.cu, same shape): 1 issuer 0.68 ms, 2 issuers
+// 0.43 ms, 3 issuers (A_lo: 160 columns in TMEM) 0.50 ms, 4 issuers (128 columns) 0.59 ms -- every extra accumulator
+// pushes 32 more K columns of A_lo out of tensor memory into SS-form MMAs that pull 4 KB each through shared memory.
 //
 // Cell phase: TMEM lanes are bound to the warp's quarter, so dh_rec (lanes 0-63) is only visible to warps
 // with id % 4 in {0, 1} -- and those share two of the four SM sub-partitions.  The work is therefore split:
@@ -42,14 +46,20 @@ __device__ unsigned long long g_bwdprof[24];
 #endif
 
 namespace btk {
-constexpr int H = 64, G = 256, TB = 32, NC = 512, NT = NC + 64;    // 8 critical + 8 helper warps, 2 MMA issuer warps
+#ifndef B200RL_BWD_NI
+#define B200RL_BWD_NI 2
+#endif
+#ifndef B200RL_BWD_KS
+#define B200RL_BWD_KS 192
+#endif
+constexpr int H = 64, G = 256, TB = 32, NC = 512, NI = B200RL_BWD_NI, NT = NC + 32 * NI;    // 8 critical + 8 helper warps, NI MMA issuer warps
 constexpr int B_LBO = 144, B_SBO = 9216;                            // B: 64 core matrices along K, 16-byte skew -> conflict-free 16-byte stores
 constexpr int B_BYTES = (TB / 8) * B_SBO;                           // 36864 per hi / lo
 static_assert(63 * B_LBO + 128 <= B_SBO, "core matrices of one 8-row group must fit below SBO");
-constexpr int KS = 192;                                             // A_lo: k < KS in tensor memory, k >= KS in shared memory
+constexpr int KS = B200RL_BWD_KS;                                   // A_lo: k < KS in tensor memory, k >= KS in shared memory
 constexpr int AL_LBO = 128, AL_SBO = ((G - KS) / 4) * 128;          // 2048
-constexpr int AL_BYTES = (128 / 8) * AL_SBO;                        // 32768
-constexpr int TM_D0 = 0, TM_D1 = 32, TM_AH = 64, TM_AL = TM_AH + G, TM_COLS = 512;
+constexpr int AL_BYTES = (128 / 8) * AL_SBO;                        // 65536
+constexpr int TM_D = 0, TM_AH = NI * TB, TM_AL = TM_AH + G, TM_COLS = 512;     // accumulator i at columns 32 i
 static_assert(TM_AL + KS <= TM_COLS, "tensor memory budget");
 constexpr int NCOEF = 7;                                            // dhW, P_o, Q, P_i, P_f, P_g, f
 constexpr int CELLS = TB * H;
@@ -82,7 +92,7 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
 
     for (int i = tid; i < NH * H; i += NT) WhS[i] = W_head[i];
     if (tid == 0) {
-        tc::mbar_init(b_full, NC / 32); tc::mbar_init(acc_done, 2);
+        tc::mbar_init(b_full, NC / 32); tc::mbar_init(acc_done, NI);
         tc::fence_mbar_init();
     }
     if (warp == NC / 32) tc::tmem_alloc(tmem_slot, TM_COLS);
@@ -129,8 +139,8 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
 
     if (!cellw) {
         if (lane == 0) {
-            const int ii = warp - NC / 32;                           // K half: k-steps [16 ii, 16 ii + 16) into accumulator ii
-            const uint32_t D = tmem + (ii ? TM_D1 : TM_D0);
+            const int ii = warp - NC / 32;                           // K-steps [ii 32/NI, (ii+1) 32/NI) into accumulator ii
+            const uint32_t D = tmem + TM_D + ii * TB;
             uint32_t n = 0;
             BWP_INIT
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -140,11 +150,11 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                     tc::fence_after_sync();
                     BWP(17, NC);
 #pragma unroll
-                    for (int s0 = 0; s0 < 16; ++s0) {
-                        const int s = ii * 16 + s0, p0 = s * 8;
+                    for (int s = ii * (G / 8 / NI); s < (ii + 1) * (G / 8 / NI); ++s) {     // a contiguous K range per issuer
+                        const int p0 = s * 8;
                         const tc::SmemDesc bh = tc::make_desc(B_hi + s * 2 * B_LBO, B_LBO, B_SBO);
                         const tc::SmemDesc bl = tc::make_desc(B_lo + s * 2 * B_LBO, B_LBO, B_SBO);
-                        tc::mma_tf32_ts(D, tmem + TM_AH + p0, bh, idesc, s0 > 0 ? 1u : 0u);
+                        tc::mma_tf32_ts(D, tmem + TM_AH + p0, bh, idesc, s > ii * (G / 8 / NI) ? 1u : 0u);
                         tc::mma_tf32_ts(D, tmem + TM_AH + p0, bl, idesc, 1u);
                         if (p0 < KS) tc::mma_tf32_ts(D, tmem + TM_AL + p0, bh, idesc, 1u);
                         else tc::mma_tf32(D, tc::make_desc(ALs + ((p0 - KS) >> 2) * AL_LBO, AL_LBO, AL_SBO), bh, idesc, 1u);
@@ -160,6 +170,16 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
         const int pair = (q & 1) * 4 + cg;
         float* CO = COEF + pair * 256 + lane;                        // + (k*8)*256 + i*32
         float* DX = DHX + pair * 128 + lane;                         // + i*32
+        auto read_acc = [&](float (&d)[8]) {                         // my lane's 8 sequences: the NI partial accumulators summed
+            tc::tmem_ld8(tc::tmem_addr(tmem, my_lane, TM_D + cg * 8), d);
+#pragma unroll
+            for (int a = 1; a < NI; ++a) {
+                float e[8];
+                tc::tmem_ld8(tc::tmem_addr(tmem, my_lane, TM_D + a * TB + cg * 8), e);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) d[i] += e[i];
+            }
+        };
         uint32_t nb = 0;                                             // accumulator batches waited for so far
         BWP_INIT
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -258,11 +278,7 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                         tc::mbar_wait(acc_done, nb & 1); ++nb;
                         tc::fence_after_sync();
                         BWP(9, 64);
-                        float d0[8], d1[8];
-                        tc::tmem_ld8(tc::tmem_addr(tmem, my_lane, TM_D0 + cg * 8), d0);
-                        tc::tmem_ld8(tc::tmem_addr(tmem, my_lane, TM_D1 + cg * 8), d1);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) dxs[i] = d0[i] + d1[i];
+                        read_acc(dxs);
                         tc::fence_before_sync();
                     }
                     tc::named_bar_sync(1 + pair, 64);                // the critical thread has published dh_rec of my cells
@@ -286,12 +302,11 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                 tc::mbar_wait(acc_done, nb & 1); ++nb;               // dx_0
                 tc::fence_after_sync();
                 {
-                    float d0[8], d1[8];
-                    tc::tmem_ld8(tc::tmem_addr(tmem, my_lane, TM_D0 + cg * 8), d0);
-                    tc::tmem_ld8(tc::tmem_addr(tmem, my_lane, TM_D1 + cg * 8), d1);
+                    float d[8];
+                    read_acc(d);
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
-                        if (b0 + i < B) dx[(size_t)rowof(i) * H + j] = d0[i] + d1[i];
+                        if (b0 + i < B) dx[(size_t)rowof(i) * H + j] = d[i];
                     tc::fence_before_sync();
                 }
             } else {
@@ -305,12 +320,8 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                         tc::mbar_wait(acc_done, nb & 1); ++nb;
                         tc::fence_after_sync();
                         BWP(1, 0);
-                        float d0[8], d1[8];
-                        tc::tmem_ld8(tc::tmem_addr(tmem, my_lane, TM_D0 + cg * 8), d0);
-                        tc::tmem_ld8(tc::tmem_addr(tmem, my_lane, TM_D1 + cg * 8), d1);
+                        read_acc(dhr);
                         tc::fence_before_sync();
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) dhr[i] = d0[i] + d1[i];
                     } else {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) dhr[i] = 0.f;

@@ -25,8 +25,9 @@
 // activations, next B operand.  Global accesses are 128-byte (c, h) or 512-byte (xproj in, gates out)
 // contiguous per warp and row, each byte touched by exactly one thread.
 //
-// Two issuer warps, one per M tile: a single thread needs ~49 cycles per tcgen05.mma (tools/fwd_prof.cu)
-// while the tensor pipe needs ~16 for M128 x N32 x K8, so the 48 MMAs of a step are issue-bound.
+// Four issuer warps, (M tile) x (even / odd K-steps), each with its own accumulator: one thread gets a small
+// tcgen05.mma out only every ~50-120 cycles, issues from different threads overlap (tools/tc_probe3.cu), and the
+// tensor pipe needs ~16 cycles for M128 x N32 x K8 -- the 48 MMAs of a step are issue-bound.
 //
 // xg: on entry xproj (B, T, 64, 4), on exit the saved activations, same layout, in place: the thread
 // that owns cell (row, unit) reads its 16 bytes one step ahead and overwrites them itself.
@@ -50,8 +51,9 @@ namespace ftk {
 constexpr int H = 64, G = 256, TB = 32;
 constexpr int NG = 4;                                      // sequence groups: 4 cell warps (one per TMEM lane quarter) each
 constexpr int RW = TB / NG, CT = RW / 2;                   // sequences a warp reads / cells a thread owns
-constexpr int NC = NG * 128, NT = NC + 64;                 // cell warps + 2 MMA issuer warps
-constexpr int TM_D = 0, TM_A = 64, TM_COLS = 512;          // TMEM columns: D tiles X|Y at 0..63 ; A at 64 + (mt*2 + lo)*64 + k
+constexpr int NI = 4;                                      // MMA issuer warps: (M tile) x (even / odd K-steps), one accumulator each
+constexpr int NC = NG * 128, NT = NC + 32 * NI;
+constexpr int TM_D = 0, TM_A = NI * TB, TM_COLS = 512;     // TMEM columns: accumulator (mt, khalf) at 32 (2 mt + khalf) ; A at TM_A + (mt*2 + lo)*64 + k
 constexpr int B_LBO = 144, B_SBO = 2304;                   // B: 16 core matrices along K, 16-byte skew -> conflict-free 4-byte scatter
 constexpr int B_BYTES = (TB / 8) * B_SBO;                  // 9216 per hi / lo
 constexpr int EXF = 2 * NG * 2 * RW * 32;                  // swap buffer: [pair][direction][slot][lane] floats
@@ -77,7 +79,7 @@ lstm_fwdt_kernel(float* xg, const float* __restrict__ hx0, const float* __restri
     const bool compute = warp < NC / 32;
 
     if (tid == 0) {
-        tc::mbar_init(b_full, NC / 32); tc::mbar_init(acc_done, 2);
+        tc::mbar_init(b_full, NC / 32); tc::mbar_init(acc_done, NI);
         tc::fence_mbar_init();
     }
     if (warp == NC / 32) tc::tmem_alloc(tmem_slot, TM_COLS);
@@ -115,8 +117,8 @@ lstm_fwdt_kernel(float* xg, const float* __restrict__ hx0, const float* __restri
 
     if (!compute) {
         if (lane == 0) {
-            const int mt = warp - NC / 32;                        // this issuer's M tile: 0 = gates (i, f), 1 = (g, o)
-            const uint32_t Ah = tmem + TM_A + (mt * 2 + 0) * H, Al = tmem + TM_A + (mt * 2 + 1) * H, D = tmem + TM_D + mt * TB;
+            const int ii = warp - NC / 32, mt = ii >> 1, kh = ii & 1;   // this issuer's M tile (0 = gates (i, f), 1 = (g, o)) and K-step parity
+            const uint32_t Ah = tmem + TM_A + (mt * 2 + 0) * H, Al = tmem + TM_A + (mt * 2 + 1) * H, D = tmem + TM_D + ii * TB;
             uint32_t n = 0;
             FWP_INIT
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -126,10 +128,10 @@ lstm_fwdt_kernel(float* xg, const float* __restrict__ hx0, const float* __restri
                     tc::fence_after_sync();
                     FWP(9, NC);
 #pragma unroll
-                    for (int s = 0; s < H / 8; ++s) {
+                    for (int s = kh; s < H / 8; s += 2) {
                         const tc::SmemDesc bh = tc::make_desc(B_hi + s * 2 * B_LBO, B_LBO, B_SBO);
                         const tc::SmemDesc bl = tc::make_desc(B_lo + s * 2 * B_LBO, B_LBO, B_SBO);
-                        tc::mma_tf32_ts(D, Ah + s * 8, bh, idesc, s > 0 ? 1u : 0u);
+                        tc::mma_tf32_ts(D, Ah + s * 8, bh, idesc, s > 1 ? 1u : 0u);
                         tc::mma_tf32_ts(D, Ah + s * 8, bl, idesc, 1u);
                         tc::mma_tf32_ts(D, Al + s * 8, bh, idesc, 1u);
                     }
@@ -185,8 +187,17 @@ lstm_fwdt_kernel(float* xg, const float* __restrict__ hx0, const float* __restri
                 tc::fence_after_sync();
                 FWP(1, 0);
                 float xa[RW], xb[RW];
-                tc::tmem_ld8(tc::tmem_addr(tmem, addr_lane, TM_D + rbase), xa);        // gate i (or f) of unit j, RW sequences
-                tc::tmem_ld8(tc::tmem_addr(tmem, addr_lane, TM_D + TB + rbase), xb);   // gate g (or o)
+                {                                                       // gate i (or f) / g (or o) of unit j, RW sequences: even + odd K-step partials
+                    float e[RW];
+                    tc::tmem_ld8(tc::tmem_addr(tmem, addr_lane, TM_D + 0 * TB + rbase), xa);
+                    tc::tmem_ld8(tc::tmem_addr(tmem, addr_lane, TM_D + 1 * TB + rbase), e);
+#pragma unroll
+                    for (int r = 0; r < RW; ++r) xa[r] += e[r];
+                    tc::tmem_ld8(tc::tmem_addr(tmem, addr_lane, TM_D + 2 * TB + rbase), xb);
+                    tc::tmem_ld8(tc::tmem_addr(tmem, addr_lane, TM_D + 3 * TB + rbase), e);
+#pragma unroll
+                    for (int r = 0; r < RW; ++r) xb[r] += e[r];
+                }
                 FWP(2, 0);
 #pragma unroll
                 for (int i = 0; i < CT; ++i) { EXs[(2 * i) * 32 + lane] = fo ? xa[i] : xa[CT + i]; EXs[(2 * i + 1) * 32 + lane] = fo ? xb[i] : xb[CT + i]; }

@@ -21,14 +21,21 @@ int main() {
     for (int it = 0; it < 2; ++it) launch_bwd_tc(dhead, Whead, Whh, Wih, gates, c, cx0, dx, B, T, NH, 148, 0);
     cudaDeviceSynchronize();
     unsigned long long z[24] = {0};
+#ifdef B200RL_BWDPROF
     cudaMemcpyToSymbol(g_bwdprof, z, sizeof(z));
+#endif
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
     launch_bwd_tc(dhead, Whead, Whh, Wih, gates, c, cx0, dx, B, T, NH, 148, 0);
     cudaEventRecord(e1);
     cudaDeviceSynchronize();
     float ms; cudaEventElapsedTime(&ms, e0, e1);
+#ifdef B200RL_BWDPROF
     cudaMemcpyFromSymbol(z, g_bwdprof, sizeof(z));
+#else
+    printf("bwd_tc (no probes, NI=%d KS=%d) %.3f ms\n", btk::NI, btk::KS, ms);
+    return 0;
+#endif
     const double steps = (B / 32.0) * T;
     printf("bwd_tc %.3f ms; cycles/step critical thread: loop top %.0f | wait acc_done %.0f | tmem ld %.0f | wait coefs %.0f | read coefs + bar %.0f | 8 cells %.0f | fence+arrive %.0f\n",
            ms, z[0] / steps, z[1] / steps, z[2] / steps, z[3] / steps, z[4] / steps, z[5] / steps, z[6] / steps);
