@@ -130,7 +130,7 @@ def reference_arm(steps, warmup, rank, world):
     from oracle import models as OM
     from b200rl.synth import make_rollouts
     torch.set_num_threads(usable_cpus())
-    budget_steps = 4.0e7                                    # ~2 min at the ~3e5 env-steps/s a 16-thread host sustains
+    budget_steps = 2.5e7                                    # 2-3 min at the ~1.2e5 env-steps/s the 16-thread GPU-box host sustains
     rows = int(max(64, min(B, budget_steps / max(1, steps + warmup) / T)))
     rows = 1 << (rows.bit_length() - 1)
     torch.manual_seed(0)

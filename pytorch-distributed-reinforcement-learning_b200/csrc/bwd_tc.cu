@@ -188,7 +188,7 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
             auto rowof = [&](int i) { return (unsigned)seq(i) * (unsigned)T; };   // B*T < 2^31 (checked by the launcher)
             // the dh-dependent tail of the cell backward for cells i0 .. i0+3 of (unit j, this sequence group): 7 flops per
             // cell from the prepared coefficients, dpre to global memory and to the B operand (hi / lo)
-            auto cell_phase = [&](int t, int i0, const float (&dh4)[4], float (&dc)[4]) {
+            auto cell_phase = [&](int t, int i0, const float (&dh4)[4], float (&dc)[4], float4 (&dps)[4]) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int ii = i0 + i;
@@ -199,7 +199,7 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                     const float dct = fmaf(dh, cf[2], dc[i]);
                     const float4 dp = make_float4(dct * cf[3], dct * cf[4], dct * cf[5], dh * cf[1]);
                     dc[i] = dct * cf[6];
-                    if (b0 + ii < B) st4(gates + ((size_t)(rowof(ii) + t) * H + j) * 4, dp);
+                    dps[i] = dp;
                     float4 hi, lo;
                     tc::split_tf32(dp.x, hi.x, lo.x); tc::split_tf32(dp.y, hi.y, lo.y);
                     tc::split_tf32(dp.z, hi.z, lo.z); tc::split_tf32(dp.w, hi.w, lo.w);
@@ -208,6 +208,11 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                     *reinterpret_cast<float4*>(B_hi + ob) = hi;
                     *reinterpret_cast<float4*>(B_lo + ob) = lo;
                 }
+            };
+            auto store_dpre = [&](int t, int i0, const float4 (&dps)[4]) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (b0 + i0 + i < B) st4(gates + ((size_t)(rowof(i0 + i) + t) * H + j) * 4, dps[i]);
             };
             if (helper) {
                 float4 gcur[8]; float ccur[8], cprev[8];
@@ -286,9 +291,11 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                     float dh4[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) dh4[i] = DX[i * 32];
-                    cell_phase(t, 4, dh4, dc);
+                    float4 dps[4];
+                    cell_phase(t, 4, dh4, dc, dps);
                     tc::fence_async_smem();
                     tc::mbar_arrive_warp(b_full);
+                    store_dpre(t, 4, dps);                           // (HBM stores overlap the tensor core's step)
                     tc::named_bar_sync(1 + pair, 64);                // both threads have read their coefficients: the slots are free for step t-1
                     BWP(11, 64);
                     if (t < T - 1) {
@@ -332,10 +339,12 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                     tc::named_bar_sync(1 + pair, 64);
                     BWP(3, 0);
                     const float dh4[4] = {dhr[0], dhr[1], dhr[2], dhr[3]};
-                    cell_phase(t, 0, dh4, dc);
+                    float4 dps[4];
+                    cell_phase(t, 0, dh4, dc, dps);
                     BWP(5, 0);
                     tc::fence_async_smem();
                     tc::mbar_arrive_warp(b_full);
+                    store_dpre(t, 0, dps);
                     tc::named_bar_sync(1 + pair, 64);
                     BWP(6, 0);
                 }

@@ -204,6 +204,7 @@ lstm_fwdt_kernel(float* xg, const float* __restrict__ hx0, const float* __restri
                 FWP(3, 0);
                 tc::named_bar_sync(1 + pair, 64);
                 FWP(4, 0);
+                float4 gsv[CT]; float hsv[CT];                          // saved activations: stored to HBM AFTER the step is handed to the issuers
 #pragma unroll
                 for (int i = 0; i < CT; ++i) {
                     const float pa = EXr[(2 * i) * 32 + lane], pb = EXr[(2 * i + 1) * 32 + lane];
@@ -215,11 +216,7 @@ lstm_fwdt_kernel(float* xg, const float* __restrict__ hx0, const float* __restri
                     const float cn = fmaf(fg, cst[i], ig * gg);
                     const float hh = og * tanh_(cn);
                     cst[i] = cn;
-                    if (b0 + rbase + mine + i < B) {
-                        const size_t o = (size_t)(rowof(i) + t) * H + j;
-                        st4(xg + o * 4, make_float4(ig, fg, gg, og));
-                        c_out[o] = cn; h_out[o] = hh;
-                    }
+                    gsv[i] = make_float4(ig, fg, gg, og); hsv[i] = hh;
                     float hi, lo;
                     tc::split_tf32(hh, hi, lo);
                     const int ob = boff(rbase + mine + i);
@@ -233,6 +230,14 @@ lstm_fwdt_kernel(float* xg, const float* __restrict__ hx0, const float* __restri
                     tc::mbar_arrive_warp(b_full);
                 }
                 FWP(6, 0);
+#pragma unroll
+                for (int i = 0; i < CT; ++i) {                          // (these stores overlap the tensor core's next step)
+                    if (b0 + rbase + mine + i < B) {
+                        const size_t o = (size_t)(rowof(i) + t) * H + j;
+                        st4(xg + o * 4, gsv[i]);
+                        c_out[o] = cst[i]; h_out[o] = hsv[i];
+                    }
+                }
             }
         }
     }
