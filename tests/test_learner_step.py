@@ -254,3 +254,40 @@ def test_sac_continuous_generalised_action_width(backend):
             _close(L[k], float(r[k]), rtol=1e-4, atol=1e-7, what=f"{k}[{i}]")
         _close(torch.cat([v.reshape(-1) for v in model.actor.state_dict().values()]).cpu(), r["actor_params"], what="actor params", **PARAMS)
         _close(torch.cat([v.reshape(-1) for v in model.critic.state_dict().values()]).cpu(), r["critic_params"], what="critic params", **PARAMS)
+
+
+@pytest.mark.gpu
+def test_full_size_tcgen05_path_agrees_with_ffma_path(monkeypatch):
+    """BASELINE shape (B=4096, T=128, obs 4, A=2), where the oracle is too slow: the tcgen05 kernels (forward 3, backward 1
+    + torso pass) and the independently written FFMA kernels (forward 0, backward 0, FFMA weight gradients) must produce the
+    same loss scalars and the same flat gradient from the same weights and batch; and the update must not depend on the
+    order of the sequences (sums over B are the only coupling)."""
+    from b200rl import ops as O
+    from b200rl.engine import OnPolicyEngine
+    from b200rl.networks import models as M
+    from b200rl.synth import make_rollouts
+    dev = torch.device("cuda:0")
+    B, T = 4096, 128
+    batch = {k: v.to(dev) for k, v in make_rollouts(B, T, 4, 2).items()}
+
+    def run(fwd, bwd, wg, perm=None):
+        monkeypatch.setattr(O, "FWD_VARIANT", fwd)
+        monkeypatch.setattr(O, "BWD_VARIANT", bwd)
+        monkeypatch.setenv("B200RL_WGRAD_VARIANT", str(wg))
+        torch.manual_seed(0)
+        model = M.MlpLSTMSingle(4, 2, T, 64).to(dev)
+        eng = OnPolicyEngine(model.actor, "PPO", oracle.DEFAULT_HYPER)
+        b = batch if perm is None else {k: v[perm].contiguous() for k, v in batch.items()}
+        eng.update(b)
+        L = eng.losses()
+        return L, eng.grad.clone()
+
+    L_tc, g_tc = run(3, 1, 1)
+    L_ff, g_ff = run(0, 0, 0)
+    for k in ("policy-loss", "value-loss", "policy-entropy", "loss", "ratio-avg"):
+        _close(L_tc[k], L_ff[k], rtol=1e-4, atol=1e-7, what=k)
+    _close(g_tc.cpu(), g_ff.cpu(), rtol=1e-3, atol=2e-5 * float(g_ff.abs().max()), what="flat gradient, tcgen05 vs FFMA")
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(1)).to(dev)
+    L_p, g_p = run(3, 1, 1, perm)
+    _close(L_p["loss"], L_tc["loss"], rtol=1e-5, atol=1e-8, what="loss under a permutation of the sequences")
+    _close(g_p.cpu(), g_tc.cpu(), rtol=1e-3, atol=2e-5 * float(g_tc.abs().max()), what="gradient under a permutation of the sequences")
