@@ -117,8 +117,13 @@ __device__ __forceinline__ void sigm_tanh(float x, float y, float& sx, float& ty
     const float pa = 1.0f + a, pb = 1.0f + b, r = rcp_approx(pa * pb);
     sx = r * pb; ty = (r * pa) * (1.0f - b);
 }
-__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+#ifdef B200RL_EMUL      // the host emulator tolerates unaligned 16-byte accesses, the GPU traps on them: check here
+#define B200RL_ALIGN16(p) do { if (reinterpret_cast<uintptr_t>(p) & 15) { fprintf(stderr, "emul: misaligned 16-byte access %s:%d\n", __FILE__, __LINE__); abort(); } } while (0)
+#else
+#define B200RL_ALIGN16(p) do { } while (0)
+#endif
+__device__ __forceinline__ float4 ld4(const float* p) { B200RL_ALIGN16(p); return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { B200RL_ALIGN16(p); *reinterpret_cast<float4*>(p) = v; }
 }  // namespace b200rl
 
 namespace b200rl {

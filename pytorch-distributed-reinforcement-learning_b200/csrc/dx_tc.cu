@@ -277,18 +277,23 @@ lstm_dx_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ u,
 // --------------------------------------------------------------------------- head gradients
 // Bandwidth-bound over h (256 B per row): 1024 threads = 4 row groups x 256 so that each SM has
 // 32 warps of loads in flight; the groups are combined through shared memory at the end.
-constexpr int HG_R = 64, HG_G = 4;
+// TILED (NH <= 4, the actor-critic heads): a thread owns (head c, 4 consecutive k, 16 of the chunk's 64 rows) and does 4 FMA
+// per scalar + 16-byte shared-memory load; one FMA per two scalar loads made the reduction LDS-bound (ncu r1h: mio_throttle 3.2).
+constexpr int HG_R = 64, HG_G = 4, HG_S = 68;       // rows per chunk, row groups, smem row stride (16-byte aligned rows)
+template <bool TILED>
 __global__ void __launch_bounds__(256 * HG_G)
 head_grad_kernel(const float* __restrict__ h, const float* __restrict__ dhead, float* __restrict__ partials,
                  long long P, long long off_Whead, long long off_bhead, long long rows, int NH) {
     B200RL_DYN_SMEM(float, smem);
     const int grp = threadIdx.x >> 8, tid = threadIdx.x & 255;
-    float* S = smem + grp * (HG_R * 65 + HG_R * B200RL_MAX_HEADS);
-    float* Dh = S + HG_R * 65;
-    constexpr int E = (B200RL_MAX_HEADS * 64 + 255) / 256;
+    float* S = smem + grp * (HG_R * HG_S + HG_R * B200RL_MAX_HEADS);
+    float* Dh = S + HG_R * HG_S;
+    constexpr int E = TILED ? 1 : (B200RL_MAX_HEADS * 64 + 255) / 256;
     float acc[E], accb = 0.f;
+    float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int e = 0; e < E; ++e) acc[e] = 0.f;
+    const int items = NH * 16, slice = tid / items, item = tid - slice * items, tc_ = item >> 4, tk4 = item & 15;   // TILED roles
     const long long nch = (rows + HG_R - 1) / HG_R;
     const long long nloop = (nch + (long long)gridDim.x * HG_G - 1) / ((long long)gridDim.x * HG_G);
     // software pipeline: the HBM loads of chunk it+1 are in flight (registers) while chunk it is reduced from shared
@@ -315,8 +320,7 @@ head_grad_kernel(const float* __restrict__ h, const float* __restrict__ dhead, f
 #pragma unroll
         for (int e = 0; e < HV; ++e) {
             const int i = e * 256 + tid, r = i >> 4, c4 = i & 15;
-            float* d = S + r * 65 + c4 * 4;
-            d[0] = hv[e].x; d[1] = hv[e].y; d[2] = hv[e].z; d[3] = hv[e].w;
+            st4(S + r * HG_S + c4 * 4, hv[e]);
         }
 #pragma unroll
         for (int e = 0; e < DV; ++e) {
@@ -325,15 +329,26 @@ head_grad_kernel(const float* __restrict__ h, const float* __restrict__ dhead, f
         }
         __syncthreads();
         fetch(it + 1);
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const int o = e * 256 + tid;
-            if (o < NH * 64) {
-                const int c = o >> 6, k = o & 63;
-                float s = 0.f;
+        if (TILED) {
+            if (slice < 4) {
 #pragma unroll 8
-                for (int r = 0; r < HG_R; ++r) s = fmaf(Dh[r * NH + c], S[r * 65 + k], s);
-                acc[e] += s;
+                for (int r = slice * 16; r < slice * 16 + 16; ++r) {
+                    const float d = Dh[r * NH + tc_];
+                    const float4 v = ld4(S + r * HG_S + tk4 * 4);
+                    acc4.x = fmaf(d, v.x, acc4.x); acc4.y = fmaf(d, v.y, acc4.y); acc4.z = fmaf(d, v.z, acc4.z); acc4.w = fmaf(d, v.w, acc4.w);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int o = e * 256 + tid;
+                if (o < NH * 64) {
+                    const int c = o >> 6, k = o & 63;
+                    float s = 0.f;
+#pragma unroll 8
+                    for (int r = 0; r < HG_R; ++r) s = fmaf(Dh[r * NH + c], S[r * HG_S + k], s);
+                    acc[e] += s;
+                }
             }
         }
         if (tid < NH) {
@@ -342,24 +357,35 @@ head_grad_kernel(const float* __restrict__ h, const float* __restrict__ dhead, f
             accb += s;
         }
     }
-    // combine the row groups: red[grp][NH*64 + NH]
+    // combine the row groups (and row slices): red[part][NH*64 + NH]
     __syncthreads();
     float* red = smem;
-    const int RW = NH * 64 + NH;
+    const int RW = NH * 64 + NH, RS = (RW + 3) & ~3;        // row stride of `red`: 16-byte aligned for the float4 stores
+    const int nparts_red = TILED ? HG_G * 4 : HG_G;
+    if (TILED) {
+        for (int i = threadIdx.x; i < nparts_red * RS; i += 256 * HG_G) red[i] = 0.f;     // (bias slots are written by one slice only)
+        __syncthreads();
+        if (slice < 4) st4(red + (grp * 4 + slice) * RS + tc_ * 64 + tk4 * 4, acc4);
+        if (tid < NH) red[(grp * 4) * RS + NH * 64 + tid] = accb;
+    } else {
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-        const int o = e * 256 + tid;
-        if (o < NH * 64) red[grp * RW + o] = acc[e];
+        for (int e = 0; e < E; ++e) {
+            const int o = e * 256 + tid;
+            if (o < NH * 64) red[grp * RS + o] = acc[e];
+        }
+        if (tid < NH) red[grp * RS + NH * 64 + tid] = accb;
     }
-    if (tid < NH) red[grp * RW + NH * 64 + tid] = accb;
     __syncthreads();
     float* out = partials + (size_t)blockIdx.x * P;
     for (int i = threadIdx.x; i < RW; i += 256 * HG_G) {
         float s = 0.f;
-        for (int gg = 0; gg < HG_G; ++gg) s += red[gg * RW + i];
+        for (int gg = 0; gg < nparts_red; ++gg) s += red[gg * RS + i];
         if (i < NH * 64) out[off_Whead + i] = s; else out[off_bhead + (i - NH * 64)] = s;
     }
 }
+
+static int launch_head_grad(const float* h, const float* dhead, float* partials, int nparts, long long P,
+                            long long off_Whead, long long off_bhead, long long rows, int NH, void* stream);
 
 // --------------------------------------------------------------------------- torso gradients from a stored dx
 // When the backward kernel already produced dx = dpre . W_ih (bwd_tc.cu fuses that GEMM into the recurrent one),
@@ -432,6 +458,19 @@ static int dx_set_smem(K kern, size_t smem) {
     return 0;
 }
 
+static int launch_head_grad(const float* h, const float* dhead, float* partials, int nparts, long long P,
+                            long long off_Whead, long long off_bhead, long long rows, int NH, void* stream) {
+    const size_t hsm = sizeof(float) * HG_G * (HG_R * HG_S + HG_R * B200RL_MAX_HEADS);
+    if (NH <= 4) {
+        if (dx_set_smem(head_grad_kernel<true>, hsm)) return 1;
+        B200RL_LAUNCH(head_grad_kernel<true>, nparts, 256 * HG_G, hsm, stream, h, dhead, partials, P, off_Whead, off_bhead, rows, NH);
+    } else {
+        if (dx_set_smem(head_grad_kernel<false>, hsm)) return 1;
+        B200RL_LAUNCH(head_grad_kernel<false>, nparts, 256 * HG_G, hsm, stream, h, dhead, partials, P, off_Whead, off_bhead, rows, NH);
+    }
+    return check_launch("lstm_wgrad(head grad)");
+}
+
 int launch_dx_tc(const float* dpre, const float* u, const float* W_ih, const float* Wt, const float* bt,
                  const float* h, const float* dhead, float* partials, int nparts, long long P,
                  long long off_Wt, long long off_bt, long long off_Whead, long long off_bhead,
@@ -450,10 +489,7 @@ int launch_dx_tc(const float* dpre, const float* u, const float* W_ih, const flo
     else B200RL_DX_LAUNCH(32);
 #undef B200RL_DX_LAUNCH
     if (check_launch("lstm_wgrad(dx tc)")) return 1;
-    const size_t hsm = sizeof(float) * HG_G * (HG_R * 65 + HG_R * B200RL_MAX_HEADS);
-    if (dx_set_smem(head_grad_kernel, hsm)) return 1;
-    B200RL_LAUNCH(head_grad_kernel, nparts, 256 * HG_G, hsm, stream, h, dhead, partials, P, off_Whead, off_bhead, rows, NH);
-    return check_launch("lstm_wgrad(head grad)");
+    return launch_head_grad(h, dhead, partials, nparts, P, off_Whead, off_bhead, rows, NH, stream);
 }
 
 int launch_torso_from_dx(const float* dx, const float* u, const float* Wt, const float* bt,
@@ -474,10 +510,7 @@ int launch_torso_from_dx(const float* dx, const float* u, const float* Wt, const
         B200RL_LAUNCH(kern, nparts, 512, tsm, stream, dx, u, Wt, bt, partials, P, off_Wt, off_bt, rows, Fin);
     }
     if (check_launch("lstm_wgrad(torso from dx)")) return 1;
-    const size_t hsm = sizeof(float) * HG_G * (HG_R * 65 + HG_R * B200RL_MAX_HEADS);
-    if (dx_set_smem(head_grad_kernel, hsm)) return 1;
-    B200RL_LAUNCH(head_grad_kernel, nparts, 256 * HG_G, hsm, stream, h, dhead, partials, P, off_Whead, off_bhead, rows, NH);
-    return check_launch("lstm_wgrad(head grad)");
+    return launch_head_grad(h, dhead, partials, nparts, P, off_Whead, off_bhead, rows, NH, stream);
 }
 
 }  // namespace b200rl

@@ -528,13 +528,19 @@ lstm_fwd16_kernel(const float* __restrict__ u, const float* __restrict__ hx0, co
 // ============================================================================== head_fwd
 // head_out[row][c] = b[c] + sum_k h[row][k] W[c][k];   128 rows per CTA pass, staged through smem; the next pass's
 // rows are already in flight (registers) while this one is reduced.
-constexpr int HR = 128;
+// TILED (NH <= 4, the actor-critic heads): four threads share a row, each holds its 16 k-columns of W_head in registers
+// (chunks kp, kp+4, kp+8, kp+12 of the row's sixteen float4) and reads h with conflict-free 16-byte loads (row stride 80
+// floats: a quarter-warp = 2 rows x 4 chunks covers eight bank groups); two shuffles finish the dot products.  The scalar
+// form needed two shared-memory loads per FMA and was LDS-bound (ncu r1h: short_scoreboard 8.1).
+constexpr int HR = 128, HFS = 80;
+template <bool TILED>
 __global__ void __launch_bounds__(HR)
 head_fwd_kernel(const float* __restrict__ h, const float* __restrict__ W, const float* __restrict__ b,
                 float* __restrict__ out, long long rows, int NH) {
-    __shared__ float Ht[HR * (H + 1)];
-    __shared__ float Ws[32 * H];
-    __shared__ float bs[32];
+    B200RL_DYN_SMEM(float, smem);
+    float* Ht = smem;                       // [HR][HFS]
+    float* Ws = Ht + HR * HFS;              // [32][H]
+    float* bs = Ws + 32 * H;                // [32]
     const int tid = threadIdx.x;
     for (int i = tid; i < NH * H; i += HR) Ws[i] = W[i];
     if (tid < NH) bs[tid] = b[tid];
@@ -551,19 +557,52 @@ head_fwd_kernel(const float* __restrict__ h, const float* __restrict__ W, const 
         }
     };
     fetch(blockIdx.x);
+    __syncthreads();
+    const int kp = tid & 3, rsub = tid >> 2;              // TILED roles: k-chunk set, row inside a 32-row sub-pass
+    float4 wreg[TILED ? 4 : 1][4];                        // W[c][chunk kp + 4 e]
+    float breg[TILED ? 4 : 1];
+    if (TILED) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            breg[c] = c < NH ? bs[c] : 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) wreg[c][e] = c < NH ? ld4(Ws + c * H + (e * 4 + kp) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
     for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
         const long long r0 = blk * HR;
         __syncthreads();
 #pragma unroll
         for (int it = 0; it < NV; ++it) {
             const int idx = it * HR + tid, r = idx >> 4, c4 = idx & 15;
-            float* d = Ht + r * (H + 1) + c4 * 4;
-            d[0] = pv[it].x; d[1] = pv[it].y; d[2] = pv[it].z; d[3] = pv[it].w;
+            st4(Ht + r * HFS + c4 * 4, pv[it]);
         }
         __syncthreads();
         fetch(blk + gridDim.x);
-        if (r0 + tid < rows) {
-            const float* hr = Ht + tid * (H + 1);
+        if (TILED) {
+#pragma unroll
+            for (int sub = 0; sub < HR / 32; ++sub) {
+                const int r = sub * 32 + rsub;
+                float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float4 v = ld4(Ht + r * HFS + (e * 4 + kp) * 4);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        a[c] = fmaf(v.x, wreg[c][e].x, fmaf(v.y, wreg[c][e].y, fmaf(v.z, wreg[c][e].z, fmaf(v.w, wreg[c][e].w, a[c]))));
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    a[c] += __shfl_xor_sync(kFull, a[c], 1);
+                    a[c] += __shfl_xor_sync(kFull, a[c], 2);
+                }
+                if (kp < NH && r0 + r < rows) {          // lane kp of the four writes head kp
+                    const float v = kp == 0 ? a[0] + breg[0] : kp == 1 ? a[1] + breg[1] : kp == 2 ? a[2] + breg[2] : a[3] + breg[3];
+                    out[(size_t)(r0 + r) * NH + kp] = v;
+                }
+            }
+        } else if (r0 + tid < rows) {
+            const float* hr = Ht + tid * HFS;
             for (int c = 0; c < NH; ++c) {
                 float a = bs[c];
 #pragma unroll 16
@@ -1065,7 +1104,14 @@ extern "C" int b200rl_head_fwd(const float* h, const float* W_head, const float*
     B200RL_REQUIRE(rows >= 1 && NH >= 1 && NH <= B200RL_MAX_HEADS, "head_fwd: bad shape rows=%lld NH=%d", rows, NH);
     const long long nblk = (rows + HR - 1) / HR;
     const long long cap = (long long)sm_count() * 4;
-    B200RL_LAUNCH(head_fwd_kernel, (int)(nblk < cap ? nblk : cap), HR, 0, stream, h, W_head, b_head, head_out, rows, NH);
+    const size_t hsm = sizeof(float) * (size_t)(HR * HFS + 32 * H + 32);
+    if (NH <= 4) {
+        if (set_smem(head_fwd_kernel<true>, hsm, "head_fwd")) return 1;
+        B200RL_LAUNCH(head_fwd_kernel<true>, (int)(nblk < cap ? nblk : cap), HR, hsm, stream, h, W_head, b_head, head_out, rows, NH);
+    } else {
+        if (set_smem(head_fwd_kernel<false>, hsm, "head_fwd")) return 1;
+        B200RL_LAUNCH(head_fwd_kernel<false>, (int)(nblk < cap ? nblk : cap), HR, hsm, stream, h, W_head, b_head, head_out, rows, NH);
+    }
     return check_launch("head_fwd");
 }
 
