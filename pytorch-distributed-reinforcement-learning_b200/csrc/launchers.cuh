@@ -12,9 +12,8 @@ int launch_dx_tc(const float* dpre, const float* u, const float* W_ih, const flo
                  long long off_Wt, long long off_bt, long long off_Whead, long long off_bhead,
                  float* du, int B, int T, int Fin, int NH, void* stream);
 // xproj_tc.cu: xproj[b,t,p] = bias + ReLU(torso) . W_ih^T for all rows, gate-interleaved columns
-// (`igfo`: order the four gate columns of a unit (i, g, f, o) instead of (i, f, g, o) -- what fwd_tc.cu reads)
 int launch_xproj_tc(const float* u, const float* Wt, const float* bt, const float* W_ih, const float* b_ih, const float* b_hh,
-                    float* xproj, int B, int T, int Fin, int igfo, int sms, void* stream);
+                    float* xproj, int B, int T, int Fin, int sms, void* stream);
 // fwd_tc.cu: recurrent LSTM forward with the per-step GEMM on tcgen05; xg = xproj (i,g,f,o) in, saved activations out
 int launch_fwd_tc(float* xg, const float* hx0, const float* cx0, const float* W_hh, float* c, float* h,
                   int B, int T, int sms, void* stream);

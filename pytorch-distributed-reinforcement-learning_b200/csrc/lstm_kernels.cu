@@ -1076,12 +1076,12 @@ extern "C" int b200rl_lstm_fwd(const float* u, const float* hx0, const float* cx
     const int grid = ntiles < sm_count() ? ntiles : sm_count();
     if (variant == 3) {
         // input projection AND the recurrent GEMM on tcgen05
-        if (launch_xproj_tc(u, Wt, bt, W_ih, b_ih, b_hh, gates, B, T, Fin, 0, sm_count(), stream)) return 1;
+        if (launch_xproj_tc(u, Wt, bt, W_ih, b_ih, b_hh, gates, B, T, Fin, sm_count(), stream)) return 1;
         return launch_fwd_tc(gates, hx0, cx0, W_hh, c, h, B, T, sm_count(), stream);
     }
     if (variant == 2) {
         // input projection on tcgen05 for all (b,t), staged in the (not yet written) `gates` buffer
-        if (launch_xproj_tc(u, Wt, bt, W_ih, b_ih, b_hh, gates, B, T, Fin, 0, sm_count(), stream)) return 1;
+        if (launch_xproj_tc(u, Wt, bt, W_ih, b_ih, b_hh, gates, B, T, Fin, sm_count(), stream)) return 1;
         const size_t smx = fwdx_smem_bytes();
         if (set_smem(lstm_fwdx_kernel, smx, "lstm_fwd(recurrent)")) return 1;
         B200RL_LAUNCH(lstm_fwdx_kernel, grid, NT, smx, stream, gates, hx0, cx0, W_hh, c, h, B, T);
