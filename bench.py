@@ -286,7 +286,7 @@ def main():
         log(f"value leg done: {total_ms / a.steps:.3f} ms/step")
 
     # ---- e2e: the reference-facing learning() coroutine fed with pinned HOST batches
-    n_e2e = min(a.steps, 50)
+    n_e2e = min(a.steps, 200)
     pinned = [tuple(t.pin_memory() for t in as_reference_tuple(b, T)[:6]) + (b["hx"].pin_memory(), b["cx"].pin_memory())
               for b in host]
     learner.args.loss_log_interval = 1                        # D2H read of the losses every step
