@@ -10,7 +10,8 @@ from . import native
 from .native import ptr
 
 H = 64
-# kernel variants (env-overridable for A/B measurements): forward 3 = tcgen05 input projection + tcgen05 recurrent
+# kernel variants (env-overridable for A/B measurements): forward 4 = as 3 with two 16-sequence groups per CTA in ping-pong,
+# 3 = tcgen05 input projection + tcgen05 recurrent
 # kernel (W_hh resident in tensor memory), 2 = tcgen05 input projection + FFMA recurrent kernel (K=64),
 # 1 = 16-warp split-K FFMA, 0 = 8-warp FFMA with the projection in the loop
 FWD_VARIANT = int(os.environ.get("B200RL_FWD_VARIANT", "3"))

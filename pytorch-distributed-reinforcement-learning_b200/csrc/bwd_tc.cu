@@ -171,13 +171,15 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
         float* CO = COEF + pair * 256 + lane;                        // + (k*8)*256 + i*32
         float* DX = DHX + pair * 128 + lane;                         // + i*32
         auto read_acc = [&](float (&d)[8]) {                         // my lane's 8 sequences: the NI partial accumulators summed
-            tc::tmem_ld8(tc::tmem_addr(tmem, my_lane, TM_D + cg * 8), d);
+            uint32_t u[NI][8];                                       // all loads in flight, one wait
 #pragma unroll
-            for (int a = 1; a < NI; ++a) {
-                float e[8];
-                tc::tmem_ld8(tc::tmem_addr(tmem, my_lane, TM_D + a * TB + cg * 8), e);
+            for (int a = 0; a < NI; ++a) tc::tmem_ld8_async(tc::tmem_addr(tmem, my_lane, TM_D + a * TB + cg * 8), u[a]);
+            tc::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 8; ++i) d[i] += e[i];
+            for (int i = 0; i < 8; ++i) {
+                d[i] = __uint_as_float(u[0][i]);
+#pragma unroll
+                for (int a = 1; a < NI; ++a) d[i] += __uint_as_float(u[a][i]);
             }
         };
         uint32_t nb = 0;                                             // accumulator batches waited for so far

@@ -188,15 +188,17 @@ lstm_fwdt_kernel(float* xg, const float* __restrict__ hx0, const float* __restri
                 FWP(1, 0);
                 float xa[RW], xb[RW];
                 {                                                       // gate i (or f) / g (or o) of unit j, RW sequences: even + odd K-step partials
-                    float e[RW];
-                    tc::tmem_ld8(tc::tmem_addr(tmem, addr_lane, TM_D + 0 * TB + rbase), xa);
-                    tc::tmem_ld8(tc::tmem_addr(tmem, addr_lane, TM_D + 1 * TB + rbase), e);
+                    uint32_t u0[RW], u1[RW], u2[RW], u3[RW];            // four loads in flight, one wait
+                    tc::tmem_ld8_async(tc::tmem_addr(tmem, addr_lane, TM_D + 0 * TB + rbase), u0);
+                    tc::tmem_ld8_async(tc::tmem_addr(tmem, addr_lane, TM_D + 1 * TB + rbase), u1);
+                    tc::tmem_ld8_async(tc::tmem_addr(tmem, addr_lane, TM_D + 2 * TB + rbase), u2);
+                    tc::tmem_ld8_async(tc::tmem_addr(tmem, addr_lane, TM_D + 3 * TB + rbase), u3);
+                    tc::tmem_ld_wait();
 #pragma unroll
-                    for (int r = 0; r < RW; ++r) xa[r] += e[r];
-                    tc::tmem_ld8(tc::tmem_addr(tmem, addr_lane, TM_D + 2 * TB + rbase), xb);
-                    tc::tmem_ld8(tc::tmem_addr(tmem, addr_lane, TM_D + 3 * TB + rbase), e);
-#pragma unroll
-                    for (int r = 0; r < RW; ++r) xb[r] += e[r];
+                    for (int r = 0; r < RW; ++r) {
+                        xa[r] = __uint_as_float(u0[r]) + __uint_as_float(u1[r]);
+                        xb[r] = __uint_as_float(u2[r]) + __uint_as_float(u3[r]);
+                    }
                 }
                 FWP(2, 0);
 #pragma unroll

@@ -17,6 +17,9 @@ int launch_xproj_tc(const float* u, const float* Wt, const float* bt, const floa
 // fwd_tc.cu: recurrent LSTM forward with the per-step GEMM on tcgen05; xg = xproj (i,g,f,o) in, saved activations out
 int launch_fwd_tc(float* xg, const float* hx0, const float* cx0, const float* W_hh, float* c, float* h,
                   int B, int T, int sms, void* stream);
+// fwd_tc2.cu: the same with two 16-sequence groups per CTA in ping-pong (tensor core of one group under the cell phase of the other)
+int launch_fwd_tc2(float* xg, const float* hx0, const float* cx0, const float* W_hh, float* c, float* h,
+                   int B, int T, int sms, void* stream);
 // dx_tc.cu: torso gradients from a stored dx (written by bwd_tc.cu) + head gradients
 int launch_torso_from_dx(const float* dx, const float* u, const float* Wt, const float* bt,
                          const float* h, const float* dhead, float* partials, int nparts, long long P,

@@ -1071,9 +1071,14 @@ extern "C" int b200rl_lstm_fwd(const float* u, const float* hx0, const float* cx
                                int B, int T, int Fin, int variant, void* stream) {
     B200RL_REQUIRE(B >= 1 && T >= 1, "lstm_fwd: bad shape B=%d T=%d", B, T);
     B200RL_REQUIRE(Fin >= 1 && Fin <= MAXF, "lstm_fwd: Fin=%d out of range [1,%d]", Fin, MAXF);
-    B200RL_REQUIRE(variant >= 0 && variant <= 3, "lstm_fwd: unknown variant %d", variant);
+    B200RL_REQUIRE(variant >= 0 && variant <= 4, "lstm_fwd: unknown variant %d", variant);
     const int ntiles = (B + TM - 1) / TM;
     const int grid = ntiles < sm_count() ? ntiles : sm_count();
+    if (variant == 4) {
+        // as 3, recurrent kernel with two sequence groups per CTA in ping-pong
+        if (launch_xproj_tc(u, Wt, bt, W_ih, b_ih, b_hh, gates, B, T, Fin, sm_count(), stream)) return 1;
+        return launch_fwd_tc2(gates, hx0, cx0, W_hh, c, h, B, T, sm_count(), stream);
+    }
     if (variant == 3) {
         // input projection AND the recurrent GEMM on tcgen05
         if (launch_xproj_tc(u, Wt, bt, W_ih, b_ih, b_hh, gates, B, T, Fin, sm_count(), stream)) return 1;

@@ -145,6 +145,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
 }
+// several tcgen05.ld in flight, one wait: issue with tmem_ld8_async (results are NOT valid yet), then tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld8_async(uint32_t taddr, uint32_t (&u)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 4 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&r)[4]) {
+    uint32_t u[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = __uint_as_float(u[i]);
+}
 // 8 consecutive accumulator columns of this thread's TMEM lane
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&r)[8]) {
     uint32_t u[8];
@@ -241,6 +258,15 @@ inline void tmem_st16(uint32_t taddr, const float (&r)[16]) {
 inline void tmem_ld32(uint32_t taddr, float (&r)[32]) {
     const int lane = (int)(taddr >> 16), col = (int)(taddr & 0xffff);
     for (int i = 0; i < 32; ++i) r[i] = emul_tmem().d[lane][col + i];
+}
+inline void tmem_ld8_async(uint32_t taddr, uint32_t (&u)[8]) {
+    const int lane = (int)(taddr >> 16), col = (int)(taddr & 0xffff);
+    for (int i = 0; i < 8; ++i) u[i] = __float_as_uint(emul_tmem().d[lane][col + i]);
+}
+inline void tmem_ld_wait() {}
+inline void tmem_ld4(uint32_t taddr, float (&r)[4]) {
+    const int lane = (int)(taddr >> 16), col = (int)(taddr & 0xffff);
+    for (int i = 0; i < 4; ++i) r[i] = emul_tmem().d[lane][col + i];
 }
 inline void tmem_ld8(uint32_t taddr, float (&r)[8]) {
     const int lane = (int)(taddr >> 16), col = (int)(taddr & 0xffff);

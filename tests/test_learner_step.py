@@ -44,11 +44,11 @@ def test_forward_matches_reference(backend, name):
     _close(logits.cpu(), g["fwd/logits"], what="logits")
 
 
-@pytest.mark.parametrize("variant", [0, 2, 3])
+@pytest.mark.parametrize("variant", [0, 2, 3, 4])
 def test_forward_kernel_variants_agree_with_reference(backend, variant, monkeypatch):
     """Every forward kernel generation stays selectable (B200RL_FWD_VARIANT) and parity-green: 0 = FFMA with
     the projection in the loop, 2 = tcgen05 projection + FFMA recurrence, 3 = tcgen05 projection + tcgen05
-    recurrence (default)."""
+    recurrence (default), 4 = as 3 with two sequence groups per CTA in ping-pong (measured: no faster, kept for A/B)."""
     from b200rl import ops as O
     ops, dev = backend
     monkeypatch.setattr(O, "FWD_VARIANT", variant)
