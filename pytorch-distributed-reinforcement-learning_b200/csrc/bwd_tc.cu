@@ -154,8 +154,8 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                         const int p0 = s * 8;
                         const tc::SmemDesc bh = tc::make_desc(B_hi + s * 2 * B_LBO, B_LBO, B_SBO);
                         const tc::SmemDesc bl = tc::make_desc(B_lo + s * 2 * B_LBO, B_LBO, B_SBO);
-                        tc::mma_tf32_ts(D, tmem + TM_AH + p0, bh, idesc, s > ii * (G / 8 / NI) ? 1u : 0u);
-                        tc::mma_tf32_ts(D, tmem + TM_AH + p0, bl, idesc, 1u);
+                        tc::mma_tf32_ts(D, tmem + TM_AH + p0, bl, idesc, s > ii * (G / 8 / NI) ? 1u : 0u);   // (order: one operand changes per MMA)
+                        tc::mma_tf32_ts(D, tmem + TM_AH + p0, bh, idesc, 1u);
                         if (p0 < KS) tc::mma_tf32_ts(D, tmem + TM_AL + p0, bh, idesc, 1u);
                         else tc::mma_tf32(D, tc::make_desc(ALs + ((p0 - KS) >> 2) * AL_LBO, AL_LBO, AL_SBO), bh, idesc, 1u);
                     }

@@ -131,8 +131,8 @@ lstm_fwdt_kernel(float* xg, const float* __restrict__ hx0, const float* __restri
                     for (int s = kh; s < H / 8; s += 2) {
                         const tc::SmemDesc bh = tc::make_desc(B_hi + s * 2 * B_LBO, B_LBO, B_SBO);
                         const tc::SmemDesc bl = tc::make_desc(B_lo + s * 2 * B_LBO, B_LBO, B_SBO);
-                        tc::mma_tf32_ts(D, Ah + s * 8, bh, idesc, s > 1 ? 1u : 0u);
-                        tc::mma_tf32_ts(D, Ah + s * 8, bl, idesc, 1u);
+                        tc::mma_tf32_ts(D, Ah + s * 8, bl, idesc, s > 1 ? 1u : 0u);     // (order: one operand changes per MMA)
+                        tc::mma_tf32_ts(D, Ah + s * 8, bh, idesc, 1u);
                         tc::mma_tf32_ts(D, Al + s * 8, bh, idesc, 1u);
                     }
                     tc::mma_commit(acc_done);
