@@ -10,9 +10,12 @@
 // The two GEMMs of a step are ONE tcgen05 accumulation with the weights as M:
 //   D[128 x 32] = [W_hh^T ; W_ih^T][128 x 256] . dpre_t^T[256 x 32]     (lanes 0-63: dh_rec, lanes 64-127: dx)
 // so the torso gradient's GEMM (a separate 537 MB pass over dpre before) rides along for free.
-// 3xTF32: A_hi lives in tensor memory (256 columns); A_lo for k < 192 too (192 columns), the last 64 k
-// in shared memory (32 KB, SS-form MMAs); dpre (B operand, hi/lo, K-major) is rewritten every step by the
-// cell phase.  96 MMAs per step; one thread gets a small tcgen05.mma out only every ~60-120 cycles while issues from
+// Split precision: A_hi (TF32) lives in tensor memory (256 columns) and meets dpre_hi and dpre_lo (TF32, K-major B
+// operands in shared memory, rewritten every step by the cell phase) in two kind::tf32 MMAs per K-step; the third term
+// A_lo . dpre_hi is ~2^-11 of the result, so it runs in bf16 (kind::f16, K = 16: half the MMAs): A_lo as bf16 pairs
+// is 128 more TMEM columns and dpre_hi gets a bf16 copy.  Its error is 2^-9 of a 2^-11 term, i.e. ~2^-20 relative, the
+// same order as the dropped lo*lo term.  (With A_lo in TF32 the last 64 K columns did not fit in tensor memory and
+// ran as SS-form MMAs that pull 4 KB of A through shared memory each: +0.06 ms for 8 of them.)  96 MMAs per step; one thread gets a small tcgen05.mma out only every ~60-120 cycles while issues from
 // different threads overlap (tools/tc_probe3.cu), so TWO issuer warps split K into halves with an accumulator each and
 // the readers sum the partials.  Measured alternatives (tools/bwd_prof.cu, same shape): 1 issuer 0.68 ms, 2 issuers
 // 0.43 ms, 3 issuers (A_lo: 160 columns in TMEM) 0.50 ms, 4 issuers (128 columns) 0.59 ms -- every extra accumulator
@@ -49,24 +52,21 @@ namespace btk {
 #ifndef B200RL_BWD_NI
 #define B200RL_BWD_NI 2
 #endif
-#ifndef B200RL_BWD_KS
-#define B200RL_BWD_KS 192
-#endif
 constexpr int H = 64, G = 256, TB = 32, NC = 512, NI = B200RL_BWD_NI, NT = NC + 32 * NI;    // 8 critical + 8 helper warps, NI MMA issuer warps
 constexpr int B_LBO = 144, B_SBO = 9216;                            // B: 64 core matrices along K, 16-byte skew -> conflict-free 16-byte stores
 constexpr int B_BYTES = (TB / 8) * B_SBO;                           // 36864 per hi / lo
 static_assert(63 * B_LBO + 128 <= B_SBO, "core matrices of one 8-row group must fit below SBO");
-constexpr int KS = B200RL_BWD_KS;                                   // A_lo: k < KS in tensor memory, k >= KS in shared memory
-constexpr int AL_LBO = 128, AL_SBO = ((G - KS) / 4) * 128;          // 2048
-constexpr int AL_BYTES = (128 / 8) * AL_SBO;                        // 65536
-constexpr int TM_D = 0, TM_AH = NI * TB, TM_AL = TM_AH + G, TM_COLS = 512;     // accumulator i at columns 32 i
-static_assert(TM_AL + KS <= TM_COLS, "tensor memory budget");
+constexpr int C_LBO = 144, C_SBO = 4608;                            // bf16 copy of dpre_hi (third split term): 32 core matrices (8 k) along K, same skew
+constexpr int C_BYTES = (TB / 8) * C_SBO;                           // 18432
+static_assert(31 * C_LBO + 128 <= C_SBO, "core matrices of one 8-row group must fit below SBO");
+constexpr int TM_D = 0, TM_AH = NI * TB, TM_AL = TM_AH + G, TM_COLS = 512;     // accumulator i at columns 32 i ; A_lo: bf16 pairs, G/2 columns
+static_assert(TM_AL + G / 2 <= TM_COLS, "tensor memory budget");
 constexpr int NCOEF = 7;                                            // dhW, P_o, Q, P_i, P_f, P_g, f
 constexpr int CELLS = TB * H;
 }  // namespace btk
 
 static inline size_t bwdt_smem_bytes(int NH) {
-    return 2 * (size_t)btk::B_BYTES + btk::AL_BYTES + sizeof(float) * (size_t)(btk::NCOEF * btk::CELLS + NH * btk::H + 8 * 8 * NH + 8 * 4 * 32) + 64;
+    return 2 * (size_t)btk::B_BYTES + btk::C_BYTES + sizeof(float) * (size_t)(btk::NCOEF * btk::CELLS + NH * btk::H + 8 * 8 * NH + 8 * 4 * 32) + 64;
 }
 
 __global__ void __launch_bounds__(btk::NT, 1)
@@ -77,8 +77,8 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
     B200RL_DYN_SMEM(unsigned char, smem);
     unsigned char* B_hi = smem;
     unsigned char* B_lo = smem + B_BYTES;
-    unsigned char* ALs = smem + 2 * B_BYTES;
-    float* COEF = reinterpret_cast<float*>(ALs + AL_BYTES);          // COEF[(k*8 + pair)*256 + i*32 + lane]
+    unsigned char* B_16 = smem + 2 * B_BYTES;                        // dpre_hi again, as bf16 (K-major, 8 per core-matrix row)
+    float* COEF = reinterpret_cast<float*>(B_16 + C_BYTES);          // COEF[(k*8 + pair)*256 + i*32 + lane]
     float* WhS = COEF + NCOEF * CELLS;                               // WhS[c*64 + j]
     float* DHS = WhS + NH * H;                                       // DHS[helper pair][8 sequences * NH]: dhead rows of the step being prepared
     float* DHX = DHS + 8 * 8 * NH;                                   // DHX[pair][4][lane]: dh_rec of the cells the helper finishes
@@ -110,31 +110,29 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
     if (cellw) {
         const int m = 32 * q + lane;
         const float* wsrc = (m < H ? W_hh : W_ih) + (m & (H - 1));
-        for (int k0 = 0; k0 < 64; k0 += 16) {
-            float hi[16], lo[16];
+        for (int k0 = 0; k0 < 64; k0 += 32) {
+            float lo16[16];                                          // 32 bf16 of A_lo = 16 packed columns
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const int p = cg * 64 + k0 + e, n = (p & 3) * H + (p >> 2);
-                tc::split_tf32(wsrc[(size_t)n * H], hi[e], lo[e]);
-            }
-            const int p0 = cg * 64 + k0;
-            tc::tmem_st16(tc::tmem_addr(tmem, my_lane, TM_AH + p0), hi);
-            if (p0 < KS) {
-                tc::tmem_st16(tc::tmem_addr(tmem, my_lane, TM_AL + p0), lo);
-            } else {
+            for (int hh = 0; hh < 2; ++hh) {
+                float hi[16], lo[16];
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
-                    const int pp = p0 + e - KS;
-                    *reinterpret_cast<float*>(ALs + (m & 7) * 16 + (m >> 3) * AL_SBO + (pp & 3) * 4 + (pp >> 2) * AL_LBO) = lo[e];
+                    const int p = cg * 64 + k0 + hh * 16 + e, n = (p & 3) * H + (p >> 2);
+                    tc::split_tf32(wsrc[(size_t)n * H], hi[e], lo[e]);
                 }
+                tc::tmem_st16(tc::tmem_addr(tmem, my_lane, TM_AH + cg * 64 + k0 + hh * 16), hi);
+#pragma unroll
+                for (int e = 0; e < 16; e += 2)
+                    lo16[hh * 8 + e / 2] = __uint_as_float((unsigned)tc::bf16_bits(lo[e]) | ((unsigned)tc::bf16_bits(lo[e + 1]) << 16));
             }
+            tc::tmem_st16(tc::tmem_addr(tmem, my_lane, TM_AL + (cg * 64 + k0) / 2), lo16);
         }
     }
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
-    const uint32_t idesc = tc::make_idesc_tf32(128, TB, false, false);
+    const uint32_t idesc = tc::make_idesc_tf32(128, TB, false, false), idesc16 = tc::make_idesc_bf16(128, TB);
     const int ntiles = (B + TB - 1) / TB;
 
     if (!cellw) {
@@ -156,8 +154,8 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                         const tc::SmemDesc bl = tc::make_desc(B_lo + s * 2 * B_LBO, B_LBO, B_SBO);
                         tc::mma_tf32_ts(D, tmem + TM_AH + p0, bl, idesc, s > ii * (G / 8 / NI) ? 1u : 0u);   // (order: one operand changes per MMA)
                         tc::mma_tf32_ts(D, tmem + TM_AH + p0, bh, idesc, 1u);
-                        if (p0 < KS) tc::mma_tf32_ts(D, tmem + TM_AL + p0, bh, idesc, 1u);
-                        else tc::mma_tf32(D, tc::make_desc(ALs + ((p0 - KS) >> 2) * AL_LBO, AL_LBO, AL_SBO), bh, idesc, 1u);
+                        if (s & 1)                                   // third split term A_lo . dpre_hi in bf16, K = 16: one MMA per two K-steps
+                            tc::mma_bf16_ts(D, tmem + TM_AL + (p0 - 8) / 2, tc::make_desc(B_16 + (s >> 1) * 2 * C_LBO, C_LBO, C_SBO), idesc16, 1u);
                     }
                     tc::mma_commit(acc_done);
                     BWP(18, NC);
@@ -209,6 +207,9 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                     const int ob = (r & 7) * 16 + (r >> 3) * B_SBO + j * B_LBO;
                     *reinterpret_cast<float4*>(B_hi + ob) = hi;
                     *reinterpret_cast<float4*>(B_lo + ob) = lo;
+                    const unsigned long long h16 = (unsigned long long)((unsigned)tc::bf16_bits(hi.x) | ((unsigned)tc::bf16_bits(hi.y) << 16)) |
+                                                   ((unsigned long long)((unsigned)tc::bf16_bits(hi.z) | ((unsigned)tc::bf16_bits(hi.w) << 16)) << 32);
+                    *reinterpret_cast<unsigned long long*>(B_16 + (r & 7) * 16 + (r >> 3) * C_SBO + (j >> 1) * C_LBO + (j & 1) * 8) = h16;
                 }
             };
             auto store_dpre = [&](int t, int i0, const float4 (&dps)[4]) {

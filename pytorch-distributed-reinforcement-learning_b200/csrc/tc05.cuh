@@ -11,6 +11,7 @@
 //   K-major : elem(mn, k) at  (mn%8)*16 + (mn/8)*SBO + (k%4)*4  + (k/4)*LBO
 // i.e. both are built from the same 128-byte "core matrix" of 8 rows x 16 bytes.
 #pragma once
+#include <string.h>
 #include "common.cuh"
 
 namespace b200rl {
@@ -30,6 +31,13 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn_m
          | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16)
          | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+
+// instruction descriptor for kind::f16 with bf16 inputs, fp32 accumulate, both operands K-major
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// fp32 -> bf16 bits by truncation (used for the small third split term only) / back
+__host__ __device__ inline unsigned short bf16_bits(float f) { unsigned u; memcpy(&u, &f, 4); return (unsigned short)(u >> 16); }
 
 #ifndef B200RL_EMUL
 // ------------------------------------------------------------------------------ device
@@ -108,6 +116,16 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, Sm
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T with bf16 inputs, K = 16: a 32-bit TMEM column of A holds k = 2c (low half) and
+// k = 2c + 1 (high half) (measured, tools/tc_probe4.cu); B is K-major, 8 bf16 per 16-byte core-matrix row
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, SmemDesc b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
         "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
 }
 // arrive on `bar` once every MMA issued so far by this thread has completed
@@ -248,6 +266,22 @@ inline void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, SmemDesc b, uint32_t i
         for (int n = 0; n < N; ++n) {
             float s = accumulate ? t.d[m][d_tmem + n] : 0.f;
             for (int k = 0; k < 8; ++k) s += __uint_as_float(__float_as_uint(t.d[m][a_tmem + k]) & kTf32Mask) * emul_elem(b, bmn, n, k);
+            t.d[m][d_tmem + n] = s;
+        }
+}
+inline void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, SmemDesc b, uint32_t idesc, uint32_t accumulate) {
+    const int M = (int)((idesc >> 24) & 31) << 4, N = (int)((idesc >> 17) & 63) << 3;
+    EmulTmem& t = emul_tmem();
+    auto up = [](unsigned short h) { unsigned u = (unsigned)h << 16; float f; memcpy(&f, &u, 4); return f; };
+    for (int m = 0; m < M; ++m)
+        for (int n = 0; n < N; ++n) {
+            float s = accumulate ? t.d[m][d_tmem + n] : 0.f;
+            for (int k = 0; k < 16; ++k) {
+                const unsigned cell = __float_as_uint(t.d[m][a_tmem + k / 2]);
+                unsigned short bb;
+                memcpy(&bb, b.base + (size_t)(n % 8) * 16 + (size_t)(n / 8) * b.sbo + (size_t)(k % 8) * 2 + (size_t)(k / 8) * b.lbo, 2);
+                s += up((unsigned short)(k & 1 ? cell >> 16 : cell & 0xffff)) * up(bb);
+            }
             t.d[m][d_tmem + n] = s;
         }
 }

@@ -287,6 +287,10 @@ def test_full_size_tcgen05_path_agrees_with_ffma_path(monkeypatch):
     for k in ("policy-loss", "value-loss", "policy-entropy", "loss", "ratio-avg"):
         _close(L_tc[k], L_ff[k], rtol=1e-4, atol=1e-7, what=k)
     _close(g_tc.cpu(), g_ff.cpu(), rtol=1e-3, atol=2e-5 * float(g_ff.abs().max()), what="flat gradient, tcgen05 vs FFMA")
+    # split-precision check: the tcgen05 kernels' third term (bf16 / tf32 lo parts) carries ~2^-11 of every product; if it were
+    # dropped or mis-laid the gradient would be off by ~1e-4 in norm, two orders above the reduction-order noise measured here
+    rel = float((g_tc - g_ff).norm() / g_ff.norm())
+    assert rel < 2e-5, f"tcgen05 vs FFMA gradient differ by {rel:.2e} in norm"
     perm = torch.randperm(B, generator=torch.Generator().manual_seed(1)).to(dev)
     L_p, g_p = run(3, 1, 1, perm)
     _close(L_p["loss"], L_tc["loss"], rtol=1e-5, atol=1e-8, what="loss under a permutation of the sequences")
