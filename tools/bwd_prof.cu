@@ -33,7 +33,7 @@ int main() {
 #ifdef B200RL_BWDPROF
     cudaMemcpyFromSymbol(z, g_bwdprof, sizeof(z));
 #else
-    printf("bwd_tc (no probes, NI=%d KS=%d) %.3f ms\n", btk::NI, btk::KS, ms);
+    printf("bwd_tc (no probes, NI=%d) %.3f ms\n", btk::NI, ms);
     return 0;
 #endif
     const double steps = (B / 32.0) * T;
