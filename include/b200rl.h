@@ -69,7 +69,9 @@ int b200rl_soft_update(const float* src, float* target, long long n, float tau, 
  * Wt (H, Fin), bt (H) torso Linear;  W_ih/W_hh (4H, H), b_ih/b_hh (4H) PyTorch layout
  * saved activations (private layout, only lstm_bwd / lstm_wgrad read them):
  *   gates (B, T, H, 4) post-activation i,f,g,o ; c (B, T, H) ; h (B, T, H)
- * `variant`: 0 = default kernel.                                                     */
+ * `variant`: 0 = FFMA kernel with the input projection in the loop; 1 = 16-warp FFMA;
+ *            2 = tcgen05 input projection + FFMA recurrence; 3 = tcgen05 input projection +
+ *            tcgen05 recurrence (what the Python layer uses); 4 = as 3, ping-pong groups.  */
 int b200rl_lstm_fwd(const float* u, const float* hx0, const float* cx0,
                     const float* Wt, const float* bt,
                     const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh,
