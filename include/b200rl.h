@@ -140,6 +140,8 @@ int b200rl_impala_head(const float* head_out, const float* act, const float* rew
  *                the policy columns of dhead are zeroed.
  *   vmpo_select: per timestep column of gae_all (Bg,n): thr[t] = k-th largest over the batch (torch.topk(gae, k, dim=0));
  *                colstat[t] = column max, colstat[n+t] = sum over the selected of exp((g - max)/(eta+1e-7)).
+ *                Exactly k rows per column, as topk: rows tied AT thr[t] are taken in global row order up to
+ *                tie_cut[t] (INT_MAX when all of them belong to the top k).
  *                gae_all is the rank's own matrix on one GPU, the all-gathered one when the batch is sharded.
  *   vmpo_grad:   psi = softmax over all selected; adds dLoss/dz (policy + alpha*KL term) to dhead; scalars[0] += L_pi,
  *                scalars[2] += sum KL, scalars[3] += #selected, scalars[6],[7] = softmax max / normaliser.
@@ -150,10 +152,10 @@ int b200rl_vmpo_gae(const float* head_out, const float* rew, const float* is_fir
                     float* gae, float* dhead, double* scalars, int B, int T, int A,
                     float gamma, float lambda_, float c_value, double N_global, void* stream);
 int b200rl_vmpo_select(const float* gae_all, int Bg, int n, int k, const double* duals,
-                       float* thr, float* colstat, void* stream);
+                       float* thr, float* colstat, int* tie_cut, void* stream);
 int b200rl_vmpo_grad(const float* head_out, const float* act, const float* behav_logits, const float* gae,
-                     const float* thr, const float* colstat, const double* duals,
-                     float* dhead, double* scalars, int B, int T, int A,
+                     const float* thr, const float* colstat, const int* tie_cut, const double* duals,
+                     float* dhead, double* scalars, int B, int T, int A, int row_offset /* rank * B when sharded */,
                      float c_policy, double N_global, void* stream);
 int b200rl_vmpo_dual_step(double* duals, double* dual_sq, const double* scalars, double* losses_out,
                           double coef_eta, double coef_alpha, double lr, double rms_alpha, double rms_eps,
@@ -173,6 +175,32 @@ int b200rl_clip_adam(float* param, float* grad, float* m, float* v, long long n,
                      float grad_scale, float max_norm, float lr, float beta1, float beta2,
                      float eps, int step, const float* mask /* 0/1 per entry or NULL */,
                      float* norm_out, void* stream);
+
+/* ---- data-parallel step over NVLink peer memory (csrc/peer_kernels.cu) ---------------------------------------------
+ * For a batch sharded over the GPUs of one box (the reference has no multi-GPU learner) this ONE kernel
+ * replaces  dist.all_reduce(grad) ; clip_grad_norm_ ; optimizer.step()  (single-GPU tail:
+ * agents/learner_module/ppo/learning.py:93-106, agents/learner.py:70,360-367): flag handshake with the peers, one-shot
+ * all-reduce of the flat gradient by direct peer loads (rank order, bit-identical on every rank), global-norm clip,
+ * RMSprop (optimizer 0: s1 = square average, a1 = alpha) or Adam (optimizer 1: s1 = m, s2 = v, a1/a2 = betas).
+ *   peer_alloc / peer_open / peer_close / peer_free: a cudaMalloc'd, zeroed region and its 64-byte CUDA-IPC handle; the
+ *     other ranks map it with peer_open (peer access is enabled lazily).
+ *   peer_step: peer_grad[r] / peer_scal[r] = rank r's gradient (n floats, n % 4 == 0) and 8 fp64 loss sums for THIS step
+ *     (the caller alternates two buffers by step parity), peer_flags[r] = base of rank r's flag array (world x 32 u32),
+ *     my_flags = this rank's; gsync / part = local scratch (one u32, zeroed once; 64 doubles); epoch = 1, 2, 3, ... per
+ *     launch; gsync_target = sum of `grid` over all launches so far including this one.  grad_out receives the reduced,
+ *     scaled, clipped gradient, scal_out the reduced loss sums ([0..3] summed, [4] min, [5] max over ranks), *status
+ *     becomes 1 if a peer never announced its gradient within the timeout (default 30 s) -- the kernel never hangs.   */
+int b200rl_peer_alloc(long long bytes, void** ptr_out, unsigned char* handle64_out);
+int b200rl_peer_open(const unsigned char* handle64, void** ptr_out);
+int b200rl_peer_close(void* ptr);
+int b200rl_peer_free(void* ptr);
+int b200rl_peer_set_timeout_ms(long long ms);
+int b200rl_peer_step(int optimizer, float* param, float* s1, float* s2, const float* mask, float* grad_out,
+                     const void* const* peer_grad, const void* const* peer_scal, void* const* peer_flags,
+                     void* my_flags, void* gsync, double* part, double* scal_out, float* norm_out, int* status,
+                     long long n, int rank, int world, unsigned epoch, int grid, unsigned gsync_target,
+                     float grad_scale, float max_norm, float lr, float a1, float a2, float eps, int adam_step,
+                     void* stream);
 
 /* ---- SAC heads (element-wise over (B,T); scalars as above: [0] policy, [1] value, [2] entropy term) ----------
  * discrete SAC                                     agents/learner_module/sac/learning.py:36-143

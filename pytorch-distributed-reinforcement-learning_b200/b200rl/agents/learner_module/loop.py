@@ -20,7 +20,9 @@ after enqueuing update i the loop enqueues stream-ordered device->pinned-host co
 scalars of update i, starts the H2D of batch i+1, and only then finishes iteration i-1 on the host (`pub_model`, logging,
 checkpoint) while the GPU is busy with update i.  The host-side work (0.6 ms per iteration at B=4096, T=128: sync
 latency, state-dict export, loss read-back, kernel enqueue) no longer leaves the GPU idle; what the workers receive is
-bit-identical, one update (1.5 ms) later.  `B200RL_PIPELINE=0` selects the synchronous schedule.
+bit-identical, one update (1.2 ms) later -- but ONLY while the queue already holds the next batch: whenever the loop is
+about to wait on an empty queue it first finishes the pending iteration, so a slow feeder never sees a model that is a
+whole batch-collection interval stale.  `B200RL_PIPELINE=0` selects the synchronous schedule.
 """
 import asyncio
 import os
@@ -84,7 +86,16 @@ async def run_learning(parent, timer, queue_name, update, losses, publish_state,
         batch_args = None
         with timer.timer("learner-throughput", check_throughput=True):
             with timer.timer("learner-batching-time"):
-                batch_args, ahead = (ahead, None) if ahead is not None else (await queue.get(), None)
+                if ahead is not None:
+                    batch_args, ahead = ahead, None
+                else:
+                    if pending is not None and queue.empty():
+                        # nothing to overlap with: the feeder is slower than the learner (the normal case with real workers), so
+                        # publish / log iteration i NOW instead of after the next batch has been collected -- otherwise the
+                        # workers would gather all of batch i+1 under model i-1
+                        finish(*pending)
+                        pending = None
+                    batch_args = await queue.get()
             if batch_args is not None:
                 with timer.timer("learner-forward-time"):
                     dev_batch = parent.to_gpu(*batch_args)

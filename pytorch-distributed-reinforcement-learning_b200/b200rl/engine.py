@@ -19,9 +19,33 @@ import os
 
 import torch
 
+from . import comm as _comm
 from . import ops as _ops
 
 H = _ops.H
+
+
+def _make_comm(process_group, comm, device, ops):
+    """`comm` wins; a torch.distributed group becomes a PeerGroup (NVLink peer kernels) on CUDA devices, a TorchComm otherwise."""
+    if comm is not None or process_group is None:
+        return comm
+    if _comm.PeerGroup.available(device) and not ops.lib.emulated:
+        return _comm.PeerGroup(process_group, device, ops.lib)
+    return _comm.TorchComm(process_group)
+
+
+def _channel(comm, n, device, ops):
+    """The fused exchange + clip + optimizer kernel works on a `PeerChannel`: over the communicator's peer mappings when
+    there is one, else (single rank) over a private local region -- the same kernel runs at every world size."""
+    if comm is not None and hasattr(comm, "channel"):
+        return comm.channel(n)
+    if comm is None:
+        nbytes = _comm.HEADER_BYTES + 2 * ((n * 4 + 64 + 255) // 256 * 256)
+        region = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        ch = _comm.PeerChannel(n, 0, 1, device, ops.lib, local_regions=[region.data_ptr()])
+        ch._keep = region
+        return ch
+    return None                     # TorchComm (gloo / NCCL fallback): all_reduce + single-CTA clip/optimizer kernels
 
 _SCALAR_INIT = [0.0, 0.0, 0.0, 0.0, float("inf"), float("-inf"), 0.0, 0.0]
 
@@ -35,15 +59,17 @@ def _sm_count(device, ops):
 class OnPolicyEngine:
     """PPO / PPO-Continuous / IMPALA update for one `_FlatNet` actor-critic."""
 
-    def __init__(self, net, algo, hyper, ops=None, process_group=None):
+    def __init__(self, net, algo, hyper, ops=None, process_group=None, comm=None):
         self.net, self.algo, self.hp = net, algo, dict(hyper)
         self.ops = ops or _ops.default()
-        self.pg = process_group
-        self.world = 1 if process_group is None else torch.distributed.get_world_size(process_group)
         self.flat = net.flat_parameters()
         self.L = net._layout
         dev = self.flat.device
         self.device = dev
+        self.comm = _make_comm(process_group, comm, dev, self.ops)
+        self.world = 1 if self.comm is None else self.comm.world
+        self.rank = 0 if self.comm is None else self.comm.rank
+        self.chan = _channel(self.comm, self.L.P, dev, self.ops)
         self.grad = torch.zeros_like(self.flat)
         self.sq_avg = torch.zeros_like(self.flat)            # RMSprop state (learner.py:70)
         self.scalars = torch.zeros(8, dtype=torch.float64, device=dev)
@@ -95,34 +121,40 @@ class OnPolicyEngine:
         u = obs.reshape(B, T, -1)
         outs = self._alloc_outs(B, T) if self.debug_outs is not None else None
 
+        # gradient / loss-sum buffers of this step: the peer channel's (other ranks read them over NVLink) or the local ones
+        gbuf, sbuf = self.chan.begin() if self.chan is not None else (self.grad, self.scalars)
         ops.lstm_fwd(L, self.flat, u, batch["hx"], batch["cx"], self.ws)
         ops.head_fwd(L, self.flat, self.ws["h"], self.head_out)
-        self.scalars.copy_(self._scalar_init)
+        sbuf.copy_(self._scalar_init)
         if self.algo == "IMPALA":
-            ops.impala_head(self.head_out, batch, self.dhead, self.scalars, hp, self.net.n_outputs, outs)
+            ops.impala_head(self.head_out, batch, self.dhead, sbuf, hp, self.net.n_outputs, outs)
         else:
-            ops.ppo_head(self.head_out, batch, self.dhead, self.scalars, hp, self.net.n_outputs,
+            ops.ppo_head(self.head_out, batch, self.dhead, sbuf, hp, self.net.n_outputs,
                          self.net.continuous, outs)
         ops.lstm_bwd(L, self.flat, self.dhead, self.ws, batch["cx"])
         ops.lstm_wgrad(L, self.flat, self.ws, batch["hx"], u, self.dhead, self.partials, variant=self.wgrad_variant)
-        ops.reduce_partials(self.partials, self.grad)
-        scale = 1.0
-        if self.world > 1:
-            torch.distributed.all_reduce(self.grad, group=self.pg)          # the ONE gradient collective
-            scale = 1.0 / self.world
-        ops.clip_rmsprop(self.flat, self.grad, self.sq_avg, L.P, scale, hp["max_grad_norm"], hp["lr"],
-                         0.99, 1e-5, self.grad_norm)
+        ops.reduce_partials(self.partials, gbuf)
+        scale = 1.0 / self.world
+        if self.chan is not None:
+            # ONE kernel: peer handshake + one-shot all-reduce over NVLink + global-norm clip + RMSprop (+ the loss sums)
+            self.chan.step(0, self.flat, self.sq_avg, None, None, self.grad, self.scalars, self.grad_norm, scale,
+                           hp["max_grad_norm"], hp["lr"], 0.99, 0.0, 1e-5, 0, ops._stream(self.device))
+        else:
+            if self.world > 1:
+                self.comm.all_reduce(self.grad)                                 # the ONE gradient collective
+            ops.clip_rmsprop(self.flat, self.grad, self.sq_avg, L.P, scale, hp["max_grad_norm"], hp["lr"],
+                             0.99, 1e-5, self.grad_norm)
         self.n_launches += 8 + {0: 0, 1: 2, 2: 1}[self.wgrad_variant] + (1 if _ops.FWD_VARIANT >= 2 else 0)
 
     # -------------------------------------------------------------------- scalars
     def _reduced_scalars(self):
         s = self.scalars
-        if self.world > 1:
+        if self.world > 1 and self.chan is None:      # (the peer step already reduced them)
             s = s.clone()
             mm = torch.stack([-s[4], s[5]])
-            torch.distributed.all_reduce(mm, op=torch.distributed.ReduceOp.MAX, group=self.pg)
+            self.comm.all_reduce(mm, op="max")
             sums = s[:4].clone()
-            torch.distributed.all_reduce(sums, group=self.pg)
+            self.comm.all_reduce(sums)
             s = torch.cat([sums, torch.stack([-mm[0], mm[1]]), s[6:]])
         return s
 
@@ -142,7 +174,10 @@ class OnPolicyEngine:
         """Host copy of the loss scalars of the LAST update (synchronises).  Keys follow
         the reference's `detached_losses` (ppo/learning.py:83-88); `ratio` is reduced to
         (min, max, mean) instead of shipping the (B,T-1,1) tensor to the host."""
-        return self._losses_from(self._reduced_scalars().cpu().tolist(), float(self.grad_norm.item()))
+        out = self._losses_from(self._reduced_scalars().cpu().tolist(), float(self.grad_norm.item()))
+        if self.chan is not None:
+            self.chan.check()
+        return out
 
     # ---------------------------------------------------------- stream-ordered snapshot
     def snapshot_async(self, with_losses=True):
@@ -181,8 +216,8 @@ class VMPOEngine(OnPolicyEngine):
     policy / KL gradients) and the two fp64 dual variables with their own RMSprop state.
     `log_eta`, `log_alpha` live on the device as `self.duals` (fp64)."""
 
-    def __init__(self, net, hyper, ops=None, process_group=None):
-        super().__init__(net, "V-MPO", hyper, ops=ops, process_group=process_group)
+    def __init__(self, net, hyper, ops=None, process_group=None, comm=None):
+        super().__init__(net, "V-MPO", hyper, ops=ops, process_group=process_group, comm=comm)
         dev = self.device
         init = math.log(self.hp["v_mpo_lagrange_multiplier_init"])
         self.duals = torch.full((2,), init, dtype=torch.float64, device=dev)      # log_eta, log_alpha
@@ -197,6 +232,7 @@ class VMPOEngine(OnPolicyEngine):
         self.gae = torch.empty(B, T - 1, device=dev)
         self.gae_all = self.gae if self.world == 1 else torch.empty(B * self.world, T - 1, device=dev)
         self.thr = torch.empty(T - 1, device=dev)
+        self.tie_cut = torch.empty(T - 1, dtype=torch.int32, device=dev)
         self.colstat = torch.empty(2 * (T - 1), device=dev)
         self._vm_shape = (B, T)
 
@@ -216,23 +252,31 @@ class VMPOEngine(OnPolicyEngine):
         from .native import ptr
         ops._chk(batch["act"], batch["rew"], batch["is_fir"], batch["logits"], batch["hx"], batch["cx"])
 
+        gbuf, sbuf = self.chan.begin() if self.chan is not None else (self.grad, self.scalars)
         ops.lstm_fwd(L, self.flat, u, batch["hx"], batch["cx"], self.ws)
         ops.head_fwd(L, self.flat, self.ws["h"], self.head_out)
-        self.scalars.copy_(self._zero8)
+        sbuf.copy_(self._zero8)
         lib.call("b200rl_vmpo_gae", ptr(self.head_out), ptr(batch["rew"]), ptr(batch["is_fir"]), ptr(self.gae),
-                 ptr(self.dhead), ptr(self.scalars), B, T, A, hp["gamma"], hp["lmbda"], hp["value_loss_coef"], N, st)
+                 ptr(self.dhead), ptr(sbuf), B, T, A, hp["gamma"], hp["lmbda"], hp["value_loss_coef"], N, st)
         if self.world > 1:
-            torch.distributed.all_gather_into_tensor(self.gae_all, self.gae, group=self.pg)
-        lib.call("b200rl_vmpo_select", ptr(self.gae_all), Bg, T - 1, k, ptr(self.duals), ptr(self.thr), ptr(self.colstat), st)
+            self.comm.all_gather(self.gae_all, self.gae)       # the extra V-MPO exchange: top-k is over the WHOLE batch
+        lib.call("b200rl_vmpo_select", ptr(self.gae_all), Bg, T - 1, k, ptr(self.duals), ptr(self.thr), ptr(self.colstat),
+                 ptr(self.tie_cut), st)
         lib.call("b200rl_vmpo_grad", ptr(self.head_out), ptr(batch["act"]), ptr(batch["logits"]), ptr(self.gae), ptr(self.thr),
-                 ptr(self.colstat), ptr(self.duals), ptr(self.dhead), ptr(self.scalars), B, T, A, hp["policy_loss_coef"], N, st)
+                 ptr(self.colstat), ptr(self.tie_cut), ptr(self.duals), ptr(self.dhead), ptr(sbuf), B, T, A, self.rank * B,
+                 hp["policy_loss_coef"], N, st)
         ops.lstm_bwd(L, self.flat, self.dhead, self.ws, batch["cx"])
         ops.lstm_wgrad(L, self.flat, self.ws, batch["hx"], u, self.dhead, self.partials, variant=self.wgrad_variant)
-        ops.reduce_partials(self.partials, self.grad)
-        if self.world > 1:                      # kernels already normalise by the GLOBAL N: plain sum, no 1/world
-            torch.distributed.all_reduce(self.grad, group=self.pg)
-            torch.distributed.all_reduce(self.scalars[:4], group=self.pg)
-        ops.clip_rmsprop(self.flat, self.grad, self.sq_avg, L.P, 1.0, hp["max_grad_norm"], hp["lr"], 0.99, 1e-5, self.grad_norm)
+        ops.reduce_partials(self.partials, gbuf)
+        # (the kernels already normalise by the GLOBAL N: plain sum over ranks, no 1/world)
+        if self.chan is not None:
+            self.chan.step(0, self.flat, self.sq_avg, None, None, self.grad, self.scalars, self.grad_norm, 1.0,
+                           hp["max_grad_norm"], hp["lr"], 0.99, 0.0, 1e-5, 0, st)
+        else:
+            if self.world > 1:
+                self.comm.all_reduce(self.grad)
+                self.comm.all_reduce(self.scalars[:4])
+            ops.clip_rmsprop(self.flat, self.grad, self.sq_avg, L.P, 1.0, hp["max_grad_norm"], hp["lr"], 0.99, 1e-5, self.grad_norm)
         lib.call("b200rl_vmpo_dual_step", ptr(self.duals), ptr(self.dual_sq), ptr(self.scalars), ptr(self.losses_dev),
                  hp["coef_eta"], float(coef_alpha), hp["lr"], 0.99, 1e-5, N, float(k * (T - 1)),
                  hp["policy_loss_coef"], hp["value_loss_coef"], st)
@@ -241,6 +285,8 @@ class VMPOEngine(OnPolicyEngine):
     def losses(self):
         v = self.losses_dev.cpu().tolist()
         d = self.duals.cpu().tolist()
+        if self.chan is not None:
+            self.chan.check()
         return {"policy-loss": v[0], "value-loss": v[1], "loss-temperature": v[2], "loss-alpha": v[3], "loss": v[4],
                 "kl-mean": v[5], "log_eta": d[0], "log_alpha": d[1], "selected": float(self.scalars[3].item()),
                 "grad-norm": float(self.grad_norm.item())}
@@ -255,15 +301,10 @@ class SACEngine:
     SURVEY.md A.6-8), so the "target" forward is the critic forward and `soft_update` is
     theta <- (1-tau) theta + tau theta; `separate_target=True` keeps a real copy instead."""
 
-    def __init__(self, model, hyper, continuous, ops=None, separate_target=False, tau=0.005, process_group=None):
+    def __init__(self, model, hyper, continuous, ops=None, separate_target=False, tau=0.005, process_group=None, comm=None):
         self.ops = ops or _ops.default()
         self.hp = dict(hyper)
         self.cont = continuous
-        # data parallel: the replay batch is sharded over ranks (equal shards); every loss is a mean over the batch, so the
-        # actor / twin-critic gradients and the temperature statistics are summed over ranks and scaled by 1/world
-        # (three small all-reduces per update: actor grad, the alpha statistics, critic grad)
-        self.pg = process_group
-        self.world = 1 if process_group is None else torch.distributed.get_world_size(process_group)
         self.actor, self.twin = model.actor, model.critic
         self.q = [self.twin.q1, self.twin.q2]
         self.fa = self.actor.flat_parameters()
@@ -271,6 +312,16 @@ class SACEngine:
         self.La, self.Lq = self.actor._layout, self.q[0]._layout
         dev = self.fa.device
         self.device = dev
+        # data parallel: the replay batch is sharded over ranks (equal shards); every loss is a mean over the batch, so the
+        # actor / twin-critic gradients and the temperature statistics are summed over ranks and scaled by 1/world.  Two
+        # DEPENDENT exchanges per update (the critic target uses the actor AFTER its step, sac_continuous/learning.py:50-71),
+        # each one fused peer kernel (exchange + clip + Adam; the loss / temperature sums ride along)
+        self.comm = _make_comm(process_group, comm, dev, self.ops)
+        self.world = 1 if self.comm is None else self.comm.world
+        self.chan_a = _channel(self.comm, self.La.P, dev, self.ops)
+        self.chan_q = _channel(self.comm, 2 * self.Lq.P, dev, self.ops)
+        self.sc_a = torch.zeros(8, dtype=torch.float64, device=dev)      # reduced sums of the actor phase / the critic phase
+        self.sc_q = torch.zeros(8, dtype=torch.float64, device=dev)
         z = lambda t: torch.zeros_like(t)
         self.ga, self.ma, self.va = z(self.fa), z(self.fa), z(self.fa)
         self.gq, self.mq, self.vq = z(self.fq), z(self.fq), z(self.fq)
@@ -347,7 +398,12 @@ class SACEngine:
         N = float(B * (T - 1))
         self.step += 1
         lr, mg = hp["lr"], hp["max_grad_norm"]
-        self.scalars.zero_()
+        # gradient / loss-sum buffers of this update: the peer channels' (read by the other ranks over NVLink) or local ones
+        ga, sA = self.chan_a.begin() if self.chan_a is not None else (self.ga, self.scalars)
+        gq, sQ = self.chan_q.begin() if self.chan_q is not None else (self.gq, self.scalars)
+        sA.zero_()
+        if sQ is not sA:
+            sQ.zero_()
 
         if not self.cont:
             A = La.NH
@@ -355,10 +411,9 @@ class SACEngine:
             for i in range(2):
                 self._net_fwd(Lq, self.fq, i * Pq, uo, hx, cx, self.wsq[i], self.Q[i])
             lib.call("b200rl_sac_actor_head", ptr(self.hoa), ptr(self.Q[0]), ptr(self.Q[1]), ptr(self.alpha_state),
-                     ptr(self.dhoa), ptr(self.scalars), B, T, A, st)
-            self._net_bwd(La, self.fa, 0, uo, hx, cx, self.wsa, self.dhoa, self.pa, self.ga)
-            sc = self._reduce_actor()
-            ops.clip_adam(self.fa, self.ga, self.ma, self.va, La.P, 1.0 / self.world, mg, lr, self.step, norm_out=self.norm_a)
+                     ptr(self.dhoa), ptr(sA), B, T, A, st)
+            self._net_bwd(La, self.fa, 0, uo, hx, cx, self.wsa, self.dhoa, self.pa, ga)
+            sc = self._actor_step(ga, sA, mg, lr, st)
             lib.call("b200rl_sac_alpha_step", ptr(self.alpha_state), ptr(sc), ptr(self.alpha_out), N * self.world, float(A), lr, self.step, st)
             self._net_fwd(La, self.fa, 0, uo, hx, cx, self.wsa, self.hoa)            # updated actor
             if self.separate_target:
@@ -366,9 +421,9 @@ class SACEngine:
                     self._net_fwd(Lq, self.ftq, i * Pq, uo, hx, cx, self.wsa, self.TQ[i])
             lib.call("b200rl_sac_critic_head", ptr(self.hoa), ptr(self.Q[0]), ptr(self.Q[1]), ptr(self.TQ[0]), ptr(self.TQ[1]),
                      ptr(act), ptr(batch["rew"]), ptr(batch["is_fir"]), ptr(self.alpha_state), ptr(self.dQ[0]), ptr(self.dQ[1]),
-                     ptr(self.td), ptr(self.scalars), B, T, A, hp["gamma"], st)
+                     ptr(self.td), ptr(sQ), B, T, A, hp["gamma"], st)
             for i in range(2):
-                self._net_bwd(Lq, self.fq, i * Pq, uo, hx, cx, self.wsq[i], self.dQ[i], self.pq[i], self.gq[i * Pq:(i + 1) * Pq])
+                self._net_bwd(Lq, self.fq, i * Pq, uo, hx, cx, self.wsq[i], self.dQ[i], self.pq[i], gq[i * Pq:(i + 1) * Pq])
             pol_den = N
         else:
             A = Ad
@@ -378,14 +433,13 @@ class SACEngine:
             u1 = torch.cat([uo, self.a_pol], -1)
             for i in range(2):
                 self._net_fwd(Lq, self.fq, i * Pq, u1, hx, cx, self.wsq[i], self.Q[i])
-            lib.call("b200rl_sac_cont_minq_grad", ptr(self.Q[0]), ptr(self.Q[1]), ptr(self.dQ[0]), ptr(self.dQ[1]), ptr(self.scalars), B, T, A, st)
+            lib.call("b200rl_sac_cont_minq_grad", ptr(self.Q[0]), ptr(self.Q[1]), ptr(self.dQ[0]), ptr(self.dQ[1]), ptr(sA), B, T, A, st)
             for i in range(2):                                                          # dQ/da: critic backward to its input only
                 self._net_bwd(Lq, self.fq, i * Pq, u1, hx, cx, self.wsq[i], self.dQ[i], self.scratch, None, du=self.du[i])
             lib.call("b200rl_sac_cont_actor_grad", ptr(self.hoa), ptr(eps1), ptr(self.a_pol), ptr(self.logp), ptr(self.du[0]), ptr(self.du[1]),
-                     ptr(self.alpha_state), ptr(self.dhoa), ptr(self.scalars), B, T, A, f, st)
-            self._net_bwd(La, self.fa, 0, uo, hx, cx, self.wsa, self.dhoa, self.pa, self.ga)
-            sc = self._reduce_actor()
-            ops.clip_adam(self.fa, self.ga, self.ma, self.va, La.P, 1.0 / self.world, mg, lr, self.step, norm_out=self.norm_a)
+                     ptr(self.alpha_state), ptr(self.dhoa), ptr(sA), B, T, A, f, st)
+            self._net_bwd(La, self.fa, 0, uo, hx, cx, self.wsa, self.dhoa, self.pa, ga)
+            sc = self._actor_step(ga, sA, mg, lr, st)
             lib.call("b200rl_sac_alpha_step", ptr(self.alpha_state), ptr(sc), ptr(self.alpha_out), N * A * self.world, float(A), lr, self.step, st)
             self._net_fwd(La, self.fa, 0, uo, hx, cx, self.wsa, self.hoa)            # updated actor, fresh noise
             lib.call("b200rl_sac_cont_sample", ptr(self.hoa), ptr(eps2), ptr(self.a_pol), ptr(self.logp), B, T, A, st)
@@ -397,33 +451,49 @@ class SACEngine:
                 self._net_fwd(Lq, self.fq, i * Pq, u3, hx, cx, self.wsq[i], self.Q[i])
             lib.call("b200rl_sac_cont_critic_head", ptr(self.TQ[0]), ptr(self.TQ[1]), ptr(self.logp), ptr(self.Q[0]), ptr(self.Q[1]),
                      ptr(batch["rew"]), ptr(batch["is_fir"]), ptr(self.alpha_state), ptr(self.dQ[0]), ptr(self.dQ[1]), ptr(self.td),
-                     ptr(self.scalars), B, T, A, hp["gamma"], st)
+                     ptr(sQ), B, T, A, hp["gamma"], st)
             for i in range(2):
-                self._net_bwd(Lq, self.fq, i * Pq, u3, hx, cx, self.wsq[i], self.dQ[i], self.pq[i], self.gq[i * Pq:(i + 1) * Pq])
+                self._net_bwd(Lq, self.fq, i * Pq, u3, hx, cx, self.wsq[i], self.dQ[i], self.pq[i], gq[i * Pq:(i + 1) * Pq])
             pol_den = N * A
-        if self.world > 1:
-            torch.distributed.all_reduce(self.gq, group=self.pg)
-        ops.clip_adam(self.fq, self.gq, self.mq, self.vq, 2 * Pq, 1.0 / self.world, mg, lr, self.step, norm_out=self.norm_q, mask=self.qmask)
+        # twin-critic step: exchange #2 + joint clip + Adam
+        if self.chan_q is not None:
+            self.chan_q.step(1, self.fq, self.mq, self.vq, self.qmask, self.gq, self.sc_q, self.norm_q, 1.0 / self.world, mg, lr,
+                             0.9, 0.999, 1e-8, self.step, st)
+        else:
+            if self.world > 1:
+                self.comm.all_reduce(self.gq)
+            ops.clip_adam(self.fq, self.gq, self.mq, self.vq, 2 * Pq, 1.0 / self.world, mg, lr, self.step, norm_out=self.norm_q, mask=self.qmask)
         ops.soft_update_flat(self.fq, self.ftq, self.tau)
         self._pol_den, self._N = pol_den * self.world, N * self.world
         self.n_launches += 1
 
-    def _reduce_actor(self):
-        """Sum the actor gradient and the running loss / temperature statistics over ranks; returns the statistics the
-        temperature step reads (a reduced copy: `self.scalars` keeps accumulating local sums for the critic loss)."""
-        if self.world == 1:
-            return self.scalars
-        torch.distributed.all_reduce(self.ga, group=self.pg)
-        sc = self.scalars.clone()
-        torch.distributed.all_reduce(sc, group=self.pg)
+    def _actor_step(self, ga, sA, mg, lr, st):
+        """Exchange #1 + clip + Adam on the actor; returns the rank-summed loss / temperature statistics of the actor phase
+        (what the temperature step reads)."""
+        if self.chan_a is not None:
+            self.chan_a.step(1, self.fa, self.ma, self.va, None, self.ga, self.sc_a, self.norm_a, 1.0 / self.world, mg, lr,
+                             0.9, 0.999, 1e-8, self.step, st)
+            return self.sc_a
+        sc = sA
+        if self.world > 1:
+            self.comm.all_reduce(self.ga)
+            sc = sA.clone()                      # (`self.scalars` keeps accumulating local sums for the critic loss)
+            self.comm.all_reduce(sc)
+        self.ops.clip_adam(self.fa, self.ga, self.ma, self.va, self.La.P, 1.0 / self.world, mg, lr, self.step, norm_out=self.norm_a)
         return sc
 
     def losses(self):
-        sc = self.scalars
-        if self.world > 1:
-            sc = sc.clone()
-            torch.distributed.all_reduce(sc, group=self.pg)
-        s = sc.cpu().tolist()
+        if self.chan_a is not None:
+            sa, sq = self.sc_a.cpu().tolist(), self.sc_q.cpu().tolist()
+            s = [sa[0], sq[1]]
+            self.chan_a.check()
+            self.chan_q.check()
+        else:
+            sc = self.scalars
+            if self.world > 1:
+                sc = sc.clone()
+                self.comm.all_reduce(sc)
+            s = sc.cpu().tolist()
         ao = self.alpha_out.cpu().tolist()
         pol, val = s[0] / self._pol_den, s[1] / self._N
         return {"policy-loss": pol, "value-loss": val, "loss_alpha": ao[0], "alpha": ao[1],

@@ -33,11 +33,18 @@ SIGNATURES = {
     "b200rl_ppo_head": [_P] * 13 + [_I, _I, _I, _I] + [_F] * 6 + [_P],
     "b200rl_impala_head": [_P] * 13 + [_I, _I, _I] + [_F] * 6 + [_P],
     "b200rl_vmpo_gae": [_P] * 6 + [_I, _I, _I, _F, _F, _F, C.c_double, _P],
-    "b200rl_vmpo_select": [_P, _I, _I, _I, _P, _P, _P, _P],
-    "b200rl_vmpo_grad": [_P] * 9 + [_I, _I, _I, _F, C.c_double, _P],
+    "b200rl_vmpo_select": [_P, _I, _I, _I, _P, _P, _P, _P, _P],
+    "b200rl_vmpo_grad": [_P] * 10 + [_I, _I, _I, _I, _F, C.c_double, _P],
     "b200rl_vmpo_dual_step": [_P] * 4 + [C.c_double] * 9 + [_P],
     "b200rl_clip_rmsprop": [_P, _P, _P, _L] + [_F] * 5 + [_P, _P],
     "b200rl_clip_adam": [_P, _P, _P, _P, _L] + [_F] * 6 + [_I, _P, _P, _P],
+    "b200rl_peer_alloc": [_L, _P, _P],
+    "b200rl_peer_open": [_P, _P],
+    "b200rl_peer_close": [_P],
+    "b200rl_peer_free": [_P],
+    "b200rl_peer_set_timeout_ms": [_L],
+    "b200rl_peer_step": [_I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, C.c_uint, _I, C.c_uint]
+                        + [_F] * 6 + [_I, _P],
     "b200rl_sac_actor_head": [_P] * 6 + [_I, _I, _I, _P],
     "b200rl_sac_critic_head": [_P] * 13 + [_I, _I, _I, _F, _P],
     "b200rl_sac_cont_sample": [_P] * 4 + [_I, _I, _I, _P],

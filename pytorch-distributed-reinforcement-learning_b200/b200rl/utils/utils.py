@@ -101,7 +101,10 @@ class HostStager:
 
     def __init__(self, device):
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:      # reference-style 'cuda': tensors report cuda:<index>
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.pinned = [{}, {}]
+        self._h2d_done = [None, None]    # per set: event after the last async H2D that READ this set's pinned staging buffers
         self.devbuf = [{}, {}]
         self._released = [None, None]    # compute-stream events: set k may be overwritten once this has happened
         self.flip = 0
@@ -120,6 +123,14 @@ class HostStager:
         buf.copy_(t)
         return buf
 
+    def _wait_staging_free(self, slot):
+        """The host is about to overwrite set `slot`'s pinned staging buffers: the async H2D that last read them must have
+        finished (`_released` only orders the DEVICE buffers; without this a slow copy could ship a half-overwritten batch)."""
+        ev = self._h2d_done[slot]
+        if ev is not None:
+            ev.synchronize()
+            self._h2d_done[slot] = None
+
     def _dev(self, slot, name, shape):
         buf = self.devbuf[slot].get(name)
         if buf is None or buf.shape != shape:
@@ -129,6 +140,8 @@ class HostStager:
 
     def _ship(self, batch_args, slot):
         out, nbytes = [], 0
+        self._wait_staging_free(slot)
+        staged = False
         for name, t in zip(BATCH_FIELDS, batch_args):
             if t is None or name in self.skip:
                 out.append(None)
@@ -138,11 +151,18 @@ class HostStager:
             if t.device == self.device:
                 out.append(t.contiguous())
                 continue
-            src = t if (t.is_pinned() and t.is_contiguous()) else self._pin(slot, name, t)
+            if t.is_pinned() and t.is_contiguous():
+                src = t
+            else:
+                src, staged = self._pin(slot, name, t), True
             dst = self._dev(slot, name, src.shape)
             dst.copy_(src, non_blocking=True)
             out.append(dst)
             nbytes += src.numel() * 4
+        if staged and self.device.type == "cuda":
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self._h2d_done[slot] = ev
         return tuple(out), nbytes
 
     def _release_current(self):

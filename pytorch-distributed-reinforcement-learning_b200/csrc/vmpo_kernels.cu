@@ -81,10 +81,12 @@ __device__ __forceinline__ unsigned umax_(unsigned a, unsigned b) { return a > b
 __device__ __forceinline__ unsigned f2key(float f) { unsigned b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
 __device__ __forceinline__ float key2f(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
 
-// one CTA per timestep column t: thr[t] = k-th largest of gae[:, t]; colstat[t] = max, colstat[n+t] = sum exp((g-max)*inv_eta) over selected
+// one CTA per timestep column t: thr[t] = k-th largest of gae[:, t]; colstat[t] = max, colstat[n+t] = sum exp((g-max)*inv_eta) over selected.
+// Exactly k rows are selected per column, as torch.topk does: rows above the threshold, plus -- when several rows TIE at the
+// threshold value -- the lowest-indexed of them up to tie_cut[t] (INT_MAX when every tied row is taken, the usual case).
 __global__ void __launch_bounds__(256)
 vmpo_select_kernel(const float* __restrict__ gae, int Bg, int n, int k, const double* __restrict__ duals,
-                   float* __restrict__ thr, float* __restrict__ colstat) {
+                   float* __restrict__ thr, float* __restrict__ colstat, int* __restrict__ tie_cut) {
     B200RL_DYN_SMEM(unsigned, keys);
     __shared__ int hist[256];
     __shared__ unsigned s_prefix;
@@ -115,6 +117,23 @@ vmpo_select_kernel(const float* __restrict__ gae, int Bg, int n, int k, const do
         __syncthreads();
     }
     const unsigned tkey = s_prefix;
+    // ties at the threshold: s_k of them belong to the top k
+    __shared__ int s_ties, s_cut;
+    if (tid == 0) { s_ties = 0; s_cut = 0x7fffffff; }
+    __syncthreads();
+    {
+        int mine = 0;
+        for (int b = tid; b < Bg; b += 256) mine += keys[b] == tkey;
+        if (mine) atomicAdd(&s_ties, mine);
+    }
+    __syncthreads();
+    if (tid == 0 && s_ties > s_k) {                       // rare (duplicate / saturated advantages): serial scan in index order
+        int left = s_k, b = 0;
+        for (; b < Bg && left > 0; ++b) left -= keys[b] == tkey;
+        s_cut = b - 1;
+    }
+    __syncthreads();
+    const int cut = s_cut;
     // column max
     for (int o = 16; o > 0; o >>= 1) kmax = umax_(kmax, __shfl_xor_sync(kFull, kmax, o));
     __shared__ unsigned wmax[8];
@@ -126,7 +145,7 @@ vmpo_select_kernel(const float* __restrict__ gae, int Bg, int n, int k, const do
     double s = 0;
     for (int b = tid; b < Bg; b += 256) {
         const unsigned key = keys[b];
-        if (key >= tkey) s += (double)expf((key2f(key) - colmax) * inv);
+        if (key > tkey || (key == tkey && b <= cut)) s += (double)expf((key2f(key) - colmax) * inv);
     }
     s = warp_sum(s);
     if ((tid & 31) == 0) red[tid >> 5] = s;
@@ -134,14 +153,14 @@ vmpo_select_kernel(const float* __restrict__ gae, int Bg, int n, int k, const do
     if (tid == 0) {
         double a = 0;
         for (int w = 0; w < 8; ++w) a += red[w];
-        thr[t] = key2f(tkey); colstat[t] = colmax; colstat[n + t] = (float)a;
+        thr[t] = key2f(tkey); colstat[t] = colmax; colstat[n + t] = (float)a; tie_cut[t] = cut;
     }
 }
 
 struct VmpoGradArgs {
     const float* head_out; const float* act; const float* blogits; const float* gae; const float* thr; const float* colstat;
-    const double* duals; float* dhead; double* scalars;
-    int B, T, A, NH;
+    const double* duals; float* dhead; double* scalars; const int* tie_cut;
+    int B, T, A, NH, row_offset;
     float c_pol, invN;
 };
 
@@ -222,7 +241,8 @@ vmpo_grad_kernel(VmpoGradArgs a) {
             s_kl += (double)kl;
             const float g = __ldg(a.gae + on + t);
             float psi = 0.f;
-            if (g >= __ldg(a.thr + t)) {
+            const float th = __ldg(a.thr + t);
+            if (g > th || (g == th && a.row_offset + row <= __ldg(a.tie_cut + t))) {
                 psi = expf(g * inv - mf) * invZ;
                 s_pol += (double)(-psi * d.logp);
                 s_cnt += 1.0;
@@ -291,7 +311,7 @@ extern "C" int b200rl_vmpo_gae(const float* head_out, const float* rew, const fl
 }
 
 extern "C" int b200rl_vmpo_select(const float* gae_all, int Bg, int n, int k, const double* duals,
-                                  float* thr, float* colstat, void* stream) {
+                                  float* thr, float* colstat, int* tie_cut, void* stream) {
     B200RL_REQUIRE(Bg >= 1 && n >= 1 && k >= 1 && k <= Bg, "vmpo_select: bad shape Bg=%d n=%d k=%d", Bg, n, k);
     const size_t smem = sizeof(unsigned) * (size_t)Bg;
     B200RL_REQUIRE(smem <= 200 * 1024, "vmpo_select: batch of %d sequences does not fit the shared-memory key buffer", Bg);
@@ -299,16 +319,16 @@ extern "C" int b200rl_vmpo_select(const float* gae_all, int Bg, int n, int k, co
     cudaError_t e = cudaFuncSetAttribute(vmpo_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error("vmpo_select: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
 #endif
-    B200RL_LAUNCH(vmpo_select_kernel, n, 256, smem, stream, gae_all, Bg, n, k, duals, thr, colstat);
+    B200RL_LAUNCH(vmpo_select_kernel, n, 256, smem, stream, gae_all, Bg, n, k, duals, thr, colstat, tie_cut);
     return check_launch("vmpo_select");
 }
 
 extern "C" int b200rl_vmpo_grad(const float* head_out, const float* act, const float* behav_logits, const float* gae,
-                                const float* thr, const float* colstat, const double* duals,
-                                float* dhead, double* scalars, int B, int T, int A,
+                                const float* thr, const float* colstat, const int* tie_cut, const double* duals,
+                                float* dhead, double* scalars, int B, int T, int A, int row_offset,
                                 float c_policy, double N_global, void* stream) {
     B200RL_REQUIRE(B >= 1 && T >= 2 && A >= 1 && A <= MAXA, "vmpo_grad: bad shape B=%d T=%d A=%d", B, T, A);
-    VmpoGradArgs a{head_out, act, behav_logits, gae, thr, colstat, duals, dhead, scalars, B, T, A, 1 + A, c_policy, (float)(1.0 / N_global)};
+    VmpoGradArgs a{head_out, act, behav_logits, gae, thr, colstat, duals, dhead, scalars, tie_cut, B, T, A, 1 + A, row_offset, c_policy, (float)(1.0 / N_global)};
     B200RL_LAUNCH(vmpo_grad_kernel, vm_grid(B), kHeadThreads, 0, stream, a);
     return check_launch("vmpo_grad");
 }

@@ -110,6 +110,7 @@ static inline unsigned atomicInc(unsigned* p, unsigned wrap) {
 }
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 static inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
 static inline int __float_as_int(float f) { int v; memcpy(&v, &f, 4); return v; }
