@@ -58,6 +58,17 @@ class HostScalar(float):
         return self
 
 
+async def _next_batch(queue, stop_event, poll=0.05):
+    """`await queue.get()`, but a learner whose feeder has stopped leaves its loop instead of waiting forever (the
+    reference blocks in `queue.get()` until the process is terminated): returns None once `stop_event` is set."""
+    while True:
+        try:
+            return await asyncio.wait_for(queue.get(), timeout=poll)
+        except asyncio.TimeoutError:
+            if stop_event.is_set():
+                return None
+
+
 async def run_learning(parent, timer, queue_name, update, losses, publish_state, checkpoint_obj):
     assert hasattr(parent, queue_name)
     parent.idx = 0
@@ -95,7 +106,7 @@ async def run_learning(parent, timer, queue_name, update, losses, publish_state,
                         # workers would gather all of batch i+1 under model i-1
                         finish(*pending)
                         pending = None
-                    batch_args = await queue.get()
+                    batch_args = await _next_batch(queue, parent.stop_event)
             if batch_args is not None:
                 with timer.timer("learner-forward-time"):
                     dev_batch = parent.to_gpu(*batch_args)

@@ -339,6 +339,7 @@ class SACEngine:
         self.n_launches = 0
         self.wgrad_variant = int(os.environ.get("B200RL_WGRAD_VARIANT", "1"))
         self.debug = None
+        self.noise_fn = None          # SAC-Continuous: callable (B, T, A) -> (eps1, eps2) replacing the two N(0,1) draws (tests)
 
     @property
     def log_alpha(self):
@@ -427,6 +428,8 @@ class SACEngine:
             pol_den = N
         else:
             A = Ad
+            if noise is None and self.noise_fn is not None:
+                noise = self.noise_fn(B, T, A)
             eps1, eps2 = noise if noise is not None else (torch.randn(B, T, A, device=self.device), torch.randn(B, T, A, device=self.device))
             self._net_fwd(La, self.fa, 0, uo, hx, cx, self.wsa, self.hoa)
             lib.call("b200rl_sac_cont_sample", ptr(self.hoa), ptr(eps1), ptr(self.a_pol), ptr(self.logp), B, T, A, st)

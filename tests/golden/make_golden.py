@@ -60,8 +60,11 @@ class StopAfter:
         return self.calls > self.n
 
 
-def base_args(algo, B, T, A, tmp):
+def base_args(algo, B, T, A, tmp, overrides=None):
     a = copy.copy(Params)
+    for k, v in (overrides or {}).items():         # hyper-parameter overrides of a case (stored as hyper/<key> in the fixture)
+        assert hasattr(a, k), k
+        setattr(a, k, v)
     a.algo, a.batch_size, a.seq_len, a.action_space = algo, B, T, A
     a.device = torch.device("cpu")
     a.model_dir = tmp
@@ -89,11 +92,13 @@ def sd_np(sd, prefix):
     return {f"{prefix}/{k}": v.detach().numpy().copy() for k, v in sd.items()}
 
 
-def on_policy_case(name, algo, B, T, f, A, n_steps, continuous=False, seed=0):
+def on_policy_case(name, algo, B, T, f, A, n_steps, continuous=False, seed=0, overrides=None):
     torch.manual_seed(seed)
     cls = ref_models.MlpLSTMSingleContinuous if continuous else ref_models.MlpLSTMSingle
     model = cls(f, A, T, Params.hidden_size)
     out = {"meta": np.array([B, T, f, A, Params.hidden_size, n_steps, int(continuous)])}
+    for k, v in (overrides or {}).items():
+        out[f"hyper/{k}"] = np.array(v, dtype=np.float64)
     out.update(sd_np(model.actor.state_dict(), "sd0"))
     batches = [make_rollouts(B, T, f, A, continuous=continuous, batch_index=i) for i in range(n_steps)]
     for i, b in enumerate(batches):
@@ -115,7 +120,7 @@ def on_policy_case(name, algo, B, T, f, A, n_steps, continuous=False, seed=0):
             out["fwd/kl"] = ref_cl.kldivergence(b0["logits"][:, :-1], logits[:, :-1]).numpy()
 
     with tempfile.TemporaryDirectory() as tmp:
-        args = base_args(algo, B, T, A, tmp)
+        args = base_args(algo, B, T, A, tmp, overrides)
         parent = SimpleNamespace(args=args, model=model, stop_event=StopAfter(n_steps), heartbeat=None,
                                  to_gpu=partial(make_gpu_batch, device=args.device), device=args.device)
         parent._batches = [as_reference_tuple(b, T) for b in batches]
@@ -156,11 +161,13 @@ def on_policy_case(name, algo, B, T, f, A, n_steps, continuous=False, seed=0):
     print(name, "loss", out["out/loss"])
 
 
-def sac_case(name, continuous, B, T, f, A, n_steps, seed=0):
+def sac_case(name, continuous, B, T, f, A, n_steps, seed=0, overrides=None):
     torch.manual_seed(seed)
     cls = ref_models.MlpLSTMSeperateContinuous if continuous else ref_models.MlpLSTMSeperate
     model = cls(f, A, T, Params.hidden_size)
     out = {"meta": np.array([B, T, f, A, Params.hidden_size, n_steps, int(continuous)])}
+    for k, v in (overrides or {}).items():
+        out[f"hyper/{k}"] = np.array(v, dtype=np.float64)
     out.update(sd_np(model.actor.state_dict(), "actor0"))
     out.update(sd_np(model.critic.state_dict(), "critic0"))
     batches = [make_rollouts(B, T, f, A, continuous=continuous, batch_index=i, act_dim=1) for i in range(n_steps)]
@@ -178,7 +185,7 @@ def sac_case(name, continuous, B, T, f, A, n_steps, seed=0):
         return e
 
     with tempfile.TemporaryDirectory() as tmp:
-        args = base_args("SAC-Continuous" if continuous else "SAC", B, T, A, tmp)
+        args = base_args("SAC-Continuous" if continuous else "SAC", B, T, A, tmp, overrides)
         dev = args.device
         parent = SimpleNamespace(args=args, model=model, stop_event=StopAfter(n_steps), heartbeat=None,
                                  to_gpu=partial(make_gpu_batch, device=dev), device=dev)
@@ -245,6 +252,14 @@ def init_case():
     np.savez_compressed(os.path.join(HERE, "init_seed0.npz"), **slim)
     print("init_seed0 ok")
 
+
+if __name__ == "__main__" and "--branches" in sys.argv:
+    # round 2: branches the first fixtures never reached -- an ACTIVE clip_grad_norm_ (coef < 1) under RMSprop and under Adam,
+    # and K_epoch = 2 (two updates per batch)
+    on_policy_case("ppo_clip", "PPO", 8, 6, 4, 2, 3, overrides={"max_grad_norm": 1e-3})
+    on_policy_case("ppo_kepoch2", "PPO", 8, 6, 4, 2, 2, overrides={"K_epoch": 2})
+    sac_case("sac_clip", False, 8, 5, 4, 2, 2, overrides={"max_grad_norm": 1e-2})
+    sys.exit(0)
 
 if __name__ == "__main__":
     on_policy_case("ppo_small", "PPO", 8, 6, 4, 2, 3)
