@@ -3,18 +3,22 @@
 
     python bench.py --gpus N --steps K --warmup W [--impl reference]
 
-A "step" is one learner update (forward over the (B,T) window, GAE, PPO loss, BPTT,
-clip_grad_norm_, RMSprop) over one batch of synthetic rollouts.  Workload = the
-north-star shape: PPO, CartPole-shape rollouts, B=4096 sequences x T=128 steps, obs=4,
-A=2, per GPU (weak scaling: every rank owns its own 4096 sequences; one NCCL all-reduce
-of the 135 KB flat gradient per step).  Rollouts are pre-generated (workers / manager /
-storage are out of the learner path, as the north_star asks) and resident in HBM for
-`value`; the `e2e` leg drives the reference-facing `learning()` coroutine with pinned
-HOST batches, so it pays the H2D of every batch and a D2H read of the losses each step.
+A "step" is one learner update (forward over the (B,T) window, GAE, PPO loss, BPTT, clip_grad_norm_, RMSprop) over one
+batch of synthetic rollouts.  Workload = the north-star shape: PPO, CartPole-shape rollouts, B=4096 sequences x T=128
+steps, obs=4, A=2, per GPU (weak scaling: every rank owns its own 4096 sequences; the gradient exchange is fused with the
+clip + RMSprop step in one kernel over NVLink peer memory -- no library collective on the stream).  Rollouts are
+pre-generated (workers / manager / storage are out of the learner path, as the north_star asks) and resident in HBM for
+`value`; the `e2e` leg drives the reference-facing `learning()` coroutine with HOST batches, so it pays the H2D of every
+batch and a D2H read of the losses each step.
 
-`--impl reference` times the reference's own algorithm on the host CPUs: the torch-CPU
-oracle port (`oracle/`, the restatement pinned to the reference's outputs -- the
-reference itself is pure Python and is not present on the GPU box).
+Extra keys (all measured in the same run): `roofline` (dominant kernel vs the measured HBM peak, plus tensor-pipe
+utilisation of the 3xTF32 GEMMs and the end-to-end compulsory-bytes fraction), `kernels_ms`, `configs` (the other
+BASELINE.json configs at their stated per-GPU shapes), `strong_scaling` (N > 1: global B = 4096 split over the ranks),
+`dp_parity` (N > 1: sharded PPO / V-MPO / SAC-Continuous updates vs the full-batch oracle), `cpu_baseline` +
+`parity_in_run` (N = 1: the reference's CPU learner on this host and the first GPU update checked against it).
+
+`--impl reference` times the reference's own CPU learner on the host cores: the UNMODIFIED reference staged under
+`oracle/_ref` (oracle/build_ref.py; `kind: "reference"`), else the torch-CPU oracle port (`kind: "port"`).
 """
 import argparse
 import asyncio
@@ -24,7 +28,6 @@ import statistics
 import sys
 import threading
 import time
-from types import SimpleNamespace
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "pytorch-distributed-reinforcement-learning_b200")
@@ -41,10 +44,17 @@ UNIT = "env-steps/s"
 NBUF = 4                       # distinct pre-generated batches cycled through
 
 
-def hyper_args(device):
+def config_dict(world):
+    """Identical in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "algo": "PPO", "sequences_per_gpu": B, "seq_len": T, "obs": F, "actions": A,
+            "hidden": H, "global_batch_sequences": B * world, "parallelism": f"dp{world}",
+            "l2": "per-step working set (saved activations 0.8 GB) >> 126 MB L2; 4 input batches cycled"}
+
+
+def hyper_args(device, algo="PPO", b=B, t=T, a_=A):
     from b200rl.utils.utils import load_params
     a = load_params(os.path.join(PKG, "b200rl", "utils", "parameters.json"))
-    a.algo, a.batch_size, a.seq_len, a.action_space = "PPO", B, T, A
+    a.algo, a.batch_size, a.seq_len, a.action_space = algo, b, t, a_
     a.device = device
     a.result_dir = None
     a.model_dir = None
@@ -52,9 +62,8 @@ def hyper_args(device):
 
 
 def usable_cpus():
-    """Host threads we can really use: min(affinity mask, cgroup CPU quota).  The GPU boxes
-    expose 128 logical CPUs under a 16-CPU cgroup quota; 128 torch threads there run ~10x
-    slower than 16."""
+    """Host threads we can really use: min(affinity mask, cgroup CPU quota).  The GPU boxes expose 128 logical CPUs under
+    a 16-CPU cgroup quota; 128 torch threads there run ~10x slower than 16."""
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     try:
         q, per = open("/sys/fs/cgroup/cpu.max").read().split()
@@ -120,62 +129,104 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-# ------------------------------------------------------------------ reference arm
-def reference_arm(steps, warmup, rank, world):
-    """The reference's CPU learner (oracle port, all host threads) on the same workload.
-    Each step is a bounded sample: a PPO update on `rows` of the 4096 sequences (T=128)."""
-    if rank != 0:
-        return
+# ------------------------------------------------------------------ CPU legs (the only places that execute oracle/)
+def _ref_available():
+    from oracle import ref_driver
+    return ref_driver.available()
+
+
+def cpu_learner(rows):
+    """(kind, run(batches) -> (seconds per update list, losses list, flat params))."""
+    from b200rl.synth import make_rollouts, as_reference_tuple
+    if _ref_available():
+        from oracle import ref_driver
+        ref = ref_driver.ReferencePPO(F, A, T, rows)
+
+        def run(idx):
+            batches = [as_reference_tuple({k: v[:rows].contiguous() for k, v in make_rollouts(B, T, F, A, batch_index=i).items()}, T)
+                       for i in idx]
+            times, logs, _ = ref.run(batches)
+            return times, [l[0] for l in logs], ref.flat_params()
+        return "reference", run
     import oracle
     from oracle import models as OM
-    from b200rl.synth import make_rollouts
-    torch.set_num_threads(usable_cpus())
-    budget_steps = 2.5e7                                    # 2-3 min at the ~1.2e5 env-steps/s the 16-thread GPU-box host sustains
+    torch.manual_seed(0)
+    learner = oracle.OracleLearner("PPO", OM.init_params("single", F, A), fused_cell=True)
+
+    def run(idx):
+        times, losses, r = [], [], None
+        for i in idx:
+            b = {k: v[:rows].contiguous() for k, v in make_rollouts(B, T, F, A, batch_index=i).items()}
+            t0 = time.perf_counter()
+            r = learner.update(b)
+            times.append(time.perf_counter() - t0)
+            losses.append(float(r["loss"]))
+        return times, losses, r["params"]
+    return "port", run
+
+
+def reference_arm(steps, warmup, rank, world):
+    """The reference's CPU learner (all usable host threads) on the same workload.  Each step is one `learning()` iteration
+    on `rows` of the 4096 sequences (T=128): all of them when the run fits a few minutes, else a bounded sample."""
+    if rank != 0:
+        return
+    nthreads = usable_cpus()
+    torch.set_num_threads(nthreads)
+    budget_steps = 5.0e7                                    # ~4-5 min at the ~1.7e5 env-steps/s a 16-thread host sustains
     rows = int(max(64, min(B, budget_steps / max(1, steps + warmup) / T)))
     rows = 1 << (rows.bit_length() - 1)
-    torch.manual_seed(0)
-    params = OM.init_params("single", F, A)
-    learner = oracle.OracleLearner("PPO", params, fused_cell=True)
-    batches = [{k: v[:rows].contiguous() for k, v in make_rollouts(B, T, F, A, batch_index=i).items()} for i in range(2)]
-    for i in range(warmup):
-        learner.update(batches[i % 2])
-    t0 = time.perf_counter()
-    for i in range(steps):
-        learner.update(batches[i % 2])
-    dt = time.perf_counter() - t0
+    kind, run = cpu_learner(rows)
+    run([i % 2 for i in range(warmup)])
+    times, _, _ = run([i % 2 for i in range(steps)])
+    dt = sum(times)
     val = rows * T * steps / dt
-    sample = f"PPO update on {rows} of the {B} sequences (T={T}) per step, {steps} steps"
+    what = "the UNMODIFIED reference's learning() from oracle/_ref" if kind == "reference" else "oracle port of the reference's learning()"
+    sample = f"{what}: PPO update on {rows} of the {B} sequences (T={T}) per step, {steps} steps, {nthreads} threads"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": steps,
         "warmup": warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "algo": "PPO", "sequences_per_step": rows, "seq_len": T},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": config_dict(world),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthreads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def cpu_baseline():
-    """Oracle port timed on this host (bounded sample: 1 warm-up + 3 full-size updates)."""
-    import oracle
-    from oracle import models as OM
+def cpu_baseline_and_parity(dev):
+    """Reference CPU learner timed on this host (bounded sample: 1 warm-up + up to 3 full-size updates), and the first GPU
+    update checked against its first update on the same batch and initial weights."""
+    from b200rl.engine import OnPolicyEngine
+    from b200rl.networks.models import MlpLSTMSingle
     from b200rl.synth import make_rollouts
+    import oracle
     nthreads = usable_cpus()
     old = torch.get_num_threads()
     torch.set_num_threads(nthreads)
-    torch.manual_seed(0)
-    learner = oracle.OracleLearner("PPO", OM.init_params("single", F, A), fused_cell=True)
-    batch = make_rollouts(B, T, F, A)
+    kind, run = cpu_learner(B)
     t0 = time.perf_counter()
-    learner.update(batch)
-    n = 3 if time.perf_counter() - t0 < 10 else 1
-    t0 = time.perf_counter()
-    for _ in range(n):
-        learner.update(batch)
-    dt = time.perf_counter() - t0
+    times, losses, params1 = run([0])                       # first update, batch 0: the parity reference (and the warm-up)
+    params1 = params1.clone()
+    n = 3 if time.perf_counter() - t0 < 12 else 1
+    times, _, _ = run([1 + i % 2 for i in range(n)])
+    dt = sum(times)
     torch.set_num_threads(old)
-    return {"value": B * T * n / dt, "unit": UNIT, "cores": nthreads, "kind": "port",
-            "sample": f"{n} full PPO updates at B={B}, T={T} after 1 warm-up ({dt:.1f} s of CPU work)"}
+    base = {"value": B * T * n / dt, "unit": UNIT, "cores": nthreads, "kind": kind,
+            "sample": f"{n} full PPO updates at B={B}, T={T} after 1 warm-up ({dt:.1f} s of CPU work), "
+                      + ("UNMODIFIED reference learning() from oracle/_ref" if kind == "reference" else "oracle port")}
+    # the same first update on the GPU, fresh weights (same seed -> bit-identical initial state dict, tests/test_oracle_golden.py)
+    torch.manual_seed(0)
+    model = MlpLSTMSingle(F, A, T, H).to(dev)
+    eng = OnPolicyEngine(model.actor, "PPO", oracle.DEFAULT_HYPER)
+    eng.update({k: v.to(dev) for k, v in make_rollouts(B, T, F, A, batch_index=0).items()})
+    L = eng.losses()
+    got = torch.cat([v.reshape(-1) for v in model.actor.views_of(eng.flat).values()]).cpu()
+    loss_rel = abs(L["loss"] - losses[0]) / max(abs(losses[0]), 1e-12)
+    perr = (got - params1).abs()
+    tol = 1e-6 + 1e-4 * params1.abs()
+    parity = {"against": kind, "what": "first PPO update at B=4096,T=128: total loss and parameters after the RMSprop step",
+              "loss_gpu": L["loss"], "loss_cpu": losses[0], "loss_rel_err": loss_rel,
+              "params_max_abs_err": float(perr.max()), "params_violations": int((perr > tol).sum()), "rtol": 1e-4,
+              "pass": bool(loss_rel < 1e-4 and int((perr > tol).sum()) == 0)}
+    return base, parity
 
 
 # ----------------------------------------------------------------------- GPU arm
@@ -217,6 +268,137 @@ def load_traffic(kernel):
     return None
 
 
+class Timed:
+    """K steps between CUDA events on the compute stream, barrier + synchronize on both sides, max over ranks."""
+
+    def __init__(self, dev, world, dist):
+        self.dev, self.world, self.dist = dev, world, dist
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize(self.dev)
+
+    def run(self, fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        self.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        return float(ms.item())
+
+
+def dp_parity(dev, rank, world, pg):
+    """Sharded updates over the real communicator (NCCL group + NVLink peer kernels) vs the full-batch oracle, small shapes:
+    PPO (one fused exchange), V-MPO (all-gather of the advantages + global top-k), SAC-Continuous (two dependent exchanges)."""
+    import oracle
+    from collections import OrderedDict
+    from b200rl.engine import OnPolicyEngine, VMPOEngine, SACEngine
+    from b200rl.networks import models as M
+    from b200rl.synth import make_rollouts
+    out = {}
+    Bs, Ts = 16 * world, 16
+    sh = Bs // world
+    cut = lambda t: t[rank * sh:(rank + 1) * sh].contiguous().to(dev)
+    for algo in ("PPO", "V-MPO"):
+        torch.manual_seed(0)
+        model = M.MlpLSTMSingle(4, 2, Ts, 64)
+        sd = OrderedDict((k, v.clone()) for k, v in model.actor.state_dict().items())
+        model = model.to(dev)
+        full = make_rollouts(Bs, Ts, 4, 2)
+        shard = {k: cut(v) for k, v in full.items()}
+        if algo == "V-MPO":
+            eng = VMPOEngine(model.actor, oracle.DEFAULT_HYPER, process_group=pg)
+            for _ in range(2):
+                eng.update(shard, 0.0075)
+        else:
+            eng = OnPolicyEngine(model.actor, algo, oracle.DEFAULT_HYPER, process_group=pg)
+            for _ in range(2):
+                eng.update(shard)
+        L = eng.losses()
+        params = torch.cat([v.reshape(-1) for v in model.actor.views_of(eng.flat).values()]).cpu()
+        if rank == 0:
+            orc = oracle.OracleLearner(algo, sd)
+            for _ in range(2):
+                r = orc.update(full, coef_alpha=torch.tensor(0.0075)) if algo == "V-MPO" else orc.update(full)
+            perr = (params - r["params"]).abs()
+            out[algo] = {"loss_rel_err": abs(L["loss"] - float(r["loss"])) / abs(float(r["loss"])),
+                         "params_max_abs_err": float(perr.max()),
+                         "pass": bool(abs(L["loss"] - float(r["loss"])) <= 1e-4 * abs(float(r["loss"])) + 1e-7
+                                      and bool((perr <= 1e-6 + 1e-4 * r["params"].abs()).all())),
+                         "fused_peer_step": eng.chan is not None and eng.chan.world == world}
+    # SAC-Continuous
+    f, Ad, Tq = 5, 2, 5
+    torch.manual_seed(3)
+    model = M.MlpLSTMSeperateContinuous(f, Ad, Tq, 64, act_dim=Ad)
+    pa = OrderedDict((k, v.clone()) for k, v in model.actor.state_dict().items())
+    pc = OrderedDict((k, v.clone()) for k, v in model.critic.state_dict().items())
+    model = model.to(dev)
+    eng = SACEngine(model, oracle.DEFAULT_HYPER, True, process_group=pg)
+    g = torch.Generator().manual_seed(11)
+    batches = [make_rollouts(Bs, Tq, f, Ad, continuous=True, batch_index=i, act_dim=Ad) for i in range(2)]
+    noise = [[torch.randn(Bs, Tq, Ad, generator=g), torch.randn(Bs, Tq, Ad, generator=g)] for _ in range(2)]
+    for b, nz in zip(batches, noise):
+        eng.update({k: cut(v) for k, v in b.items()}, noise=[cut(e) for e in nz])
+    L = eng.losses()
+    pa_got = torch.cat([v.reshape(-1) for v in model.actor.state_dict().values()]).cpu()
+    pc_got = torch.cat([v.reshape(-1) for v in model.critic.state_dict().values()]).cpu()
+    if rank == 0:
+        orc = oracle.OracleLearner("SAC-Continuous", {"actor": pa, "critic": pc})
+        for b, nz in zip(batches, noise):
+            r = orc.update(b, noise=nz)
+        ea, ec = (pa_got - r["actor_params"]).abs(), (pc_got - r["critic_params"]).abs()
+        out["SAC-Continuous"] = {"loss_rel_err": abs(L["loss"] - float(r["loss"])) / abs(float(r["loss"])),
+                                 "params_max_abs_err": float(max(ea.max(), ec.max())),
+                                 "pass": bool(abs(L["loss"] - float(r["loss"])) <= 1e-4 * abs(float(r["loss"])) + 1e-7
+                                              and bool((ea <= 1e-6 + 1e-4 * r["actor_params"].abs()).all())
+                                              and bool((ec <= 1e-6 + 1e-4 * r["critic_params"].abs()).all())),
+                                 "fused_peer_step": eng.chan_a is not None and eng.chan_a.world == world}
+        out["shape"] = f"{Bs} sequences over {world} ranks, 2 updates each, vs the full-batch oracle (rtol 1e-4)"
+    return out
+
+
+def other_configs(dev, rank, world, pg, timed, steps=10, warmup=3):
+    """The other BASELINE.json configs at their stated per-GPU shapes (cfg4 / cfg5 are 8-GPU configs: 1/8 of the global batch
+    per rank, so at N=8 these ARE the stated configs; at other N the global batch is N/8 of it)."""
+    import oracle
+    from b200rl.engine import OnPolicyEngine, VMPOEngine, SACEngine
+    from b200rl.networks import models as M
+    from b200rl.synth import make_rollouts
+    res = {}
+
+    def run(name, eng, batches, Bn, Tn, upd):
+        ms = timed.run(lambda i: upd(eng, batches[i % len(batches)]), steps, warmup) / steps
+        res[name] = {"ms_per_step": ms, "env_steps_per_sec": world * Bn * Tn / (ms * 1e-3), "sequences_per_gpu": Bn, "seq_len": Tn}
+        del eng
+        torch.cuda.empty_cache()
+
+    torch.manual_seed(0)
+    for name, algo, Bn, Tn, f, Aa, cont in (("cfg2_impala_B4096_T128", "IMPALA", 4096, 128, 4, 2, False),
+                                             ("cfg3_ppo_continuous_B2048_T128", "PPO-Continuous", 2048, 128, 2, 1, True),
+                                             ("cfg1_ppo_B64_T32", "PPO", 64, 32, 4, 2, False)):
+        model = (M.MlpLSTMSingleContinuous if cont else M.MlpLSTMSingle)(f, Aa, Tn, 64).to(dev)
+        eng = OnPolicyEngine(model.actor, algo, oracle.DEFAULT_HYPER, process_group=pg)
+        bs = [{k: v.to(dev) for k, v in make_rollouts(Bn, Tn, f, Aa, continuous=cont, batch_index=rank * 100 + i).items()} for i in range(2)]
+        run(name, eng, bs, Bn, Tn, lambda e, b: e.update(b))
+    model = M.MlpLSTMSingle(4, 2, 128, 64).to(dev)
+    eng = VMPOEngine(model.actor, oracle.DEFAULT_HYPER, process_group=pg)
+    bs = [{k: v.to(dev) for k, v in make_rollouts(1024, 128, 4, 2, batch_index=rank * 100 + i).items()} for i in range(2)]
+    run("cfg4_vmpo_1024_per_gpu_T128", eng, bs, 1024, 128, lambda e, b: e.update(b, 0.0075))
+    model = M.MlpLSTMSeperateContinuous(17, 6, 5, 64, act_dim=6).to(dev)
+    eng = SACEngine(model, oracle.DEFAULT_HYPER, True, process_group=pg)
+    bs = [{k: v.to(dev) for k, v in make_rollouts(8192, 5, 17, 6, continuous=True, batch_index=rank * 100 + i, act_dim=6).items()} for i in range(2)]
+    run("cfg5_sac_continuous_8192_per_gpu_T5_obs17_act6", eng, bs, 8192, 5, lambda e, b: e.update(b))
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -224,6 +406,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip configs / strong scaling / dp parity (profiling runs)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -247,6 +430,14 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
+    timed = Timed(dev, world, dist)
+    clocks = ClockSampler(local)                             # (NVML init happens HERE, not between the barrier and the timed region)
+
+    out_extra = {}
+    if world > 1 and not a.no_extras:
+        out_extra["dp_parity"] = dp_parity(dev, rank, world, pg)
+        if rank == 0:
+            log("dp parity:", json.dumps(out_extra["dp_parity"]))
 
     torch.manual_seed(0)                                     # same initial weights on every rank
     model = MlpLSTMSingle(F, A, T, H)
@@ -256,16 +447,11 @@ def main():
     host = [make_rollouts(B, T, F, A, batch_index=rank * 1000 + i) for i in range(NBUF)]
     dev_batches = [{k: v.to(dev) for k, v in b.items()} for b in host]
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
     # ---- value: K updates, rollouts resident in HBM
     for i in range(a.warmup):
         eng.update(dev_batches[i % NBUF])
-    barrier()
-    clocks = ClockSampler(local)
+    timed.barrier()
+    timed.barrier()                                          # (second pass: every rank leaves within microseconds of the others)
     clocks.start()
     launches0 = eng.n_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -273,7 +459,7 @@ def main():
     for i in range(a.steps):
         eng.update(dev_batches[i % NBUF])
     e1.record()
-    barrier()
+    timed.barrier()
     clk = clocks.stop()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
@@ -285,7 +471,8 @@ def main():
     if rank == 0:
         log(f"value leg done: {total_ms / a.steps:.3f} ms/step")
 
-    # ---- e2e: the reference-facing learning() coroutine fed with pinned HOST batches
+    # ---- e2e: the reference-facing learning() coroutine fed with HOST batches (pinned, as a storage process that writes into
+    # a registered ring would provide them)
     n_e2e = min(a.steps, 200)
     pinned = [tuple(t.pin_memory() for t in as_reference_tuple(b, T)[:6]) + (b["hx"].pin_memory(), b["cx"].pin_memory())
               for b in host]
@@ -293,61 +480,93 @@ def main():
     logged = []
     learner.log_loss_tensorboard = lambda timer, loss, detached: logged.append(float(loss))
 
-    def run_coroutine(n):
+    def run_coroutine(n, batches):
         learner.stop_event = StopAfter(n)
 
         async def go():
             q = asyncio.Queue()
             for i in range(n):
-                q.put_nowait(pinned[i % NBUF])
+                q.put_nowait(batches[i % NBUF])
             learner.batch_queue = q
             await learning_ppo(learner, ExecutionTimer(num_transition=B * T))
         asyncio.run(go())
 
-    run_coroutine(3)
-    barrier()
-    e0.record()
-    run_coroutine(n_e2e)
-    e1.record()
-    barrier()
-    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * T * n_e2e / (float(ms2.item()) * 1e-3)
+    def e2e_leg(batches, n):
+        run_coroutine(3, batches)
+        timed.barrier()
+        e0.record()
+        run_coroutine(n, batches)
+        e1.record()
+        timed.barrier()
+        m2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(m2, op=dist.ReduceOp.MAX)
+        return float(m2.item())
+
+    ms2 = e2e_leg(pinned, n_e2e)
+    e2e_value = world * B * T * n_e2e / (ms2 * 1e-3)
     h2d = learner.to_gpu.bytes_last
-    if rank == 0:
-        log(f"e2e leg done: {float(ms2.item()) / n_e2e:.3f} ms/step")
     d2h = 8 * 8 + 4
+    # the same from PAGEABLE host tensors (what `sample_batch_from_sh_memory`'s defensive copy hands over): one extra host
+    # memcpy into the pinned staging set per step
+    n_pg = min(n_e2e, 50)
+    pageable = [tuple(t.clone() for t in p) for p in pinned]
+    ms3 = e2e_leg(pageable, n_pg)
+    if rank == 0:
+        log(f"e2e leg done: {ms2 / n_e2e:.3f} ms/step pinned, {ms3 / n_pg:.3f} ms/step pageable")
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "algo": "PPO", "sequences_per_gpu": B, "seq_len": T, "obs": F, "actions": A,
-                   "hidden": H, "global_batch_sequences": B * world, "parallelism": f"dp{world}",
-                   "l2": "per-step working set (saved activations 0.8 GB) >> 126 MB L2; 4 input batches cycled"},
+        "dtype": "fp32", "data": "synthetic", "config": config_dict(world),
         "clocks": clk, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": n_e2e, "api": "b200rl.agents.learner_module.ppo.learning.learning(parent, timer)"},
+                "steps": n_e2e, "api": "b200rl.agents.learner_module.ppo.learning.learning(parent, timer)",
+                "host_batches": "pinned",
+                "pageable_value": world * B * T * n_pg / (ms3 * 1e-3), "pageable_steps": n_pg},
         "loss": losses["loss"],
+        "exchange": ("fused peer step (one-shot NVLink all-reduce + clip + RMSprop, csrc/peer_kernels.cu)"
+                     if eng.chan is not None else "NCCL all-reduce + single-CTA clip/RMSprop"),
     }
+    out.update(out_extra)
+
+    # ---- the other BASELINE configs and the strong-scaling variant (every rank takes part)
+    if not a.no_extras:
+        out["configs"] = other_configs(dev, rank, world, pg, timed)
+        if world > 1:
+            Bs = B // world
+            sb = [{k: v[:Bs].contiguous() for k, v in b.items()} for b in dev_batches[:2]]
+            ms_s = timed.run(lambda i: eng.update(sb[i % 2]), 20, 5) / 20
+            out["strong_scaling"] = {"global_batch_sequences": B, "sequences_per_gpu": Bs, "ms_per_step": ms_s,
+                                     "value": B * T / (ms_s * 1e-3), "unit": UNIT,
+                                     "note": "the recurrent kernels are bound by 128 dependent timesteps per sequence tile, not by "
+                                             "the number of tiles: below one 32-sequence tile per SM the step time stops shrinking"}
 
     if rank == 0:
         # ---- per-kernel device times (alone, CUDA events) and the roofline of the dominant one
         ops, L, hp = eng.ops, eng.L, eng.hp
         bt = dev_batches[0]
         u = bt["obs"]
+        gbuf, sbuf = (eng.chan.grad_views[0], eng.chan.scal_views[0]) if eng.chan is not None else (eng.grad, eng.scalars)
         stages = {
             "lstm_fwd": lambda i: ops.lstm_fwd(L, eng.flat, u, bt["hx"], bt["cx"], eng.ws),
             "head_fwd": lambda i: ops.head_fwd(L, eng.flat, eng.ws["h"], eng.head_out),
-            "ppo_head": lambda i: ops.ppo_head(eng.head_out, bt, eng.dhead, eng.scalars, hp, A, False, None),
+            "ppo_head": lambda i: ops.ppo_head(eng.head_out, bt, eng.dhead, sbuf, hp, A, False, None),
             "lstm_bwd": lambda i: ops.lstm_bwd(L, eng.flat, eng.dhead, eng.ws, bt["cx"]),
             "lstm_wgrad": lambda i: ops.lstm_wgrad(L, eng.flat, eng.ws, bt["hx"], u, eng.dhead, eng.partials, variant=eng.wgrad_variant),
-            "reduce_partials": lambda i: ops.reduce_partials(eng.partials, eng.grad),
-            "clip_rmsprop": lambda i: ops.clip_rmsprop(eng.flat, eng.grad, eng.sq_avg, L.P, 1.0, 40.0, 1e-4, 0.99, 1e-5, eng.grad_norm),
+            "reduce_partials": lambda i: ops.reduce_partials(eng.partials, gbuf),
         }
-        # run the chain once so every stage sees valid inputs, then time each alone
-        for fn in stages.values():
+        if world == 1:      # (the fused step handshakes with the peers: it cannot be timed alone on one rank of many)
+            scratch_p, scratch_s, scratch_g = eng.flat.clone(), eng.sq_avg.clone(), torch.empty_like(eng.grad)
+            if eng.chan is not None:
+                def opt_step(i):
+                    eng.chan.begin()
+                    eng.chan.step(0, scratch_p, scratch_s, None, None, scratch_g, eng.scalars, eng.grad_norm, 1.0, 40.0, 1e-4,
+                                  0.99, 0.0, 1e-5, 0, ops._stream(dev))
+                stages["clip_rmsprop"] = opt_step
+            else:
+                stages["clip_rmsprop"] = lambda i: ops.clip_rmsprop(scratch_p, eng.grad, scratch_s, L.P, 1.0, 40.0, 1e-4, 0.99, 1e-5, eng.grad_norm)
+        for fn in stages.values():                          # run the chain once so every stage sees valid inputs
             fn(0)
         kms = {k: event_time(fn, 10, dev) for k, fn in stages.items()}
         bt_ = B * T
@@ -360,28 +579,37 @@ def main():
             "reduce_partials": 4 * (eng.nparts * L.P + L.P),
             "clip_rmsprop": 4 * 6 * L.P,
         }
-        algo_flop = {"lstm_fwd": 2.0 * bt_ * (F * H + 2 * H * 4 * H), "lstm_bwd": 2.0 * bt_ * (4 * H * H),
-                     "lstm_wgrad": 2.0 * bt_ * (3 * 4 * H * H + H * F + H * L.NH)}
+        # model FLOPs and what the tensor pipe really executes: every GEMM runs as three TF32 passes
+        algo_flop = {"lstm_fwd": 2.0 * bt_ * (F * H + 2 * H * 4 * H), "lstm_bwd": 2.0 * bt_ * (2 * 4 * H * H),
+                     "lstm_wgrad": 2.0 * bt_ * (2 * 4 * H * H + H * F + H * L.NH)}
         dom = max(kms, key=kms.get)
         peak, peak_src, peaks = load_peaks()
         ach = algo_bytes[dom] / (kms[dom] * 1e-3) / 1e9
-        sm_max = clk.get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
-        fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+        tf32_peak = peaks.get("bf16_tflops_sustained", 1417.8) / 2.0
+        gemm_ms = sum(kms[k] for k in algo_flop)
+        issued = 3.0 * sum(algo_flop.values())
         out["roofline"] = {
             "kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
             "traffic": load_traffic(dom), "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes[dom],
-            "note": "persistent recurrent kernel (per-step tcgen05 GEMM + cell phase, 128 dependent steps): bound by the per-step "
-                    "serial latency (MMA issue ~31-44 cycles per M128xN32xK8 tf32 MMA, MUFU-bound cell phase), not by HBM; "
-                    "`fp32` = algorithmic flop rate vs the FP32 FFMA peak for scale (the GEMMs run as 3xTF32 on tcgen05); see DESIGN.md 4",
-            "fp32": {"achieved_tflops": algo_flop.get(dom, 0) / (kms[dom] * 1e-3) / 1e12, "peak_tflops": fp32_peak,
-                     "frac": algo_flop.get(dom, 0) / (kms[dom] * 1e-3) / 1e12 / fp32_peak},
+            "limited_by": "latency: persistent recurrent kernel, 128 dependent timesteps per 32-sequence tile (tcgen05 issue -> "
+                          "accumulator hand-over -> TMEM load -> MUFU cell phase -> operand rewrite); neither the HBM nor the "
+                          "tensor roofline is reached -- `frac` is the HBM-roofline fraction the metric asks for",
+            "tensor_pipe": {"kernels": sorted(algo_flop), "model_tflops": sum(algo_flop.values()) / (gemm_ms * 1e-3) / 1e12,
+                            "issued_tflops_3xtf32": issued / (gemm_ms * 1e-3) / 1e12, "peak_tflops_tf32": tf32_peak,
+                            "frac": issued / (gemm_ms * 1e-3) / 1e12 / tf32_peak,
+                            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (dense TF32 runs at half the bf16 rate)"},
+            "end_to_end": {"compulsory_bytes_per_env_step": 36, "achieved_gbs": value / world * 36 / 1e9,
+                           "frac_of_hbm_peak": value / world * 36 / 1e9 / peak,
+                           "note": "SURVEY 8d: inputs read once per update (obs 16 B + act/rew/log_prob/is_fir 16 B + hx0,cx0 "
+                                   "512 B / T); the step is LSTM-latency-bound, not bound by these bytes"},
         }
         out["kernels_ms"] = kms
         out["kernels_hbm_gbs"] = {k: algo_bytes[k] / (v * 1e-3) / 1e9 for k, v in kms.items()}
+        out["kernels_hbm_frac"] = {k: algo_bytes[k] / (v * 1e-3) / 1e9 / peak for k, v in kms.items()}
         out["step_share"] = {k: v / sum(kms.values()) for k, v in kms.items()}
         if world == 1 and not a.no_cpu_baseline:
-            log("timing the CPU port ...")
-            out["cpu_baseline"] = cpu_baseline()
+            log("timing the CPU reference ...")
+            out["cpu_baseline"], out["parity_in_run"] = cpu_baseline_and_parity(dev)
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
