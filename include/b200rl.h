@@ -78,6 +78,16 @@ int b200rl_lstm_fwd(const float* u, const float* hx0, const float* cx0,
                     float* gates, float* c, float* h,
                     int B, int T, int Fin, int variant, void* stream);
 
+/* The same forward AND the heads in one persistent tcgen05 kernel (csrc/fwd_fused.cu): torso, input projection, LSTM
+ * recurrence (networks/models.py:67-75) and head_out = h . W_head^T + b_head (models.py:77-78) without the HBM round trip
+ * of the input projection.  Requires Fin <= 8; heads are fused when head_part != NULL (scratch of B*T*2*NH floats,
+ * NH <= 4) and then head_out (B,T,NH) is written; with head_part == NULL only gates / c / h are produced.            */
+int b200rl_lstm_fwd_fused(const float* u, const float* hx0, const float* cx0,
+                          const float* Wt, const float* bt, const float* W_ih, const float* W_hh,
+                          const float* b_ih, const float* b_hh, const float* W_head, const float* b_head,
+                          float* gates, float* c, float* h, float* head_part, float* head_out,
+                          int B, int T, int Fin, int NH, void* stream);
+
 /* head_out (rows, NH) = h (rows, H) . W_head^T (NH, H) + b_head                      */
 int b200rl_head_fwd(const float* h, const float* W_head, const float* b_head,
                     float* head_out, long long rows, int NH, void* stream);
@@ -90,6 +100,15 @@ int b200rl_head_fwd(const float* h, const float* W_head, const float* b_head,
 int b200rl_lstm_bwd(const float* dhead, const float* W_head, const float* W_hh, const float* W_ih,
                     float* gates, const float* c, const float* cx0, float* dx,
                     int B, int T, int NH, int variant, void* stream);
+
+/* The tcgen05 BPTT kernel with the small gradients fused (csrc/bwd_tc.cu): besides dpre (in place in `gates`) it accumulates
+ * dW_head / db_head (h recomputed as o tanh(c)) and dWt / dbt (dx taken straight from the accumulator, ReLU mask from the
+ * recomputed torso) and writes them into slab row blockIdx of `partials` (nparts x P, >= min(ceil(B/32), SMs) rows) --
+ * replacing the head / torso passes of lstm_wgrad (then called with variant 4).  Needs Fin == 4 and NH <= 4.          */
+int b200rl_lstm_bwd_fused(const float* dhead, const float* W_head, const float* W_hh, const float* W_ih,
+                          float* gates, const float* c, const float* cx0, const float* u, const float* Wt, const float* bt,
+                          float* partials, int nparts, long long P, long long off_Wt, long long off_bt,
+                          long long off_Whead, long long off_bhead, int B, int T, int Fin, int NH, void* stream);
 
 /* BPTT, parallel part: weight gradients as `nparts` partial slabs of `P` floats each
  * (partials[part*P + off_*]); also the torso-input gradient du (B,T,Fin) if non-NULL.

@@ -219,7 +219,11 @@ class _LoopbackComm:
         proto_bytes = HEADER_BYTES + 2 * ((n * 4 + 64 + 255) // 256 * 256)
         regions = self.w._region(key, proto_bytes)
         self.barrier()
-        return PeerChannel(n, self.rank, self.world, self.device, self.lib, local_regions=[r.data_ptr() for r in regions])
+        ch = PeerChannel(n, self.rank, self.world, self.device, self.lib, local_regions=[r.data_ptr() for r in regions])
+        # all "ranks" share ONE GPU here: keep the spinning peer kernels small enough that whole SMs stay free for the other
+        # ranks' recurrent kernels (which need an SM to themselves)
+        ch.grid = max(1, min(GRID, -(-(n // 4) // (256 * 4))))
+        return ch
 
     def close(self):
         pass

@@ -123,15 +123,14 @@ class OnPolicyEngine:
 
         # gradient / loss-sum buffers of this step: the peer channel's (other ranks read them over NVLink) or the local ones
         gbuf, sbuf = self.chan.begin() if self.chan is not None else (self.grad, self.scalars)
-        ops.lstm_fwd(L, self.flat, u, batch["hx"], batch["cx"], self.ws)
-        ops.head_fwd(L, self.flat, self.ws["h"], self.head_out)
+        nfw = ops.net_fwd(L, self.flat, u, batch["hx"], batch["cx"], self.ws, self.head_out)
         sbuf.copy_(self._scalar_init)
         if self.algo == "IMPALA":
             ops.impala_head(self.head_out, batch, self.dhead, sbuf, hp, self.net.n_outputs, outs)
         else:
             ops.ppo_head(self.head_out, batch, self.dhead, sbuf, hp, self.net.n_outputs,
                          self.net.continuous, outs)
-        ops.lstm_bwd(L, self.flat, self.dhead, self.ws, batch["cx"])
+        ops.lstm_bwd(L, self.flat, self.dhead, self.ws, batch["cx"], u=u, partials=self.partials)
         ops.lstm_wgrad(L, self.flat, self.ws, batch["hx"], u, self.dhead, self.partials, variant=self.wgrad_variant)
         ops.reduce_partials(self.partials, gbuf)
         scale = 1.0 / self.world
@@ -144,7 +143,7 @@ class OnPolicyEngine:
                 self.comm.all_reduce(self.grad)                                 # the ONE gradient collective
             ops.clip_rmsprop(self.flat, self.grad, self.sq_avg, L.P, scale, hp["max_grad_norm"], hp["lr"],
                              0.99, 1e-5, self.grad_norm)
-        self.n_launches += 8 + {0: 0, 1: 2, 2: 1}[self.wgrad_variant] + (1 if _ops.FWD_VARIANT >= 2 else 0)
+        self.n_launches += nfw + 4 + (1 if self.ws.get("small_grads_done") else {0: 1, 1: 3, 2: 2}[self.wgrad_variant])   # + head, bwd, reduce, step ; wgrad stage
 
     # -------------------------------------------------------------------- scalars
     def _reduced_scalars(self):
@@ -253,8 +252,7 @@ class VMPOEngine(OnPolicyEngine):
         ops._chk(batch["act"], batch["rew"], batch["is_fir"], batch["logits"], batch["hx"], batch["cx"])
 
         gbuf, sbuf = self.chan.begin() if self.chan is not None else (self.grad, self.scalars)
-        ops.lstm_fwd(L, self.flat, u, batch["hx"], batch["cx"], self.ws)
-        ops.head_fwd(L, self.flat, self.ws["h"], self.head_out)
+        nfw = ops.net_fwd(L, self.flat, u, batch["hx"], batch["cx"], self.ws, self.head_out)
         sbuf.copy_(self._zero8)
         lib.call("b200rl_vmpo_gae", ptr(self.head_out), ptr(batch["rew"]), ptr(batch["is_fir"]), ptr(self.gae),
                  ptr(self.dhead), ptr(sbuf), B, T, A, hp["gamma"], hp["lmbda"], hp["value_loss_coef"], N, st)
@@ -265,7 +263,7 @@ class VMPOEngine(OnPolicyEngine):
         lib.call("b200rl_vmpo_grad", ptr(self.head_out), ptr(batch["act"]), ptr(batch["logits"]), ptr(self.gae), ptr(self.thr),
                  ptr(self.colstat), ptr(self.tie_cut), ptr(self.duals), ptr(self.dhead), ptr(sbuf), B, T, A, self.rank * B,
                  hp["policy_loss_coef"], N, st)
-        ops.lstm_bwd(L, self.flat, self.dhead, self.ws, batch["cx"])
+        ops.lstm_bwd(L, self.flat, self.dhead, self.ws, batch["cx"], u=u, partials=self.partials)
         ops.lstm_wgrad(L, self.flat, self.ws, batch["hx"], u, self.dhead, self.partials, variant=self.wgrad_variant)
         ops.reduce_partials(self.partials, gbuf)
         # (the kernels already normalise by the GLOBAL N: plain sum over ranks, no 1/world)
@@ -280,7 +278,7 @@ class VMPOEngine(OnPolicyEngine):
         lib.call("b200rl_vmpo_dual_step", ptr(self.duals), ptr(self.dual_sq), ptr(self.scalars), ptr(self.losses_dev),
                  hp["coef_eta"], float(coef_alpha), hp["lr"], 0.99, 1e-5, N, float(k * (T - 1)),
                  hp["policy_loss_coef"], hp["value_loss_coef"], st)
-        self.n_launches += 12 + {0: 0, 1: 2, 2: 1}[self.wgrad_variant] + (1 if _ops.FWD_VARIANT >= 2 else 0)
+        self.n_launches += nfw + 7 + (1 if self.ws.get("small_grads_done") else {0: 1, 1: 3, 2: 2}[self.wgrad_variant])
 
     def losses(self):
         v = self.losses_dev.cpu().tolist()
@@ -372,12 +370,11 @@ class SACEngine:
 
     def _net_fwd(self, L, flat, off, u, hx, cx, ws, out):
         f = flat[off:off + L.P]
-        self.ops.lstm_fwd(L, f, u, hx, cx, ws)
-        self.ops.head_fwd(L, f, ws["h"], out)
+        self.ops.net_fwd(L, f, u, hx, cx, ws, out)
 
     def _net_bwd(self, L, flat, off, u, hx, cx, ws, dhead, partials, grad, du=None):
         f = flat[off:off + L.P]
-        self.ops.lstm_bwd(L, f, dhead, ws, cx)
+        self.ops.lstm_bwd(L, f, dhead, ws, cx, u=None if du is not None else u, partials=None if du is not None else partials)
         self.ops.lstm_wgrad(L, f, ws, hx, u, dhead, partials, du=du, variant=self.wgrad_variant)
         if grad is not None:
             self.ops.reduce_partials(partials, grad)

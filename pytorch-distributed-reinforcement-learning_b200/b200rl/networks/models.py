@@ -137,7 +137,7 @@ class _FlatNet(nn.Module):
 
     # --- kernels ----------------------------------------------------------------
     def run_lstm(self, u, lstm_hxs, ops=None):
-        """-> (head_out (B,T,NH), workspace) via lstm_fwd + head_fwd."""
+        """-> (head_out (B,T,NH), workspace) via the network-forward op (one fused kernel, or lstm_fwd + head_fwd)."""
         ops = ops or _ops.default()
         flat, L = self.flat_parameters(), self._layout
         hx, cx = lstm_hxs
@@ -146,9 +146,8 @@ class _FlatNet(nn.Module):
         ws = dict(gates=torch.empty(B, T, H, 4, device=dev), c=torch.empty(B, T, H, device=dev),
                   h=torch.empty(B, T, H, device=dev))
         u = u.contiguous().float()
-        ops.lstm_fwd(L, flat, u, hx.contiguous().float(), cx.contiguous().float(), ws)
         head_out = torch.empty(B, T, L.NH, device=dev)
-        ops.head_fwd(L, flat, ws["h"], head_out)
+        ops.net_fwd(L, flat, u, hx.contiguous().float(), cx.contiguous().float(), ws, head_out)
         return head_out, ws
 
     # worker-side single-step inference (reference `act`, models.py:37-56): plain torch on

@@ -10,14 +10,17 @@ from . import native
 from .native import ptr
 
 H = 64
-# kernel variants (env-overridable for A/B measurements): forward 4 = as 3 with two 16-sequence groups per CTA in ping-pong,
+# kernel variants (env-overridable for A/B measurements): forward 5 = ONE persistent tcgen05 kernel for torso + input projection
+# + recurrence + heads (csrc/fwd_fused.cu; nets with Fin > 8 or more than 4 head outputs fall back to 3),
+# 4 = as 3 with two 16-sequence groups per CTA in ping-pong,
 # 3 = tcgen05 input projection + tcgen05 recurrent
 # kernel (W_hh resident in tensor memory), 2 = tcgen05 input projection + FFMA recurrent kernel (K=64),
 # 1 = 16-warp split-K FFMA, 0 = 8-warp FFMA with the projection in the loop
-FWD_VARIANT = int(os.environ.get("B200RL_FWD_VARIANT", "3"))
-# backward 1 = tcgen05 BPTT kernel (also emits dx = dpre . W_ih, so the weight-gradient stage skips that GEMM),
-# 0 = FFMA kernel
-BWD_VARIANT = int(os.environ.get("B200RL_BWD_VARIANT", "1"))
+FWD_VARIANT = int(os.environ.get("B200RL_FWD_VARIANT", "5"))
+# backward 2 = tcgen05 BPTT kernel that also accumulates the head and torso gradients in registers (no dx in HBM, no head_grad /
+# torso_grad passes; nets with Fin != 4 or more than 4 head outputs, or callers that need d/d(input), fall back to 1),
+# 1 = tcgen05 BPTT kernel (emits dx = dpre . W_ih, so the weight-gradient stage skips that GEMM), 0 = FFMA kernel
+BWD_VARIANT = int(os.environ.get("B200RL_BWD_VARIANT", "2"))
 
 
 class Ops:
@@ -138,9 +141,37 @@ def _lstm_fwd(self, L, flat, u, hx0, cx0, ws, variant=None):
     B, T, Fin = u.shape
     assert Fin == L.Fin
     v = lambda k: ptr(flat) + 4 * L.off[k][0]
+    variant = FWD_VARIANT if variant is None else variant
+    if variant == 5:
+        if Fin <= 8:
+            self.lib.call("b200rl_lstm_fwd_fused", ptr(u), ptr(hx0), ptr(cx0), v("Wt"), v("bt"), v("W_ih"), v("W_hh"),
+                          v("b_ih"), v("b_hh"), 0, 0, ptr(ws["gates"]), ptr(ws["c"]), ptr(ws["h"]), 0, 0, B, T, Fin, L.NH,
+                          self._stream(dev))
+            return
+        variant = 3
     self.lib.call("b200rl_lstm_fwd", ptr(u), ptr(hx0), ptr(cx0), v("Wt"), v("bt"), v("W_ih"), v("W_hh"),
-                  v("b_ih"), v("b_hh"), ptr(ws["gates"]), ptr(ws["c"]), ptr(ws["h"]), B, T, Fin,
-                  FWD_VARIANT if variant is None else variant, self._stream(dev))
+                  v("b_ih"), v("b_hh"), ptr(ws["gates"]), ptr(ws["c"]), ptr(ws["h"]), B, T, Fin, variant, self._stream(dev))
+
+
+def _net_fwd(self, L, flat, u, hx0, cx0, ws, head_out, variant=None):
+    """Network forward: saved activations into `ws` and head_out (B, T, NH) = h . W_head^T + b_head.  Variant 5 with
+    Fin <= 8 and NH <= 4 is ONE recurrent kernel (+ the 6 us head_combine); everything else is lstm_fwd + head_fwd.
+    Returns the number of kernel launches."""
+    variant = FWD_VARIANT if variant is None else variant
+    B, T, Fin = u.shape
+    if variant == 5 and Fin <= 8 and L.NH <= 4:
+        dev = self._chk(flat, u, hx0, cx0, ws["gates"], ws["c"], ws["h"], head_out)
+        hp = ws.get("head_part")
+        if hp is None or hp.shape != (B, T, 2, L.NH):
+            hp = ws["head_part"] = torch.empty(B, T, 2, L.NH, device=u.device)
+        v = lambda k: ptr(flat) + 4 * L.off[k][0]
+        self.lib.call("b200rl_lstm_fwd_fused", ptr(u), ptr(hx0), ptr(cx0), v("Wt"), v("bt"), v("W_ih"), v("W_hh"),
+                      v("b_ih"), v("b_hh"), v("W_head"), v("b_head"), ptr(ws["gates"]), ptr(ws["c"]), ptr(ws["h"]),
+                      ptr(hp), ptr(head_out), B, T, Fin, L.NH, self._stream(dev))
+        return 2
+    self.lstm_fwd(L, flat, u, hx0, cx0, ws, variant=variant)
+    self.head_fwd(L, flat, ws["h"], head_out)
+    return 2 if (variant == 5 or variant < 2) else 3
 
 
 def _head_fwd(self, L, flat, h, head_out):
@@ -150,11 +181,25 @@ def _head_fwd(self, L, flat, h, head_out):
     self.lib.call("b200rl_head_fwd", ptr(h), v("W_head"), v("b_head"), ptr(head_out), rows, L.NH, self._stream(dev))
 
 
-def _lstm_bwd(self, L, flat, dhead, ws, cx0, variant=None):
+def _lstm_bwd(self, L, flat, dhead, ws, cx0, variant=None, u=None, partials=None):
+    """`u`, `partials`: the network input and the partial-gradient slabs -- given by callers that do NOT need d/d(input), so
+    that variant 2 may fuse the head / torso gradients (it then sets ws["small_grads_done"] for lstm_wgrad)."""
     dev = self._chk(flat, dhead, ws["gates"], ws["c"], cx0)
     B, T = dhead.shape[0], dhead.shape[1]
     variant = BWD_VARIANT if variant is None else variant
     v = lambda k: ptr(flat) + 4 * L.off[k][0]
+    o = lambda k: L.off[k][0]
+    ws["small_grads_done"] = False
+    if variant == 2:
+        if u is not None and partials is not None and L.Fin == 4 and L.NH <= 4:
+            self._chk(u, partials)
+            ws["dx_fresh"] = False
+            self.lib.call("b200rl_lstm_bwd_fused", ptr(dhead), v("W_head"), v("W_hh"), v("W_ih"), ptr(ws["gates"]), ptr(ws["c"]),
+                          ptr(cx0), ptr(u), v("Wt"), v("bt"), ptr(partials), partials.shape[0], L.P, o("Wt"), o("bt"), o("W_head"),
+                          o("b_head"), B, T, L.Fin, L.NH, self._stream(dev))
+            ws["small_grads_done"] = True
+            return
+        variant = 1
     dx = None
     if variant == 1:
         dx = ws.get("dx")
@@ -171,7 +216,9 @@ def _lstm_wgrad(self, L, flat, ws, hx0, u, dhead, partials, du=None, variant=0):
     nparts = partials.shape[0]
     assert partials.shape[1] == L.P
     dx = None
-    if variant == 1 and ws.get("dx_fresh") and du is None and Fin <= 8:
+    if variant == 1 and ws.get("small_grads_done") and du is None:
+        variant = 4
+    elif variant == 1 and ws.get("dx_fresh") and du is None and Fin <= 8:
         variant, dx = 3, ws["dx"]
     v = lambda k: ptr(flat) + 4 * L.off[k][0]
     o = lambda k: L.off[k][0]
@@ -222,7 +269,7 @@ def _clip_adam(self, param, grad, m, v, n, grad_scale, max_norm, lr, step, b1=0.
                   step, ptr(mask), ptr(norm_out), self._stream(dev))
 
 
-for _n, _f in (("lstm_fwd", _lstm_fwd), ("head_fwd", _head_fwd), ("lstm_bwd", _lstm_bwd), ("lstm_wgrad", _lstm_wgrad),
+for _n, _f in (("lstm_fwd", _lstm_fwd), ("net_fwd", _net_fwd), ("head_fwd", _head_fwd), ("lstm_bwd", _lstm_bwd), ("lstm_wgrad", _lstm_wgrad),
                ("reduce_partials", _reduce_partials), ("ppo_head", _ppo_head), ("impala_head", _impala_head),
                ("clip_rmsprop", _clip_rmsprop), ("clip_adam", _clip_adam)):
     setattr(Ops, _n, _f)

@@ -32,6 +32,12 @@
 //   partner; then BOTH threads of a pair finish four cells each with 7 flops per cell:
 //   dh = D + dhW ; d_o' = dh P_o ; dct = dh Q + dc ; (dct P_i, dct P_f, dct P_g) ; dc = dct f,
 //   store dpre (global + B operand hi/lo) and hand the step to the issuers.
+//
+// Fused small gradients (`fuse`, Fin == 4 and NH <= 4): the helper threads also own
+//   dW_head[o][j] += dhead[b,t,o] h[b,t,j], db_head[o] += dhead[b,t,o]     (h = o tanh(c) is recomputed: tanh(c) is already there)
+//   dWt[j][f] += dxm obs[b,t,f], dbt[j] += dxm, dxm = dx[b,t,j] [x[b,t,j] > 0]   (dx straight from the accumulator, x from the 4-wide obs)
+// in registers across all T steps and write ONE slab row per CTA at the end: the head_grad pass (re-reads 134 MB of h) and the
+// torso_grad pass (134 MB of dx written here, read back there) of round 1 disappear, and dx never goes to HBM.
 #include "common.cuh"
 #include "tc05.cuh"
 #include "launchers.cuh"
@@ -66,14 +72,22 @@ constexpr int CELLS = TB * H;
 }  // namespace btk
 
 static inline size_t bwdt_smem_bytes(int NH) {
-    return 2 * (size_t)btk::B_BYTES + btk::C_BYTES + sizeof(float) * (size_t)(btk::NCOEF * btk::CELLS + NH * btk::H + 8 * 8 * NH + 8 * 4 * 32) + 64;
+    return 2 * (size_t)btk::B_BYTES + btk::C_BYTES + sizeof(float) * (size_t)(btk::NCOEF * btk::CELLS + NH * btk::H + 8 * 8 * NH + 8 * 4 * 32 + 8 * 32 + btk::H * 4 + btk::H) + 64;
 }
 
+struct BwdFuse {                 // fused head / torso gradients (null partials = off)
+    const float* u; const float* Wt; const float* bt; float* partials;
+    long long P, off_Wt, off_bt, off_Whead, off_bhead;
+};
+
+template <int NHT>                // 0: runtime NH, small gradients left to their own kernels ; 1..4: NH == NHT at compile time, `fz` gradients fused
 __global__ void __launch_bounds__(btk::NT, 1)
 lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_head, const float* __restrict__ W_hh,
                  const float* __restrict__ W_ih, float* gates, const float* __restrict__ c_sav,
-                 const float* __restrict__ cx0, float* __restrict__ dx, int B, int T, int NH) {
+                 const float* __restrict__ cx0, float* __restrict__ dx, int B, int T, int NH, BwdFuse fz) {
     using namespace btk;
+    constexpr bool fuse = NHT > 0;
+    if (fuse) NH = NHT;
     B200RL_DYN_SMEM(unsigned char, smem);
     unsigned char* B_hi = smem;
     unsigned char* B_lo = smem + B_BYTES;
@@ -82,7 +96,10 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
     float* WhS = COEF + NCOEF * CELLS;                               // WhS[c*64 + j]
     float* DHS = WhS + NH * H;                                       // DHS[helper pair][8 sequences * NH]: dhead rows of the step being prepared
     float* DHX = DHS + 8 * 8 * NH;                                   // DHX[pair][4][lane]: dh_rec of the cells the helper finishes
-    uint64_t* bars = reinterpret_cast<uint64_t*>(DHX + 8 * 4 * 32);           // (8-byte aligned)
+    float* OBS = DHX + 8 * 4 * 32;                                   // OBS[helper pair][8 sequences * 4]: observations of the step whose dx is drained next
+    float* WTS = OBS + 8 * 32;                                       // Wt[j][0..3]
+    float* BTS = WTS + H * 4;                                        // bt[j]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(BTS + H + ((NH & 1) ? 1 : 0));   // (8-byte aligned: NH*H + 64*NH floats precede)
     uint64_t* b_full = bars, *acc_done = bars + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
 
@@ -91,6 +108,10 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
     const int q = warp & 3, cg = (warp >> 2) & 3;                   // TMEM lane quarter, group of 8 sequences
 
     for (int i = tid; i < NH * H; i += NT) WhS[i] = W_head[i];
+    if (fuse) {
+        for (int i = tid; i < H * 4; i += NT) WTS[i] = fz.Wt[i];
+        for (int i = tid; i < H; i += NT) BTS[i] = fz.bt[i];
+    }
     if (tid == 0) {
         tc::mbar_init(b_full, NC / 32); tc::mbar_init(acc_done, NI);
         tc::fence_mbar_init();
@@ -181,6 +202,13 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
             }
         };
         uint32_t nb = 0;                                             // accumulator batches waited for so far
+        // fused small gradients, helper threads, summed over every step of every tile of this CTA: dW_head[o][j], dWt[j][f], dbt[j],
+        // db_head[lane] (lanes < NH of the half-0 warps)
+        float aWh[NHT > 0 ? NHT : 1], aWt[4], abt = 0.f, abh = 0.f;
+#pragma unroll
+        for (int o = 0; o < (NHT > 0 ? NHT : 1); ++o) aWh[o] = 0.f;
+#pragma unroll
+        for (int f = 0; f < 4; ++f) aWt[f] = 0.f;
         BWP_INIT
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int b0 = tile * TB + cg * 8;
@@ -235,6 +263,25 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                         cp_async4(dhs + e, dhead + (size_t)(rowof(i) + t) * NH + c);
                     }
                 };
+                float* obs_s = OBS + pair * 32;
+                auto fetch_obs = [&](int t) {                        // observations of step t for this warp's 8 sequences (asynchronous)
+                    __syncwarp();
+                    const int bb = b0 + (lane >> 2);
+                    cp_async4(obs_s + lane, fz.u + ((size_t)(bb < B ? bb : B - 1) * T + t) * 4 + (lane & 3));
+                };
+                auto torso = [&](const float (&dxv)[8]) {            // dWt, dbt from dx of the step whose observations sit in obs_s
+                    const float4 w = ld4(WTS + j * 4);
+                    const float btj = BTS[j];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 o4 = ld4(obs_s + i * 4);
+                        const float x = fmaf(w.x, o4.x, fmaf(w.y, o4.y, fmaf(w.z, o4.z, fmaf(w.w, o4.w, btj))));
+                        const float d = (x > 0.f && b0 + i < B) ? dxv[i] : 0.f;
+                        aWt[0] = fmaf(d, o4.x, aWt[0]); aWt[1] = fmaf(d, o4.y, aWt[1]);
+                        aWt[2] = fmaf(d, o4.z, aWt[2]); aWt[3] = fmaf(d, o4.w, aWt[3]);
+                        abt += d;
+                    }
+                };
                 auto coefs = [&](int t) {                            // everything of step t that does not need dh
                     cp_async_wait_all();
                     __syncwarp();
@@ -245,22 +292,43 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
 #endif
                     // dhead . W_head with the head index outermost: ONE runtime loop with eight independent FMA chains inside (the
                     // per-cell form compiled to a branchy unroll cascade per cell that kept the eight cells from overlapping: 4.2K cycles)
-                    float dhw[8];
+                    float dhw[8], tch[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) dhw[i] = 0.f;
-                    for (int c = 0; c < NH; ++c) {
-                        const float w = WhS[c * H + j];
+                    for (int i = 0; i < 8; ++i) { dhw[i] = 0.f; tch[i] = tanh_(ccur[i]); }
+                    if (fuse) {
+                        // compile-time head count: fully unrolled; the head gradient dW_head[c][j] += dhead[b,t,c] h[b,t,j] rides on the
+                        // same dhead values (h = o tanh(c) recomputed)
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) dhw[i] = fmaf(dhs[i * NH + c], w, dhw[i]);
+                        for (int c = 0; c < (NHT > 0 ? NHT : 1); ++c) {
+                            const float w = WhS[c * H + j];
+                            float a = 0.f;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float d = dhs[i * NHT + c];
+                                dhw[i] = fmaf(d, w, dhw[i]);
+                                a = fmaf((b0 + i < B) ? d : 0.f, gcur[i].w * tch[i], a);
+                            }
+                            aWh[c] += a;
+                        }
+                        if (q == 2 && lane < NHT) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) abh += (b0 + i < B) ? dhs[i * NHT + lane] : 0.f;
+                        }
+                    } else {
+                        for (int c = 0; c < NH; ++c) {
+                            const float w = WhS[c * H + j];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) dhw[i] = fmaf(dhs[i * NH + c], w, dhw[i]);
+                        }
                     }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float4 g4 = gcur[i];                   // i, f, g, o (post-activation)
-                        const float tch = tanh_(ccur[i]);
+                        const float th = tch[i];
                         float* co = CO + i * 32;
                         co[0 * 2048] = dhw[i];
-                        co[1 * 2048] = tch * g4.w * (1.f - g4.w);
-                        co[2 * 2048] = g4.w * (1.f - tch * tch);
+                        co[1 * 2048] = th * g4.w * (1.f - g4.w);
+                        co[2 * 2048] = g4.w * (1.f - th * th);
                         co[3 * 2048] = g4.z * g4.x * (1.f - g4.x);
                         co[4 * 2048] = cprev[i] * g4.y * (1.f - g4.y);
                         co[5 * 2048] = g4.x * (1.f - g4.z * g4.z);
@@ -302,10 +370,15 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                     tc::named_bar_sync(1 + pair, 64);                // both threads have read their coefficients: the slots are free for step t-1
                     BWP(11, 64);
                     if (t < T - 1) {
+                        if (fuse) {
+                            torso(dxs);                              // (obs_{t+1} landed before the previous coefs())
+                        } else {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            if (b0 + i < B) dx[(size_t)(rowof(i) + t + 1) * H + j] = dxs[i];
+                            for (int i = 0; i < 8; ++i)
+                                if (b0 + i < B) dx[(size_t)(rowof(i) + t + 1) * H + j] = dxs[i];
+                        }
                     }
+                    if (fuse) fetch_obs(t);                          // for dx_t, drained in the next iteration
                     if (t > 0) coefs(t - 1);
                     BWP(12, 64);
                 }
@@ -314,9 +387,16 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                 {
                     float d[8];
                     read_acc(d);
+                    if (fuse) {
+                        cp_async_wait_all();
+                        __syncwarp();
+                        torso(d);
+                        __syncwarp();                                // (the next tile's first fetch_obs overwrites the slot)
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if (b0 + i < B) dx[(size_t)rowof(i) * H + j] = d[i];
+                        for (int i = 0; i < 8; ++i)
+                            if (b0 + i < B) dx[(size_t)rowof(i) * H + j] = d[i];
+                    }
                     tc::fence_before_sync();
                 }
             } else {
@@ -354,24 +434,77 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                 tc::mbar_wait(acc_done, nb & 1); ++nb;               // batch of step 0 (dx_0): keeps the phase count in step
             }
         }
-    }
+        if (fuse) {
+            // hand the register accumulators to the CTA-wide reduction below (COEF is free once every warp has left its loops)
+            __syncthreads();
+            if (q >= 2) {
+                float* red = COEF + cg * (10 * H) + j;
+#pragma unroll
+                for (int o = 0; o < 4; ++o) red[o * H] = o < NHT ? aWh[o < NHT ? o : 0] : 0.f;
+#pragma unroll
+                for (int f = 0; f < 4; ++f) red[(4 + f) * H] = aWt[f];
+                red[8 * H] = abt;
+                red[9 * H] = abh;
+            }
+        }
+    } 
+    if (fuse && !cellw) __syncthreads();                             // (issuer warps: match the cell warps' extra barrier)
     tc::fence_before_sync();
     __syncthreads();
+    if (fuse) {
+        float* slab = fz.partials + (size_t)blockIdx.x * fz.P;
+        for (int e = tid; e < 10 * H; e += NT) {
+            const int k = e / H, jj = e - k * H;
+            const float v = (COEF[0 * 10 * H + e] + COEF[1 * 10 * H + e]) + (COEF[2 * 10 * H + e] + COEF[3 * 10 * H + e]);
+            if (k < 4) { if (k < NHT) slab[fz.off_Whead + (size_t)k * H + jj] = v; }
+            else if (k < 8) slab[fz.off_Wt + (size_t)jj * 4 + (k - 4)] = v;
+            else if (k == 8) slab[fz.off_bt + jj] = v;
+            else if (jj < NHT) slab[fz.off_bhead + jj] = v;
+        }
+    }
     if (warp == NC / 32) tc::tmem_dealloc(tmem, TM_COLS);
 }
 
 int launch_bwd_tc(const float* dhead, const float* W_head, const float* W_hh, const float* W_ih, float* gates,
                   const float* c, const float* cx0, float* dx, int B, int T, int NH, int sms, void* stream) {
-    B200RL_REQUIRE((long long)B * T < (1LL << 31), "lstm_bwd(tc): B*T must be below 2^31");
-    B200RL_REQUIRE(dx != nullptr && W_ih != nullptr, "lstm_bwd(tc): needs W_ih and the dx workspace");
+    return launch_bwd_tc_fused(dhead, W_head, W_hh, W_ih, gates, c, cx0, dx, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, 0,
+                               B, T, 0, NH, sms, stream);
+}
+
+template <int NHT>
+static int launch_bwdt(const float* dhead, const float* W_head, const float* W_hh, const float* W_ih, float* gates,
+                       const float* c, const float* cx0, float* dx, int B, int T, int NH, BwdFuse fz, int sms, void* stream) {
     const int ntiles = (B + btk::TB - 1) / btk::TB;
     const size_t smem = bwdt_smem_bytes(NH);
 #ifndef B200RL_EMUL
-    cudaError_t e = cudaFuncSetAttribute(lstm_bwdt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(lstm_bwdt_kernel<NHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error("lstm_bwd(tc): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
 #endif
-    B200RL_LAUNCH(lstm_bwdt_kernel, ntiles < sms ? ntiles : sms, btk::NT, smem, stream, dhead, W_head, W_hh, W_ih, gates, c, cx0, dx, B, T, NH);
+    B200RL_LAUNCH(lstm_bwdt_kernel<NHT>, ntiles < sms ? ntiles : sms, btk::NT, smem, stream, dhead, W_head, W_hh, W_ih, gates, c, cx0, dx, B, T, NH, fz);
     return check_launch("lstm_bwd(tc)");
+}
+
+// partials != nullptr: head and torso gradients fused (needs Fin == 4, NH <= 4; dx is not written and may be null)
+int launch_bwd_tc_fused(const float* dhead, const float* W_head, const float* W_hh, const float* W_ih, float* gates,
+                        const float* c, const float* cx0, float* dx, const float* u, const float* Wt, const float* bt,
+                        float* partials, long long P, long long off_Wt, long long off_bt, long long off_Whead, long long off_bhead,
+                        int B, int T, int Fin, int NH, int sms, void* stream) {
+    B200RL_REQUIRE((long long)B * T < (1LL << 31), "lstm_bwd(tc): B*T must be below 2^31");
+    B200RL_REQUIRE(W_ih != nullptr, "lstm_bwd(tc): needs W_ih");
+    BwdFuse fz{u, Wt, bt, partials, P, off_Wt, off_bt, off_Whead, off_bhead};
+    if (partials == nullptr) {
+        B200RL_REQUIRE(dx != nullptr, "lstm_bwd(tc): needs the dx workspace");
+        return launch_bwdt<0>(dhead, W_head, W_hh, W_ih, gates, c, cx0, dx, B, T, NH, fz, sms, stream);
+    }
+    B200RL_REQUIRE(Fin == 4 && NH >= 1 && NH <= 4 && u && Wt && bt, "lstm_bwd(tc, fused gradients): needs Fin == 4 and NH <= 4 (Fin=%d NH=%d)", Fin, NH);
+    const int ntiles = (B + btk::TB - 1) / btk::TB;
+    B200RL_REQUIRE((ntiles < sms ? ntiles : sms) >= 1, "lstm_bwd(tc): empty grid");
+    switch (NH) {
+        case 1: return launch_bwdt<1>(dhead, W_head, W_hh, W_ih, gates, c, cx0, dx, B, T, NH, fz, sms, stream);
+        case 2: return launch_bwdt<2>(dhead, W_head, W_hh, W_ih, gates, c, cx0, dx, B, T, NH, fz, sms, stream);
+        case 3: return launch_bwdt<3>(dhead, W_head, W_hh, W_ih, gates, c, cx0, dx, B, T, NH, fz, sms, stream);
+        default: return launch_bwdt<4>(dhead, W_head, W_hh, W_ih, gates, c, cx0, dx, B, T, NH, fz, sms, stream);
+    }
 }
 
 }  // namespace b200rl

@@ -1,0 +1,446 @@
+// The whole forward of the actor-critic in ONE persistent tcgen05 kernel (sm_100a):
+//
+//   x_t   = ReLU(Wt . obs_t + bt)                                             (torso, networks/models.py:67-69)
+//   pre_t = W_ih . x_t + W_hh . h_{t-1} + b_ih + b_hh ; LSTM cell             (nn.LSTMCell looped over T, models.py:71-75)
+//   head  = W_head . h_t + b_head                                             (value / logits heads, models.py:77-78)
+//
+// Round 1 ran this as three passes (lstm_xproj_tc -> lstm_fwdt -> head_fwd) with a 1 GB HBM round trip between the first two
+// (the input projection of ALL (b, t) parked in the `gates` buffer: 478 MB written, 539 MB read back) and a 134 MB re-read of h
+// by the third.  Here the input projection never leaves the SM:
+//
+//   * W_hh AND W_ih stay resident in tensor memory as the A operands of "weights as M" GEMMs D[256 x 32] (two M = 128 tiles:
+//     gates (i, f) and (g, o); N = 32 sequences): TF32 high parts 2 x 128 columns, low parts as bf16 pairs 2 x 64 columns,
+//     accumulators 4 x 32 columns -- exactly the 512 columns of an SM.
+//   * split precision as in the backward kernel: A_hi . B_hi + A_hi . B_lo in kind::tf32, the third term A_lo . B_hi (2^-11 of
+//     the result) in kind::f16 (bf16, K = 16): 20 MMAs per (tile, operand) instead of 24.
+//   * x_t is produced by the cell warps themselves, TWO steps ahead and off the critical path (4 FMAs per element from the
+//     Fin-wide observation), as a K-major B operand (hi / lo / bf16) in a double-buffered shared-memory slot; dedicated issuer
+//     warps run the input-projection MMAs of step t+1 into the accumulators WHILE the cell phase of step t runs (they only
+//     wait for the accumulators to have been read), so the recurrent MMAs of step t+1 -- the only ones on the serial chain --
+//     accumulate on top as soon as h_t is written.  The serial chain carries 40 MMAs per step instead of 48.
+//   * the heads: after a thread has handed h_t to the tensor core it multiplies its 4 cells by the head rows of its unit and the
+//     warp folds the 16 (sequence, output) sums with 16 shuffles; each unit-half warp stores its partial head (12.6 MB per
+//     update instead of re-reading 134 MB of h); head_combine_kernel adds the two halves and the bias.
+//
+// Register budget: 16 cell warps + 8 issuer warps = 768 threads = 80 registers each at launch; the issuer warp-groups give
+// theirs back (setmaxnreg.dec 40) and the cell warp-groups grow to 96 (setmaxnreg.inc); ptxas allocates per region.
+//
+// Layouts: gates (B, T, 64, 4) = post-activation (i, f, g, o) of a unit as one float4 ; c, h (B, T, 64) ; head_part
+// (B, T, 2, NH) ; everything a thread stores is a full 16-byte / 128-byte-per-warp line segment.
+#include "common.cuh"
+#include "tc05.cuh"
+#include "launchers.cuh"
+
+namespace b200rl {
+
+#ifdef B200RL_FWD3PROF
+__device__ unsigned long long g_fwd3prof[16];
+#define F3P_INIT unsigned long long f3p_prev = clock64();
+#define F3P(i, who) do { if (tid == (who)) { unsigned long long now_ = clock64(); atomicAdd(&g_fwd3prof[i], now_ - f3p_prev); f3p_prev = now_; } } while (0)
+#else
+#define F3P_INIT
+#define F3P(i, who) do { } while (0)
+#endif
+
+namespace ffk {
+constexpr int H = 64, TB = 32, MAXF = 8, MAXNH = 4;
+constexpr int NG = 4, RW = TB / NG, CT = RW / 2;          // sequence groups, sequences a warp reads, cells a thread owns
+#ifndef B200RL_FWD3_SEP
+#define B200RL_FWD3_SEP 1                                  // 1: separate issuer warps for the input projection (+ setmaxnreg) ; 0: the 4 recurrent issuers do both
+#endif
+constexpr int NI = 4;                                      // issuers per operand: (M tile) x (even / odd K-steps), one accumulator each
+constexpr int NIW = B200RL_FWD3_SEP ? 2 * NI : NI;         // issuer warps
+constexpr int NC = NG * 128, NT = NC + 32 * NIW;
+constexpr int TM_D = 0, TM_HH = 128, TM_IH = 256, TM_HHL = 384, TM_IHL = 448, TM_COLS = 512;
+constexpr int B_LBO = 144, B_SBO = 2304;                   // TF32 B operand: 16 core matrices (4 k) along K, 16-byte skew -> conflict-free 4-byte scatter
+constexpr int B_BYTES = (TB / 8) * B_SBO;                  // 9216 per hi / lo
+constexpr int C_LBO = 144, C_SBO = 1152;                   // bf16 B operand: 8 core matrices (8 k) along K
+constexpr int C_BYTES = (TB / 8) * C_SBO;                  // 4608
+constexpr int OP_BYTES = 2 * B_BYTES + C_BYTES;            // one operand set: hi | lo | bf16(hi)
+constexpr int EXF = 2 * NG * 2 * RW * 32;                  // swap buffer [pair][direction][slot][lane] floats
+constexpr int NBAR = 8;
+static_assert(15 * B_LBO + 128 <= B_SBO && 7 * C_LBO + 128 <= C_SBO, "core matrices of one 8-row group must fit below SBO");
+static_assert(RW == 8 && CT == 4, "cell phase layout");
+}  // namespace ffk
+
+static inline size_t fwd_fused_smem_bytes() {
+    return 3 * (size_t)ffk::OP_BYTES + sizeof(float) * (ffk::EXF + ffk::H * 4 + ffk::H * ffk::MAXF + ffk::H + ffk::H * 4) + 8 * ffk::NBAR + 64;
+}
+
+template <bool F4>
+__global__ void __launch_bounds__(ffk::NT, 1)
+lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0, const float* __restrict__ cx0,
+                      const float* __restrict__ Wt, const float* __restrict__ bt, const float* __restrict__ W_ih,
+                      const float* __restrict__ W_hh, const float* __restrict__ b_ih, const float* __restrict__ b_hh,
+                      const float* __restrict__ W_head, float* __restrict__ g_out, float* __restrict__ c_out,
+                      float* __restrict__ h_out, float* __restrict__ head_part, int B, int T, int Fin, int NH) {
+    using namespace ffk;
+    B200RL_DYN_SMEM(unsigned char, smem);
+    unsigned char* OPH = smem;                              // h_{t-1}: hi | lo | bf16
+    unsigned char* OPX = smem + OP_BYTES;                   // x_t: two sets
+    float* EX = reinterpret_cast<float*>(smem + 3 * OP_BYTES);
+    float* BI = EX + EXF;                                   // BI[j*4 + g] = b_ih[g*64+j] + b_hh[g*64+j]
+    float* WT = BI + H * 4;                                 // WT[j*8 + f]
+    float* BT = WT + H * MAXF;                              // bt[j]
+    float* WH = BT + H;                                     // WH[j*4 + o]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(WH + H * 4);
+    uint64_t* b_full = bars, *acc_done = bars + 1, *acc_free = bars + 2, *x_done = bars + 3, *x_full = bars + 4;   // x_full[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool compute = warp < NC / 32;
+
+    for (int i = tid; i < H * 4; i += NT) { const int j = i >> 2, g = i & 3; BI[i] = b_ih[g * H + j] + b_hh[g * H + j]; }
+    for (int i = tid; i < H * MAXF; i += NT) { const int j = i >> 3, f = i & 7; WT[i] = f < Fin ? Wt[j * Fin + f] : 0.f; }
+    for (int i = tid; i < H; i += NT) BT[i] = bt[i];
+    for (int i = tid; i < H * 4; i += NT) { const int j = i >> 2, o = i & 3; WH[i] = o < NH ? W_head[o * H + j] : 0.f; }
+    if (tid == 0) {
+        tc::mbar_init(b_full, NC / 32); tc::mbar_init(acc_done, NI); tc::mbar_init(acc_free, NC / 32); tc::mbar_init(x_done, NI);
+        tc::mbar_init(x_full, NC / 32); tc::mbar_init(x_full + 1, NC / 32);
+        tc::fence_mbar_init();
+    }
+    if (warp == NC / 32) tc::tmem_alloc(tmem_slot, TM_COLS);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    // one-time: W_hh and W_ih (PyTorch row order n = g*64 + j) -> tensor memory: thread = row n % 128 (its own TMEM lane),
+    // TF32 high parts one column per k, low parts as bf16 pairs (column c = k 2c | k 2c+1 << 16)
+    if (warp < 16) {
+        const int which = warp >> 3, mt = (warp >> 2) & 1, m = 32 * (warp & 3) + lane;
+        const float* wrow = (which ? W_ih : W_hh) + (size_t)(mt * 128 + m) * H;
+#ifdef B200RL_EMUL
+        const int st_lane = m;
+#else
+        const int st_lane = 32 * (warp & 3);
+#endif
+        for (int k0 = 0; k0 < H; k0 += 32) {
+            float lo16[16];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                float hi[16], lo[16];
+#pragma unroll
+                for (int e = 0; e < 16; e += 4) {
+                    const float4 w = ld4(wrow + k0 + hh * 16 + e);
+                    tc::split_tf32(w.x, hi[e], lo[e]); tc::split_tf32(w.y, hi[e + 1], lo[e + 1]);
+                    tc::split_tf32(w.z, hi[e + 2], lo[e + 2]); tc::split_tf32(w.w, hi[e + 3], lo[e + 3]);
+                }
+                tc::tmem_st16(tc::tmem_addr(tmem, st_lane, (which ? TM_IH : TM_HH) + mt * H + k0 + hh * 16), hi);
+#pragma unroll
+                for (int e = 0; e < 16; e += 2)
+                    lo16[hh * 8 + e / 2] = __uint_as_float((unsigned)tc::bf16_bits(lo[e]) | ((unsigned)tc::bf16_bits(lo[e + 1]) << 16));
+            }
+            tc::tmem_st16(tc::tmem_addr(tmem, st_lane, (which ? TM_IHL : TM_HHL) + mt * (H / 2) + k0 / 2), lo16);
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t idesc = tc::make_idesc_tf32(128, TB, false, false), idesc16 = tc::make_idesc_bf16(128, TB);
+    const int ntiles = (B + TB - 1) / TB;
+    const int my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long nsteps = (long long)my_tiles * T;
+
+    // 10 MMAs of one (M tile, K parity) share of D (+)= A . OP^T: A_hi . OP_lo, A_hi . OP_hi over 4 K-steps of 8, A_lo . OP_hi(bf16) over 2 of 16
+    auto issue = [&](uint32_t D, uint32_t Ahi, uint32_t Alo, const unsigned char* op, int kh, bool fresh) {
+#pragma unroll
+        for (int s = kh; s < H / 8; s += 2) {
+            const tc::SmemDesc bh = tc::make_desc(op + s * 2 * B_LBO, B_LBO, B_SBO);
+            const tc::SmemDesc bl = tc::make_desc(op + B_BYTES + s * 2 * B_LBO, B_LBO, B_SBO);
+            tc::mma_tf32_ts(D, Ahi + s * 8, bl, idesc, (fresh && s == kh) ? 0u : 1u);
+            tc::mma_tf32_ts(D, Ahi + s * 8, bh, idesc, 1u);
+        }
+#pragma unroll
+        for (int s = kh; s < H / 16; s += 2)
+            tc::mma_bf16_ts(D, Alo + s * 8, tc::make_desc(op + 2 * B_BYTES + s * 2 * C_LBO, C_LBO, C_SBO), idesc16, 1u);
+    };
+
+    if (!compute) {
+#if B200RL_FWD3_SEP && !defined(B200RL_EMUL)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+#endif
+        if (lane == 0) {
+            const int iw = warp - NC / 32;
+            const int ii = iw & (NI - 1), mt = ii >> 1, kh = ii & 1;
+            const uint32_t D = tmem + TM_D + ii * TB;
+            const uint32_t Ahh = tmem + TM_HH + mt * H, Ahhl = tmem + TM_HHL + mt * (H / 2);
+            const uint32_t Aih = tmem + TM_IH + mt * H, Aihl = tmem + TM_IHL + mt * (H / 2);
+#if B200RL_FWD3_SEP
+            if (iw >= NI) {                                  // input-projection issuer: runs one step ahead of the cell phase
+                uint32_t xc[2] = {0, 0};
+                long long N = 0;
+                for (int tl = 0; tl < my_tiles; ++tl)
+                    for (int t = 0; t < T; ++t, ++N) {
+                        const int p = t & 1;
+                        tc::mbar_wait(x_full + p, xc[p] & 1); ++xc[p];
+                        if (N > 0) tc::mbar_wait(acc_free, (uint32_t)(N - 1) & 1);
+                        tc::fence_after_sync();
+                        issue(D, Aih, Aihl, OPX + p * OP_BYTES, kh, true);
+                        tc::mma_commit(x_done);
+                    }
+            } else {
+                for (long long N = 0; N < nsteps; ++N) {
+                    tc::mbar_wait(b_full, (uint32_t)N & 1);  // h_{t-1} operand written
+                    tc::mbar_wait(x_done, (uint32_t)N & 1);  // the input projection of this step sits in the accumulator
+                    tc::fence_after_sync();
+                    issue(D, Ahh, Ahhl, OPH, kh, false);
+                    tc::mma_commit(acc_done);
+                }
+            }
+#else
+            uint32_t xc[2] = {0, 0};
+            long long N = 0;
+            for (int tl = 0; tl < my_tiles; ++tl)
+                for (int t = 0; t < T; ++t, ++N) {
+                    const int p = t & 1;
+                    tc::mbar_wait(x_full + p, xc[p] & 1); ++xc[p];
+                    if (N > 0) tc::mbar_wait(acc_free, (uint32_t)(N - 1) & 1);
+                    tc::fence_after_sync();
+                    issue(D, Aih, Aihl, OPX + p * OP_BYTES, kh, true);
+                    tc::mbar_wait(b_full, (uint32_t)N & 1);
+                    tc::fence_after_sync();
+                    issue(D, Ahh, Ahhl, OPH, kh, false);
+                    tc::mma_commit(acc_done);
+                }
+#endif
+        }
+    } else {
+#if B200RL_FWD3_SEP && !defined(B200RL_EMUL)
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+#endif
+        const int q = warp & 3, ch = warp >> 2;                // TMEM lane quarter, sequence group
+        const bool fo = q >= 2;                                // false: gates (i, g) ; true: gates (f, o)
+        const int half = q & 1;                                // which 32 of the 64 units
+        const int j = half * 32 + lane;                        // unit
+        const int pair = half + 2 * ch;
+        float* EXs = EX + pair * (2 * RW * 32) + (fo ? RW * 32 : 0);        // my outgoing slots [slot][lane]
+        const float* EXr = EX + pair * (2 * RW * 32) + (fo ? 0 : RW * 32);  // the partner's
+        const int rbase = ch * RW;                             // the RW sequences this warp reads from tensor memory
+        const int mine = fo ? CT : 0;                          // the CT of them this thread finishes
+#ifdef B200RL_EMUL
+        const int addr_lane = 32 * q + lane;
+#else
+        const int addr_lane = 32 * q;
+#endif
+        // element (sequence r, unit j) of a K-major operand set: TF32 hi/lo at tf(r), bf16 at bf(r)
+        auto tf = [&](int r) { return (r & 7) * 16 + (r >> 3) * B_SBO + (j & 3) * 4 + (j >> 2) * B_LBO; };
+        auto bf = [&](int r) { return 2 * B_BYTES + (r & 7) * 16 + (r >> 3) * C_SBO + (j & 7) * 2 + (j >> 3) * C_LBO; };
+        auto put = [&](unsigned char* op, int r, float v) {
+            float hi, lo;
+            tc::split_tf32(v, hi, lo);
+            *reinterpret_cast<float*>(op + tf(r)) = hi;
+            *reinterpret_cast<float*>(op + B_BYTES + tf(r)) = lo;
+            *reinterpret_cast<unsigned short*>(op + bf(r)) = tc::bf16_bits(hi);
+        };
+        const float4 bias = ld4(BI + j * 4);
+        uint32_t n = 0;
+        F3P_INIT
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int b0 = tile * TB;
+            auto seq = [&](int i) { const int b = b0 + rbase + mine + i; return b < B ? b : B - 1; };
+            auto rowof = [&](int i) { return (unsigned)seq(i) * (unsigned)T; };       // B*T < 2^31 (checked by the launcher)
+            // torso output x[seq i][unit j] at step tt into operand set tt & 1
+            float4 ob[CT];                                     // (F4) observations of the step whose x is produced next
+            auto load_obs = [&](int tt) {
+                if (F4) {
+#pragma unroll
+                    for (int i = 0; i < CT; ++i) ob[i] = ld4(u + (size_t)(rowof(i) + tt) * 4);
+                }
+            };
+            auto make_x = [&](int tt) {
+                unsigned char* op = OPX + (tt & 1) * OP_BYTES;
+                const float btj = BT[j];
+                if (F4) {
+                    const float4 w = ld4(WT + j * MAXF);
+#pragma unroll
+                    for (int i = 0; i < CT; ++i) {
+                        const float x = fmaf(w.x, ob[i].x, fmaf(w.y, ob[i].y, fmaf(w.z, ob[i].z, fmaf(w.w, ob[i].w, btj))));
+                        put(op, rbase + mine + i, fmaxf(x, 0.f));
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < CT; ++i) {
+                        const float* orow = u + (size_t)(rowof(i) + tt) * Fin;
+                        float x = btj;
+                        for (int f = 0; f < Fin; ++f) x = fmaf(WT[j * MAXF + f], __ldg(orow + f), x);
+                        put(op, rbase + mine + i, fmaxf(x, 0.f));
+                    }
+                }
+            };
+            float cst[CT];
+#pragma unroll
+            for (int i = 0; i < CT; ++i) {
+                const size_t b = (size_t)seq(i);
+                cst[i] = cx0[b * H + j];
+                put(OPH, rbase + mine + i, hx0[b * H + j]);
+            }
+            load_obs(0);
+            make_x(0);
+            tc::fence_async_smem();
+            tc::fence_before_sync();
+            tc::mbar_arrive_warp(x_full);
+            tc::mbar_arrive_warp(b_full);
+            if (T > 1) {
+                load_obs(1);
+                make_x(1);
+                tc::fence_async_smem();
+                tc::mbar_arrive_warp(x_full + 1);
+            }
+            if (T > 2) load_obs(2);
+
+            for (int t = 0; t < T; ++t, ++n) {
+                F3P(0, 0);
+                tc::mbar_wait(acc_done, n & 1);
+                tc::fence_after_sync();
+                F3P(1, 0);
+                float xa[RW], xb[RW];
+                {                                                       // gate i (or f) / g (or o) of unit j, RW sequences: even + odd K-step partials
+                    uint32_t u0[RW], u1[RW], u2[RW], u3[RW];            // four loads in flight, one wait
+                    tc::tmem_ld8_async(tc::tmem_addr(tmem, addr_lane, TM_D + 0 * TB + rbase), u0);
+                    tc::tmem_ld8_async(tc::tmem_addr(tmem, addr_lane, TM_D + 1 * TB + rbase), u1);
+                    tc::tmem_ld8_async(tc::tmem_addr(tmem, addr_lane, TM_D + 2 * TB + rbase), u2);
+                    tc::tmem_ld8_async(tc::tmem_addr(tmem, addr_lane, TM_D + 3 * TB + rbase), u3);
+                    tc::tmem_ld_wait();
+                    tc::fence_before_sync();
+                    tc::mbar_arrive_warp(acc_free);                     // the accumulators may take the next step's input projection
+#pragma unroll
+                    for (int r = 0; r < RW; ++r) {
+                        xa[r] = __uint_as_float(u0[r]) + __uint_as_float(u1[r]);
+                        xb[r] = __uint_as_float(u2[r]) + __uint_as_float(u3[r]);
+                    }
+                }
+                F3P(2, 0);
+#pragma unroll
+                for (int i = 0; i < CT; ++i) { EXs[(2 * i) * 32 + lane] = fo ? xa[i] : xa[CT + i]; EXs[(2 * i + 1) * 32 + lane] = fo ? xb[i] : xb[CT + i]; }
+                tc::named_bar_sync(1 + pair, 64);
+                F3P(3, 0);
+                float4 gsv[CT]; float hsv[CT];                          // saved activations: stored to HBM AFTER the step is handed to the issuers
+#pragma unroll
+                for (int i = 0; i < CT; ++i) {
+                    const float pa = EXr[(2 * i) * 32 + lane], pb = EXr[(2 * i + 1) * 32 + lane];
+                    float ig, fg, gg, og;                                   // 8 MUFU per cell: (i, g) and (f, o) share a reciprocal each, tanh(c) takes two
+                    sigm_tanh((fo ? pa : xa[i]) + bias.x, (fo ? pb : xb[i]) + bias.z, ig, gg);
+                    sigm_sigm((fo ? xa[CT + i] : pa) + bias.y, (fo ? xb[CT + i] : pb) + bias.w, fg, og);
+                    const float cn = fmaf(fg, cst[i], ig * gg);
+                    const float hh = og * tanh_(cn);
+                    cst[i] = cn;
+                    gsv[i] = make_float4(ig, fg, gg, og); hsv[i] = hh;
+                    put(OPH, rbase + mine + i, hh);
+                }
+                F3P(4, 0);
+                if (t + 1 < T) {
+                    tc::fence_async_smem();
+                    tc::fence_before_sync();
+                    tc::mbar_arrive_warp(b_full);
+                }
+                F3P(5, 0);
+                // ---- off the serial chain from here: the tensor core is running step t+1
+#pragma unroll
+                for (int i = 0; i < CT; ++i) {
+                    if (b0 + rbase + mine + i < B) {
+                        const size_t o = (size_t)(rowof(i) + t) * H + j;
+                        st4(g_out + o * 4, gsv[i]);
+                        c_out[o] = cst[i]; h_out[o] = hsv[i];
+                    }
+                }
+                if (t + 2 < T) {                                        // x of step t+2 (its set was last read by the MMAs of step t: done)
+                    make_x(t + 2);
+                    tc::fence_async_smem();
+                    tc::mbar_arrive_warp(x_full + (t & 1));
+                    if (t + 3 < T) load_obs(t + 3);
+                }
+                if (head_part != nullptr) {
+                    // heads: v[i*4 + o] = h[seq i][j] * W_head[o][j], folded over the warp's 32 units: lane l ends with slot (l >> 1) & 15
+                    const float4 wh = ld4(WH + j * 4);
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < CT; ++i) { v[i * 4] = hsv[i] * wh.x; v[i * 4 + 1] = hsv[i] * wh.y; v[i * 4 + 2] = hsv[i] * wh.z; v[i * 4 + 3] = hsv[i] * wh.w; }
+#pragma unroll
+                    for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+                        const bool up = (lane & bit) != 0;
+#pragma unroll
+                        for (int k = 0; k < w; ++k) {
+                            const float send = up ? v[k] : v[k + w], keep = up ? v[k + w] : v[k];
+                            v[k] = keep + __shfl_xor_sync(kFull, send, bit);
+                        }
+                    }
+                    v[0] += __shfl_xor_sync(kFull, v[0], 1);
+                    const int slot = (lane >> 1) & 15, si = slot >> 2, so = slot & 3;
+                    if ((lane & 1) == 0 && so < NH && b0 + rbase + mine + si < B)
+                        head_part[((size_t)(rowof(si) + t) * 2 + half) * NH + so] = v[0];
+                }
+                F3P(6, 0);
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == NC / 32) tc::tmem_dealloc(tmem, TM_COLS);
+}
+
+// head_out[r][o] = part[r][0][o] + part[r][1][o] + b_head[o]
+__global__ void __launch_bounds__(256)
+head_combine_kernel(const float* __restrict__ part, const float* __restrict__ b_head, float* __restrict__ head_out, long long n, int NH) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / NH;
+        const int o = (int)(i - r * NH);
+        head_out[i] = part[(r * 2) * NH + o] + part[(r * 2 + 1) * NH + o] + b_head[o];
+    }
+}
+
+int launch_fwd_fused(const float* u, const float* hx0, const float* cx0, const float* Wt, const float* bt, const float* W_ih,
+                     const float* W_hh, const float* b_ih, const float* b_hh, const float* W_head, const float* b_head,
+                     float* gates, float* c, float* h, float* head_part, float* head_out,
+                     int B, int T, int Fin, int NH, int sms, void* stream) {
+    B200RL_REQUIRE((long long)B * T < (1LL << 31), "lstm_fwd_fused: B*T must be below 2^31");
+    B200RL_REQUIRE(Fin >= 1 && Fin <= ffk::MAXF, "lstm_fwd_fused: Fin=%d out of range [1,%d]", Fin, ffk::MAXF);
+    B200RL_REQUIRE(head_part == nullptr || (NH >= 1 && NH <= ffk::MAXNH && head_out != nullptr), "lstm_fwd_fused: fused heads need 1 <= NH <= %d", ffk::MAXNH);
+    const int ntiles = (B + ffk::TB - 1) / ffk::TB;
+    const size_t smem = fwd_fused_smem_bytes();
+    const int grid = ntiles < sms ? ntiles : sms;
+    if (Fin == 4) {
+#ifndef B200RL_EMUL
+        cudaError_t e = cudaFuncSetAttribute(lstm_fwd_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error("lstm_fwd_fused: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+#endif
+        B200RL_LAUNCH(lstm_fwd_fused_kernel<true>, grid, ffk::NT, smem, stream, u, hx0, cx0, Wt, bt, W_ih, W_hh, b_ih, b_hh, W_head,
+                      gates, c, h, head_part, B, T, Fin, NH);
+    } else {
+#ifndef B200RL_EMUL
+        cudaError_t e = cudaFuncSetAttribute(lstm_fwd_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error("lstm_fwd_fused: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+#endif
+        B200RL_LAUNCH(lstm_fwd_fused_kernel<false>, grid, ffk::NT, smem, stream, u, hx0, cx0, Wt, bt, W_ih, W_hh, b_ih, b_hh, W_head,
+                      gates, c, h, head_part, B, T, Fin, NH);
+    }
+    if (check_launch("lstm_fwd_fused")) return 1;
+    if (head_part != nullptr) {
+        const long long n = (long long)B * T * NH;
+        const long long g = (n + 255) / 256;
+        B200RL_LAUNCH(head_combine_kernel, (int)(g > 148 * 8 ? 148 * 8 : g), 256, 0, stream, head_part, b_head, head_out, n, NH);
+        return check_launch("head_combine");
+    }
+    return 0;
+}
+
+}  // namespace b200rl
+
+using namespace b200rl;
+
+extern "C" int b200rl_lstm_fwd_fused(const float* u, const float* hx0, const float* cx0,
+                                     const float* Wt, const float* bt, const float* W_ih, const float* W_hh,
+                                     const float* b_ih, const float* b_hh, const float* W_head, const float* b_head,
+                                     float* gates, float* c, float* h, float* head_part, float* head_out,
+                                     int B, int T, int Fin, int NH, void* stream) {
+    B200RL_REQUIRE(B >= 1 && T >= 1, "lstm_fwd_fused: bad shape B=%d T=%d", B, T);
+    int sms = 148;
+#ifndef B200RL_EMUL
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+#else
+    sms = 4;
+#endif
+    return launch_fwd_fused(u, hx0, cx0, Wt, bt, W_ih, W_hh, b_ih, b_hh, W_head, b_head, gates, c, h, head_part, head_out,
+                            B, T, Fin, NH, sms, stream);
+}

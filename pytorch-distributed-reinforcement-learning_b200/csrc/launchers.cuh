@@ -17,6 +17,11 @@ int launch_xproj_tc(const float* u, const float* Wt, const float* bt, const floa
 // fwd_tc.cu: recurrent LSTM forward with the per-step GEMM on tcgen05; xg = xproj (i,g,f,o) in, saved activations out
 int launch_fwd_tc(float* xg, const float* hx0, const float* cx0, const float* W_hh, float* c, float* h,
                   int B, int T, int sms, void* stream);
+// fwd_fused.cu: torso + input projection + recurrence (+ heads) in one persistent tcgen05 kernel
+int launch_fwd_fused(const float* u, const float* hx0, const float* cx0, const float* Wt, const float* bt, const float* W_ih,
+                     const float* W_hh, const float* b_ih, const float* b_hh, const float* W_head, const float* b_head,
+                     float* gates, float* c, float* h, float* head_part, float* head_out,
+                     int B, int T, int Fin, int NH, int sms, void* stream);
 // fwd_tc2.cu: the same with two 16-sequence groups per CTA in ping-pong (tensor core of one group under the cell phase of the other)
 int launch_fwd_tc2(float* xg, const float* hx0, const float* cx0, const float* W_hh, float* c, float* h,
                    int B, int T, int sms, void* stream);
@@ -28,4 +33,9 @@ int launch_torso_from_dx(const float* dx, const float* u, const float* Wt, const
 // bwd_tc.cu: serial BPTT with dh_rec and dx = dpre . W_ih as one tcgen05 accumulation per step
 int launch_bwd_tc(const float* dhead, const float* W_head, const float* W_hh, const float* W_ih, float* gates,
                   const float* c, const float* cx0, float* dx, int B, int T, int NH, int sms, void* stream);
+// bwd_tc.cu: the same with the head (dW_head, db_head) and torso (dWt, dbt) gradients accumulated in the kernel (one slab row per CTA)
+int launch_bwd_tc_fused(const float* dhead, const float* W_head, const float* W_hh, const float* W_ih, float* gates,
+                        const float* c, const float* cx0, float* dx, const float* u, const float* Wt, const float* bt,
+                        float* partials, long long P, long long off_Wt, long long off_bt, long long off_Whead, long long off_bhead,
+                        int B, int T, int Fin, int NH, int sms, void* stream);
 }  // namespace b200rl

@@ -1135,6 +1135,18 @@ extern "C" int b200rl_lstm_bwd(const float* dhead, const float* W_head, const fl
     return check_launch("lstm_bwd");
 }
 
+extern "C" int b200rl_lstm_bwd_fused(const float* dhead, const float* W_head, const float* W_hh, const float* W_ih,
+                                     float* gates, const float* c, const float* cx0, const float* u, const float* Wt, const float* bt,
+                                     float* partials, int nparts, long long P, long long off_Wt, long long off_bt,
+                                     long long off_Whead, long long off_bhead, int B, int T, int Fin, int NH, void* stream) {
+    B200RL_REQUIRE(B >= 1 && T >= 1, "lstm_bwd_fused: bad shape B=%d T=%d", B, T);
+    B200RL_REQUIRE(partials != nullptr, "lstm_bwd_fused: needs the partial-gradient slabs");
+    const int ntiles = (B + 31) / 32;
+    B200RL_REQUIRE(nparts >= (ntiles < sm_count() ? ntiles : sm_count()), "lstm_bwd_fused: nparts=%d below the grid size", nparts);
+    return launch_bwd_tc_fused(dhead, W_head, W_hh, W_ih, gates, c, cx0, nullptr, u, Wt, bt, partials, P, off_Wt, off_bt, off_Whead, off_bhead,
+                               B, T, Fin, NH, sm_count(), stream);
+}
+
 extern "C" int b200rl_lstm_wgrad(const float* dpre, const float* h, const float* hx0, const float* u,
                                  const float* dhead, const float* Wt, const float* bt, const float* W_ih,
                                  float* partials, int nparts, long long P,
@@ -1144,13 +1156,18 @@ extern "C" int b200rl_lstm_wgrad(const float* dpre, const float* h, const float*
     B200RL_REQUIRE(B >= 1 && T >= 1, "lstm_wgrad: bad shape B=%d T=%d", B, T);
     B200RL_REQUIRE(Fin >= 1 && Fin <= MAXF && NH >= 1 && NH <= B200RL_MAX_HEADS, "lstm_wgrad: Fin=%d NH=%d out of range", Fin, NH);
     B200RL_REQUIRE(H * Fin <= WG_E * NT && NH * H <= WG_E * NT, "lstm_wgrad: head/torso too wide");
-    B200RL_REQUIRE(variant >= 0 && variant <= 3, "lstm_wgrad: unknown variant %d", variant);
+    B200RL_REQUIRE(variant >= 0 && variant <= 4, "lstm_wgrad: unknown variant %d", variant);
     B200RL_REQUIRE(nparts >= 1, "lstm_wgrad: nparts=%d", nparts);
     B200RL_REQUIRE((off_Wih % 4) == 0 && (off_Whh % 4) == 0 && (P % 4) == 0, "lstm_wgrad: W_ih/W_hh offsets and P must be multiples of 4 floats");
     const size_t smem = wgrad_smem_bytes(Fin, NH);
     // wgrad_tc runs two CTAs per SM and takes every slab; the other kernels of the stage fill an SM with one CTA and use the
     // first sm_count slabs (their entries in the remaining slabs stay zero, as allocated)
     const int np_misc = nparts < sm_count() ? nparts : sm_count();
+    if (variant == 4) {
+        // lstm_bwd_fused already accumulated the head and torso gradients: only dW_ih / dW_hh / db_ih / db_hh are left
+        B200RL_REQUIRE((long long)nparts * 32 <= (long long)B * T + 31, "lstm_wgrad: nparts=%d exceeds the number of 32-row stages", nparts);
+        return launch_wgrad_tc(dpre, h, hx0, u, Wt, bt, partials, nparts, P, off_Wih, off_Whh, off_bih, off_bhh, B, T, Fin, stream);
+    }
     if (variant == 3) {
         // dx was already produced by lstm_bwd variant 1: tcgen05 dW + a bandwidth-bound torso pass over dx
         B200RL_REQUIRE(dx != nullptr && du == nullptr, "lstm_wgrad: variant 3 needs dx (from lstm_bwd variant 1) and does not produce du");

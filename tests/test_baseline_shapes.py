@@ -142,18 +142,30 @@ def test_vmpo_eight_shards_match_oracle_at_cfg4_shape():
     W = CM.LoopbackWorld(world, dev)
     out, errs = [None] * world, []
 
+    warm = threading.Lock()
+
     def rank_main(r):
         try:
             torch.cuda.set_device(dev)
             with torch.cuda.stream(torch.cuda.Stream(dev)):
+                sh = B // world
+                shards = [{k: v[r * sh:(r + 1) * sh].contiguous().to(dev) for k, v in fulls[i].items()} for i in range(2)]
+                # (one process, one device: allocations / lazy kernel loads synchronise the device and would wait for a peer
+                # kernel that spins -- see test_peer_step_loopback_equals_full_batch: solo warm-up first, then start together)
+                with warm:
+                    scratch = M.MlpLSTMSingle(4, 2, T, 64).to(dev)
+                    VMPOEngine(scratch.actor, oracle.DEFAULT_HYPER).update(shards[0], coefs[0])
+                    torch.cuda.current_stream().synchronize()
+                    del scratch
                 model = M.MlpLSTMSingle(4, 2, T, 64)
                 model.actor.load_state_dict(sd)
                 model = model.to(dev)
                 eng = VMPOEngine(model.actor, oracle.DEFAULT_HYPER, comm=W.comm(r))
-                sh = B // world
+                eng._workspace(sh, T)
+                eng._vm_workspace(sh, T)
+                W.comm(r).barrier()
                 for i in range(2):
-                    shard = {k: v[r * sh:(r + 1) * sh].contiguous().to(dev) for k, v in fulls[i].items()}
-                    eng.update(shard, coefs[i])
+                    eng.update(shards[i], coefs[i])
                 L = eng.losses()
                 out[r] = (_flat_sd_order(model.actor, eng.flat), L)
         except Exception as e:  # noqa: BLE001

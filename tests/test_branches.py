@@ -346,7 +346,8 @@ def test_pipelined_loop_publishes_before_waiting_for_the_next_batch(tmp_path):
         await asyncio.gather(learn_ppo(learner, ExecutionTimer(num_transition=B * T)), feeder(q))
 
     asyncio.run(go())
-    assert events == ["get", "pub", "get", "pub", "get", "pub"], events
+    # (after the third publish the loop polls the queue once more, sees the stop flag and leaves)
+    assert events[:6] == ["get", "pub", "get", "pub", "get", "pub"] and events[6:] in ([], ["get"]), events
 
 
 # ------------------------------------------------------------------------------------------------ V-MPO top-k ties
@@ -398,16 +399,29 @@ def test_peer_step_loopback_equals_full_batch(world):
     W = CM.LoopbackWorld(world, dev)
     out, errs = [None] * world, []
 
+    warm = threading.Lock()
+
     def rank_main(r):
         try:
             torch.cuda.set_device(dev)
             with torch.cuda.stream(torch.cuda.Stream(dev)):
+                sh = B // world
+                shard = {k: v[r * sh:(r + 1) * sh].contiguous().to(dev) for k, v in full.items()}
+                # One process, one device: a cudaMalloc or a lazy kernel load in rank A synchronises the DEVICE and would wait
+                # for rank B's peer kernel, which spins until A announces -- so every rank first runs a solo update of the same
+                # shapes (kernels loaded, allocator pool of this stream filled), then all ranks start together.  (A real job is
+                # one process per GPU and has no such coupling.)
+                with warm:
+                    scratch = M.MlpLSTMSingle(f, A, T, 64).to(dev)
+                    OnPolicyEngine(scratch.actor, "PPO", oracle.DEFAULT_HYPER).update(shard)
+                    torch.cuda.current_stream().synchronize()
+                    del scratch
                 model = M.MlpLSTMSingle(f, A, T, 64)
                 model.actor.load_state_dict(sd)
                 model = model.to(dev)
                 eng = OnPolicyEngine(model.actor, "PPO", oracle.DEFAULT_HYPER, comm=W.comm(r))
-                sh = B // world
-                shard = {k: v[r * sh:(r + 1) * sh].contiguous().to(dev) for k, v in full.items()}
+                eng._workspace(sh, T)
+                W.comm(r).barrier()
                 for _ in range(3):
                     eng.update(shard)
                 L = eng.losses()
