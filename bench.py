@@ -295,6 +295,69 @@ class Timed:
         return float(ms.item())
 
 
+def e2e_from_shared_memory(dev, world, dist, timed, batch, n):
+    """`n` learner iterations fed from real shared-memory arrays through the learner's own two coroutines."""
+    import numpy as np
+    from b200rl.agents.learner import LearnerSinglePPO
+    from b200rl.agents.storage_module.shared_batch import reset_shared_on_policy_memory
+    from b200rl.networks.models import MlpLSTMSingle
+    args = hyper_args(dev)
+    shm = reset_shared_on_policy_memory(args, [F])
+    for k in ("obs", "act", "rew", "logits", "log_prob", "is_fir", "hx", "cx"):
+        v = np.frombuffer(shm[f"{k}_batch"][0].get_obj(), dtype=np.float32)
+        src = batch[k]
+        if k in ("hx", "cx"):                                  # the storage process keeps the (T, H) trajectory of states per slot
+            src = src[:, None, :].expand(-1, T, -1)
+        v[:] = src.reshape(-1).numpy()
+
+    class Stop:
+        flag = False
+
+        def is_set(self):
+            return self.flag
+
+    stop = Stop()
+    torch.manual_seed(0)
+    learner = LearnerSinglePPO(args, None, MlpLSTMSingle(F, A, T, H), shm, stop, None, None, [F])
+    learner.args.loss_log_interval = 1
+    learner.log_loss_tensorboard = lambda *a: None
+    state = {"pubs": 0, "target": 0}
+
+    def pub(sd):
+        state["pubs"] += 1
+        if state["pubs"] >= state["target"]:
+            stop.flag = True
+    learner.pub_model = pub
+
+    async def storage():                                       # an always-ready storage process: the batch is "collected" again at once
+        while not stop.flag:
+            if learner.sh_data_num.value == 0:
+                learner.sh_data_num.value = B
+            await asyncio.sleep(0)
+
+    def run(k):
+        stop.flag, state["pubs"], state["target"] = False, 0, k
+        learner.sh_data_num.value = B
+
+        async def go():
+            await asyncio.gather(learner.learning_chain_ppo(), storage())
+        asyncio.run(go())
+
+    run(3)
+    timed.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run(n)
+    e1.record()
+    timed.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    zero_copy = learner.zero_copy
+    del learner
+    return float(ms.item()), n
+
+
 def dp_parity(dev, rank, world, pg):
     """Sharded updates over the real communicator (NCCL group + NVLink peer kernels) vs the full-batch oracle, small shapes:
     PPO (one fused exchange), V-MPO (all-gather of the advantages + global top-k), SAC-Continuous (two dependent exchanges)."""
@@ -512,8 +575,13 @@ def main():
     n_pg = min(n_e2e, 50)
     pageable = [tuple(t.clone() for t in p) for p in pinned]
     ms3 = e2e_leg(pageable, n_pg)
+    # the whole seam from the storage side: rollouts sit in the shared-memory arrays `LearnerStorage.make_batch` fills
+    # (agents/learner_storage.py:123-159); `learning_chain_ppo`'s two coroutines take them from there.  The arrays are
+    # page-locked once (cudaHostRegister), every batch is DMA'd straight out of the slots, and the slot counter is handed back to
+    # the (here emulated: always-ready) storage process as soon as the copy engine has read them.
+    shm_ms, n_shm = e2e_from_shared_memory(dev, world, dist, timed, host[0], min(n_e2e, 100))
     if rank == 0:
-        log(f"e2e leg done: {ms2 / n_e2e:.3f} ms/step pinned, {ms3 / n_pg:.3f} ms/step pageable")
+        log(f"e2e leg done: {ms2 / n_e2e:.3f} ms/step pinned, {ms3 / n_pg:.3f} ms/step pageable, {shm_ms / n_shm:.3f} ms/step from shared memory")
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -523,7 +591,9 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": n_e2e, "api": "b200rl.agents.learner_module.ppo.learning.learning(parent, timer)",
                 "host_batches": "pinned",
-                "pageable_value": world * B * T * n_pg / (ms3 * 1e-3), "pageable_steps": n_pg},
+                "pageable_value": world * B * T * n_pg / (ms3 * 1e-3), "pageable_steps": n_pg,
+                "shared_memory_value": world * B * T * n_shm / (shm_ms * 1e-3), "shared_memory_steps": n_shm,
+                "shared_memory_api": "LearnerSinglePPO.learning_chain_ppo(): put_batch_to_batch_q (page-locked shm slots -> DMA) + learning()"},
         "loss": losses["loss"],
         "exchange": ("fused peer step (one-shot NVLink all-reduce + clip + RMSprop, csrc/peer_kernels.cu)"
                      if eng.chan is not None else "NCCL all-reduce + single-CTA clip/RMSprop"),

@@ -14,6 +14,7 @@ for, so the learner update can be driven without them (the benchmark isolates th
 from workers, as BASELINE.json's north_star asks).
 """
 import asyncio
+import os
 import pickle
 
 import numpy as np
@@ -53,8 +54,11 @@ class LearnerBase(SMInterFace):
         self.pub_socket = None
         if learner_ip is not None:
             self.zeromq_set(learner_ip, learner_port)
+        self.zero_copy = False               # shared arrays page-locked: batches are DMA'd straight out of the storage slots
         if shm_ref is not None:
             self.get_shared_memory_interface()
+            if self.device.type == "cuda" and os.environ.get("B200RL_ZERO_COPY", "1") != "0":
+                self.zero_copy = self.register_pinned()
         self.writer = None
         if getattr(args, "result_dir", None) is not None:
             from tensorboardX import SummaryWriter
@@ -64,6 +68,11 @@ class LearnerBase(SMInterFace):
     def __del__(self):
         if getattr(self, "pub_socket", None) is not None:
             self.pub_socket.close()
+        if getattr(self, "zero_copy", False):
+            try:
+                self.unregister_pinned()
+            except Exception:  # noqa: BLE001  (interpreter shutdown)
+                pass
 
     # ------------------------------------------------------------------ transport
     def zeromq_set(self, learner_ip, learner_port):
@@ -107,10 +116,11 @@ class LearnerBase(SMInterFace):
                 w.add_scalar(f"{k}-transition-per-secs", sum(v) / (len(v) + 1e-6), self.idx)
 
     # ------------------------------------------------------ shared memory -> batch
-    def sample_batch_from_sh_memory(self, sampling_method):
-        """The 8-tuple (obs, act, rew, logits, log_prob, is_fir, hx, cx) of fresh host
-        tensors (reference learner.py:168-233).  `hx`/`cx` are returned as (B, H): only
-        `[:, 0]` of the stored (B, T, H) is ever read by the update."""
+    def sample_batch_from_sh_memory(self, sampling_method, copy=True):
+        """The 8-tuple (obs, act, rew, logits, log_prob, is_fir, hx, cx) of host tensors (reference learner.py:168-233).
+        `hx`/`cx` are returned as (B, H): only `[:, 0]` of the stored (B, T, H) is ever read by the update.  `copy=True` is
+        the reference's defensive copy (fresh tensors); `copy=False` (on-policy only) returns VIEWS of the shared arrays for
+        the zero-copy path -- the caller must not reset the slot counter before it has shipped them."""
         assert sampling_method in ("on-policy", "off-policy")
         sq, bn, sha = self.args.seq_len, self.args.batch_size, self.obs_shape
         hs, ac, buf = self.args.hidden_size, self.args.action_space, self.args.buffer_size
@@ -128,7 +138,10 @@ class LearnerBase(SMInterFace):
             view = getattr(self, f"sh_{name}_batch").reshape((num, sq, *w))[idx]
             if name in ("hx", "cx"):
                 view = view[:, 0]
-            out.append(to_torch(np.array(view, dtype=np.float32, copy=True)))
+            if copy or sampling_method == "off-policy":
+                out.append(to_torch(np.array(view, dtype=np.float32, copy=True)))
+            else:
+                out.append(torch.from_numpy(view))
         return tuple(out)
 
     def is_sh_ready(self):
@@ -137,7 +150,22 @@ class LearnerBase(SMInterFace):
     async def put_batch_to_batch_q(self):
         while not self.stop_event.is_set():
             if self.is_sh_ready():
-                await self.batch_queue.put(self.sample_batch_from_sh_memory(sampling_method="on-policy"))
+                if self.zero_copy:
+                    # DMA straight out of the page-locked slots on the copy stream; the slots go back to the storage process
+                    # (counter reset) as soon as the copy engine has read them -- the queue carries device-resident batches
+                    views = self.sample_batch_from_sh_memory(sampling_method="on-policy", copy=False)
+                    shipped = self.to_gpu.ship(*views)
+                    while shipped is None and not self.stop_event.is_set():      # ring full: the learner is behind
+                        await asyncio.sleep(0.0005)
+                        shipped = self.to_gpu.ship(*views)
+                    if shipped is None:
+                        break
+                    dev, ev = shipped
+                    while not ev.query():
+                        await asyncio.sleep(0)
+                    await self.batch_queue.put(dev)
+                else:
+                    await self.batch_queue.put(self.sample_batch_from_sh_memory(sampling_method="on-policy"))
                 self.reset_data_num()
             await asyncio.sleep(0.001)
 

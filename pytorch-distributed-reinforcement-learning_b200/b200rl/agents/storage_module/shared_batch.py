@@ -49,3 +49,29 @@ class SMInterFace:
 
     def reset_data_num(self):
         self.sh_data_num.value = 0
+
+    # ---- page-locking the shared arrays: the learner's DMA engine reads rollouts straight out of the slots the storage
+    # process wrote instead of a defensive copy + a staging copy per batch
+    def register_pinned(self):
+        """cudaHostRegister every field array (idempotent).  Returns True when all of them are page-locked."""
+        import torch
+        if getattr(self, "_registered", None):
+            return True
+        rt = torch.cuda.cudart()
+        done = []
+        for key in ("obs", "act", "rew", "logits", "log_prob", "is_fir", "hx", "cx"):
+            a = getattr(self, f"sh_{key}_batch")
+            err = rt.cudaHostRegister(a.ctypes.data, a.nbytes, 0)
+            if int(err) != 0:
+                for p in done:
+                    rt.cudaHostUnregister(p)
+                return False
+            done.append(a.ctypes.data)
+        self._registered = done
+        return True
+
+    def unregister_pinned(self):
+        import torch
+        for p in getattr(self, "_registered", None) or []:
+            torch.cuda.cudart().cudaHostUnregister(p)
+        self._registered = None

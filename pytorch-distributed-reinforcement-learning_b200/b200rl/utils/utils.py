@@ -103,12 +103,17 @@ class HostStager:
         self.device = torch.device(device)
         if self.device.type == "cuda" and self.device.index is None:      # reference-style 'cuda': tensors report cuda:<index>
             self.device = torch.device("cuda", torch.cuda.current_device())
-        self.pinned = [{}, {}]
-        self._h2d_done = [None, None]    # per set: event after the last async H2D that READ this set's pinned staging buffers
-        self.devbuf = [{}, {}]
-        self._released = [None, None]    # compute-stream events: set k may be overwritten once this has happened
+        # buffer sets: 0 / 1 = the learner-side double buffer (prefetch / __call__), ("ring", k) = the feeder-side ring (ship)
+        self.pinned = defaultdict(dict)
+        self._h2d_done = {}              # per set: event after the last async H2D that READ this set's pinned staging buffers
+        self.devbuf = defaultdict(dict)
+        self._released = {}              # compute-stream events: set k may be overwritten once this has happened
         self.flip = 0
         self._in_use = None              # buffer set the learner is currently reading
+        self.ring_size = 3
+        self._ring_busy = set()          # ring slots shipped and not yet released by the learner
+        self._ring_next = 0
+        self._ring_lookup = {}           # data_ptr of a shipped batch's first tensor -> (slot, copy event, bytes)
         self.bytes_last = 0
         self.skip = set()            # fields the algorithm never reads (not shipped)
         self._pending = None         # (id of host tuple, host tuple, device tuple, event, nbytes)
@@ -126,7 +131,7 @@ class HostStager:
     def _wait_staging_free(self, slot):
         """The host is about to overwrite set `slot`'s pinned staging buffers: the async H2D that last read them must have
         finished (`_released` only orders the DEVICE buffers; without this a slow copy could ship a half-overwritten batch)."""
-        ev = self._h2d_done[slot]
+        ev = self._h2d_done.get(slot)
         if ev is not None:
             ev.synchronize()
             self._h2d_done[slot] = None
@@ -171,6 +176,8 @@ class HostStager:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(self.device))
             self._released[self._in_use] = ev
+            if isinstance(self._in_use, tuple):              # a ring slot: the feeder may ship into it again
+                self._ring_busy.discard(self._in_use[1])
 
     def prefetch(self, *batch_args):
         if self.device.type != "cuda" or self._pending is not None:
@@ -182,15 +189,55 @@ class HostStager:
             return
         self.flip = slot
         with torch.cuda.stream(self._copy_stream):
-            if self._released[slot] is not None:
+            if self._released.get(slot) is not None:
                 self._copy_stream.wait_event(self._released[slot])
             dev, nbytes = self._ship(batch_args, slot)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
         self._pending = (id(batch_args), batch_args, dev, ev, nbytes, slot)
 
+    # ------------------------------------------------------------------ feeder side: zero-copy shipping
+    def ship(self, *batch_args):
+        """Start the H2D of a host batch on the copy stream into the next free slot of a small ring of persistent device buffer
+        sets and return (device tuple, copy event) -- or None when every slot still holds a batch the learner has not consumed
+        (back-pressure).  Meant for the BATCHING coroutine: with the shared-memory arrays page-locked
+        (`SMInterFace.register_pinned`) the contiguous fields are DMA'd straight out of the slots the storage process wrote --
+        no defensive host copy, no staging copy -- and the coroutine resets the slot counter once the event has fired.  The
+        tuple is later recognised by `stager(*tuple)`, which only makes the compute stream wait for the copy."""
+        if self.device.type != "cuda":
+            return None
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        k = None
+        for d in range(self.ring_size):
+            c = (self._ring_next + d) % self.ring_size
+            if c not in self._ring_busy:
+                k = c
+                break
+        if k is None:
+            return None
+        self._ring_next = (k + 1) % self.ring_size
+        self._ring_busy.add(k)
+        key = ("ring", k)
+        with torch.cuda.stream(self._copy_stream):
+            if self._released.get(key) is not None:
+                self._copy_stream.wait_event(self._released[key])
+            dev, nbytes = self._ship(batch_args, key)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        first = next(t for t in dev if t is not None)
+        self._ring_lookup[first.data_ptr()] = (k, ev, nbytes)
+        return dev, ev
+
     def __call__(self, *batch_args):
         self._release_current()
+        first = next((t for t in batch_args if t is not None), None)
+        if first is not None and first.is_cuda and first.data_ptr() in self._ring_lookup:      # shipped by the feeder
+            k, ev, nbytes = self._ring_lookup[first.data_ptr()]
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            self.bytes_last = nbytes
+            self._in_use = ("ring", k)
+            return batch_args
         pend = self._pending
         # (`*batch_args` re-packs the caller's tuple, so compare the tensors, not the tuple object)
         if pend is not None and len(pend[1]) == len(batch_args) and all(x is y for x, y in zip(pend[1], batch_args)):

@@ -99,7 +99,7 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
     float* OBS = DHX + 8 * 4 * 32;                                   // OBS[helper pair][8 sequences * 4]: observations of the step whose dx is drained next
     float* WTS = OBS + 8 * 32;                                       // Wt[j][0..3]
     float* BTS = WTS + H * 4;                                        // bt[j]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(BTS + H + ((NH & 1) ? 1 : 0));   // (8-byte aligned: NH*H + 64*NH floats precede)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(BTS + H);                   // (8-byte aligned: an even number of floats precedes for every NH)
     uint64_t* b_full = bars, *acc_done = bars + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
 

@@ -213,7 +213,10 @@ struct EmulTmem { float d[128][512]; };
 inline EmulTmem& emul_tmem() { static EmulTmem t; return t; }
 
 // host mbarrier: bits [0,16) pending arrivals, [16,32) arrival count, bit 32 phase parity
-inline void mbar_init(uint64_t* bar, uint32_t count) { *bar = (uint64_t)count | ((uint64_t)count << 16); }
+inline void mbar_init(uint64_t* bar, uint32_t count) {
+    if (reinterpret_cast<uintptr_t>(bar) & 7) { fprintf(stderr, "emul: mbarrier at a misaligned address (the GPU traps on this)\n"); abort(); }
+    *bar = (uint64_t)count | ((uint64_t)count << 16);
+}
 inline void fence_mbar_init() {}
 inline void mbar_arrive(uint64_t* bar) {
     std::lock_guard<std::mutex> g(emul::atomic_mu());
