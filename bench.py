@@ -353,9 +353,10 @@ def e2e_from_shared_memory(dev, world, dist, timed, batch, n):
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    zero_copy = learner.zero_copy
+    info = {"zero_copy": bool(learner.zero_copy), "register_error": getattr(learner, "_register_error", None),
+            "first_field_pinned": bool(learner.sample_batch_from_sh_memory("on-policy", copy=False)[0].is_pinned())}
     del learner
-    return float(ms.item()), n
+    return float(ms.item()), n, info
 
 
 def dp_parity(dev, rank, world, pg):
@@ -579,7 +580,7 @@ def main():
     # (agents/learner_storage.py:123-159); `learning_chain_ppo`'s two coroutines take them from there.  The arrays are
     # page-locked once (cudaHostRegister), every batch is DMA'd straight out of the slots, and the slot counter is handed back to
     # the (here emulated: always-ready) storage process as soon as the copy engine has read them.
-    shm_ms, n_shm = e2e_from_shared_memory(dev, world, dist, timed, host[0], min(n_e2e, 100))
+    shm_ms, n_shm, shm_info = e2e_from_shared_memory(dev, world, dist, timed, host[0], min(n_e2e, 100))
     if rank == 0:
         log(f"e2e leg done: {ms2 / n_e2e:.3f} ms/step pinned, {ms3 / n_pg:.3f} ms/step pageable, {shm_ms / n_shm:.3f} ms/step from shared memory")
 
@@ -593,6 +594,7 @@ def main():
                 "host_batches": "pinned",
                 "pageable_value": world * B * T * n_pg / (ms3 * 1e-3), "pageable_steps": n_pg,
                 "shared_memory_value": world * B * T * n_shm / (shm_ms * 1e-3), "shared_memory_steps": n_shm,
+                "shared_memory_info": shm_info,
                 "shared_memory_api": "LearnerSinglePPO.learning_chain_ppo(): put_batch_to_batch_q (page-locked shm slots -> DMA) + learning()"},
         "loss": losses["loss"],
         "exchange": ("fused peer step (one-shot NVLink all-reduce + clip + RMSprop, csrc/peer_kernels.cu)"

@@ -69,9 +69,9 @@ int b200rl_soft_update(const float* src, float* target, long long n, float tau, 
  * Wt (H, Fin), bt (H) torso Linear;  W_ih/W_hh (4H, H), b_ih/b_hh (4H) PyTorch layout
  * saved activations (private layout, only lstm_bwd / lstm_wgrad read them):
  *   gates (B, T, H, 4) post-activation i,f,g,o ; c (B, T, H) ; h (B, T, H)
- * `variant`: 0 = FFMA kernel with the input projection in the loop; 1 = 16-warp FFMA;
- *            2 = tcgen05 input projection + FFMA recurrence; 3 = tcgen05 input projection +
- *            tcgen05 recurrence (what the Python layer uses); 4 = as 3, ping-pong groups.  */
+ * `variant`: 0 = FFMA kernel with the input projection in the loop (the independently written reference the
+ *            tensor-core kernels are cross-checked against); 3 = tcgen05 input projection + tcgen05 recurrence
+ *            (two kernels; any Fin).  The Python layer uses b200rl_lstm_fwd_fused below whenever Fin <= 8.       */
 int b200rl_lstm_fwd(const float* u, const float* hx0, const float* cx0,
                     const float* Wt, const float* bt,
                     const float* W_ih, const float* W_hh, const float* b_ih, const float* b_hh,
@@ -102,18 +102,21 @@ int b200rl_lstm_bwd(const float* dhead, const float* W_head, const float* W_hh, 
                     int B, int T, int NH, int variant, void* stream);
 
 /* The tcgen05 BPTT kernel with the small gradients fused (csrc/bwd_tc.cu): besides dpre (in place in `gates`) it accumulates
- * dW_head / db_head (h recomputed as o tanh(c)) and dWt / dbt (dx taken straight from the accumulator, ReLU mask from the
- * recomputed torso) and writes them into slab row blockIdx of `partials` (nparts x P, >= min(ceil(B/32), SMs) rows) --
- * replacing the head / torso passes of lstm_wgrad (then called with variant 4).  Needs Fin == 4 and NH <= 4.          */
+ * dW_head / db_head (h recomputed as o tanh(c); NH <= 4) into slab row blockIdx of `partials` (nparts x P, >= min(ceil(B/32),
+ * SMs) rows).  dx != NULL: dx (B,T,H) is stored as by lstm_bwd variant 1 and lstm_wgrad runs with variant 5 (tcgen05 dW +
+ * torso pass); dx == NULL (needs Fin == 4): dWt / dbt are accumulated here too (dx straight from the accumulator, ReLU mask
+ * from the recomputed torso), dx never goes to HBM and lstm_wgrad runs with variant 4 (tcgen05 dW only).                 */
 int b200rl_lstm_bwd_fused(const float* dhead, const float* W_head, const float* W_hh, const float* W_ih,
                           float* gates, const float* c, const float* cx0, const float* u, const float* Wt, const float* bt,
                           float* partials, int nparts, long long P, long long off_Wt, long long off_bt,
-                          long long off_Whead, long long off_bhead, int B, int T, int Fin, int NH, void* stream);
+                          long long off_Whead, long long off_bhead, float* dx, int B, int T, int Fin, int NH, void* stream);
 
 /* BPTT, parallel part: weight gradients as `nparts` partial slabs of `P` floats each
  * (partials[part*P + off_*]); also the torso-input gradient du (B,T,Fin) if non-NULL.
  * `variant` 0: FFMA; 1: tcgen05 dW + tcgen05 dx; 2: tcgen05 dW + FFMA rest;
- *           3: tcgen05 dW + torso gradients from `dx` (see lstm_bwd variant 1; du must be NULL, Fin <= 8). */
+ *           3: tcgen05 dW + torso gradients from `dx` (see lstm_bwd variant 1; du must be NULL, Fin <= 8);
+ *           4: tcgen05 dW only (the head / torso gradients were accumulated by b200rl_lstm_bwd_fused);
+ *           5: tcgen05 dW + torso pass over `dx` (the head gradients were accumulated by b200rl_lstm_bwd_fused). */
 int b200rl_lstm_wgrad(const float* dpre, const float* h, const float* hx0, const float* u,
                       const float* dhead, const float* Wt, const float* bt, const float* W_ih,
                       float* partials, int nparts, long long P,

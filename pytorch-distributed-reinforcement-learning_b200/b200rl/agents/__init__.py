@@ -17,10 +17,6 @@ def _awrapper(alearning):
     return factory
 
 
-async def _not_native_yet(parent, timer, *a, **k):
-    raise NotImplementedError("this algorithm has no B200-native learner path yet (see DESIGN.md, scope table)")
-
-
 ppo_awrapper = _awrapper(alearning_ppo)
 impala_awrapper = _awrapper(alearning_impala)
 v_mpo_awrapper = _awrapper(alearning_v_mpo)

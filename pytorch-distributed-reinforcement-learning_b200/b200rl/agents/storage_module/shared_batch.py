@@ -63,6 +63,7 @@ class SMInterFace:
             a = getattr(self, f"sh_{key}_batch")
             err = rt.cudaHostRegister(a.ctypes.data, a.nbytes, 0)
             if int(err) != 0:
+                self._register_error = f"cudaHostRegister({key}, {a.nbytes} B) -> {err!r}"
                 for p in done:
                     rt.cudaHostUnregister(p)
                 return False

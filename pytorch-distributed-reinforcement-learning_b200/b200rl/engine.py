@@ -143,7 +143,7 @@ class OnPolicyEngine:
                 self.comm.all_reduce(self.grad)                                 # the ONE gradient collective
             ops.clip_rmsprop(self.flat, self.grad, self.sq_avg, L.P, scale, hp["max_grad_norm"], hp["lr"],
                              0.99, 1e-5, self.grad_norm)
-        self.n_launches += nfw + 4 + (1 if self.ws.get("small_grads_done") else {0: 1, 1: 3, 2: 2}[self.wgrad_variant])   # + head, bwd, reduce, step ; wgrad stage
+        self.n_launches += nfw + 4 + ({2: 1, 1: 2}.get(self.ws.get("small_grads_done")) or {0: 1, 1: 3, 2: 2}[self.wgrad_variant])   # + head, bwd, reduce, step ; wgrad stage
 
     # -------------------------------------------------------------------- scalars
     def _reduced_scalars(self):
@@ -278,7 +278,7 @@ class VMPOEngine(OnPolicyEngine):
         lib.call("b200rl_vmpo_dual_step", ptr(self.duals), ptr(self.dual_sq), ptr(self.scalars), ptr(self.losses_dev),
                  hp["coef_eta"], float(coef_alpha), hp["lr"], 0.99, 1e-5, N, float(k * (T - 1)),
                  hp["policy_loss_coef"], hp["value_loss_coef"], st)
-        self.n_launches += nfw + 7 + (1 if self.ws.get("small_grads_done") else {0: 1, 1: 3, 2: 2}[self.wgrad_variant])
+        self.n_launches += nfw + 7 + ({2: 1, 1: 2}.get(self.ws.get("small_grads_done")) or {0: 1, 1: 3, 2: 2}[self.wgrad_variant])
 
     def losses(self):
         v = self.losses_dev.cpu().tolist()

@@ -29,7 +29,7 @@ SIGNATURES = {
     "b200rl_lstm_fwd_fused": [_P] * 16 + [_I, _I, _I, _I, _P],
     "b200rl_head_fwd": [_P, _P, _P, _P, _L, _I, _P],
     "b200rl_lstm_bwd": [_P] * 8 + [_I, _I, _I, _I, _P],
-    "b200rl_lstm_bwd_fused": [_P] * 11 + [_I, _L, _L, _L, _L, _L, _I, _I, _I, _I, _P],
+    "b200rl_lstm_bwd_fused": [_P] * 11 + [_I, _L, _L, _L, _L, _L, _P, _I, _I, _I, _I, _P],
     "b200rl_lstm_wgrad": [_P] * 8 + [_P, _I, _L] + [_L] * 8 + [_P, _P, _I, _I, _I, _I, _I, _P],
     "b200rl_reduce_partials": [_P, _P, _I, _L, _P],
     "b200rl_ppo_head": [_P] * 13 + [_I, _I, _I, _I] + [_F] * 6 + [_P],

@@ -10,15 +10,14 @@ from . import native
 from .native import ptr
 
 H = 64
-# kernel variants (env-overridable for A/B measurements): forward 5 = ONE persistent tcgen05 kernel for torso + input projection
-# + recurrence + heads (csrc/fwd_fused.cu; nets with Fin > 8 or more than 4 head outputs fall back to 3),
-# 4 = as 3 with two 16-sequence groups per CTA in ping-pong,
-# 3 = tcgen05 input projection + tcgen05 recurrent
-# kernel (W_hh resident in tensor memory), 2 = tcgen05 input projection + FFMA recurrent kernel (K=64),
-# 1 = 16-warp split-K FFMA, 0 = 8-warp FFMA with the projection in the loop
+# kernel variants (env-overridable for A/B measurements and the cross-implementation tests):
+# forward 5 = ONE persistent tcgen05 kernel for torso + input projection + recurrence + heads (csrc/fwd_fused.cu; nets with
+# Fin > 8 or more than 4 head outputs fall back to 3), 3 = tcgen05 input projection (xproj_tc.cu) + tcgen05 recurrent kernel
+# (fwd_tc.cu) + head_fwd, 0 = the independently written FFMA kernel (the reference the tensor-core paths are checked against)
 FWD_VARIANT = int(os.environ.get("B200RL_FWD_VARIANT", "5"))
 # backward 2 = tcgen05 BPTT kernel that also accumulates the head and torso gradients in registers (no dx in HBM, no head_grad /
 # torso_grad passes; nets with Fin != 4 or more than 4 head outputs, or callers that need d/d(input), fall back to 1),
+# 3 = as 2 but only the head gradients are fused (dx is stored, the torso pass stays),
 # 1 = tcgen05 BPTT kernel (emits dx = dpre . W_ih, so the weight-gradient stage skips that GEMM), 0 = FFMA kernel
 BWD_VARIANT = int(os.environ.get("B200RL_BWD_VARIANT", "2"))
 
@@ -189,15 +188,20 @@ def _lstm_bwd(self, L, flat, dhead, ws, cx0, variant=None, u=None, partials=None
     variant = BWD_VARIANT if variant is None else variant
     v = lambda k: ptr(flat) + 4 * L.off[k][0]
     o = lambda k: L.off[k][0]
-    ws["small_grads_done"] = False
-    if variant == 2:
-        if u is not None and partials is not None and L.Fin == 4 and L.NH <= 4:
+    ws["small_grads_done"] = 0
+    if variant in (2, 3):
+        if u is not None and partials is not None and L.NH <= 4 and (variant == 3 or L.Fin == 4):
             self._chk(u, partials)
-            ws["dx_fresh"] = False
+            dx = None
+            if variant == 3:
+                dx = ws.get("dx")
+                if dx is None or dx.shape[:2] != (B, T):
+                    dx = ws["dx"] = torch.empty(B, T, H, device=dhead.device)
+            ws["dx_fresh"] = variant == 3
             self.lib.call("b200rl_lstm_bwd_fused", ptr(dhead), v("W_head"), v("W_hh"), v("W_ih"), ptr(ws["gates"]), ptr(ws["c"]),
                           ptr(cx0), ptr(u), v("Wt"), v("bt"), ptr(partials), partials.shape[0], L.P, o("Wt"), o("bt"), o("W_head"),
-                          o("b_head"), B, T, L.Fin, L.NH, self._stream(dev))
-            ws["small_grads_done"] = True
+                          o("b_head"), ptr(dx), B, T, L.Fin, L.NH, self._stream(dev))
+            ws["small_grads_done"] = 2 if variant == 2 else 1          # 2: head + torso gradients done ; 1: head gradients done
             return
         variant = 1
     dx = None
@@ -216,8 +220,10 @@ def _lstm_wgrad(self, L, flat, ws, hx0, u, dhead, partials, du=None, variant=0):
     nparts = partials.shape[0]
     assert partials.shape[1] == L.P
     dx = None
-    if variant == 1 and ws.get("small_grads_done") and du is None:
+    if variant == 1 and ws.get("small_grads_done") == 2 and du is None:
         variant = 4
+    elif variant == 1 and ws.get("small_grads_done") == 1 and ws.get("dx_fresh") and du is None and Fin <= 8:
+        variant, dx = 5, ws["dx"]
     elif variant == 1 and ws.get("dx_fresh") and du is None and Fin <= 8:
         variant, dx = 3, ws["dx"]
     v = lambda k: ptr(flat) + 4 * L.off[k][0]

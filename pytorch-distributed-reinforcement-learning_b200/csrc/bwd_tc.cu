@@ -78,6 +78,7 @@ static inline size_t bwdt_smem_bytes(int NH) {
 struct BwdFuse {                 // fused head / torso gradients (null partials = off)
     const float* u; const float* Wt; const float* bt; float* partials;
     long long P, off_Wt, off_bt, off_Whead, off_bhead;
+    int torso;                   // 1: dWt / dbt accumulated here (dx never stored) ; 0: only the head gradients, dx is stored
 };
 
 template <int NHT>                // 0: runtime NH, small gradients left to their own kernels ; 1..4: NH == NHT at compile time, `fz` gradients fused
@@ -108,7 +109,8 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
     const int q = warp & 3, cg = (warp >> 2) & 3;                   // TMEM lane quarter, group of 8 sequences
 
     for (int i = tid; i < NH * H; i += NT) WhS[i] = W_head[i];
-    if (fuse) {
+    const bool ftorso = fuse && fz.torso != 0;
+    if (ftorso) {
         for (int i = tid; i < H * 4; i += NT) WTS[i] = fz.Wt[i];
         for (int i = tid; i < H; i += NT) BTS[i] = fz.bt[i];
     }
@@ -370,7 +372,7 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                     tc::named_bar_sync(1 + pair, 64);                // both threads have read their coefficients: the slots are free for step t-1
                     BWP(11, 64);
                     if (t < T - 1) {
-                        if (fuse) {
+                        if (ftorso) {
                             torso(dxs);                              // (obs_{t+1} landed before the previous coefs())
                         } else {
 #pragma unroll
@@ -378,7 +380,7 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                                 if (b0 + i < B) dx[(size_t)(rowof(i) + t + 1) * H + j] = dxs[i];
                         }
                     }
-                    if (fuse) fetch_obs(t);                          // for dx_t, drained in the next iteration
+                    if (ftorso) fetch_obs(t);                        // for dx_t, drained in the next iteration
                     if (t > 0) coefs(t - 1);
                     BWP(12, 64);
                 }
@@ -387,7 +389,7 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                 {
                     float d[8];
                     read_acc(d);
-                    if (fuse) {
+                    if (ftorso) {
                         cp_async_wait_all();
                         __syncwarp();
                         torso(d);
@@ -457,8 +459,8 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
             const int k = e / H, jj = e - k * H;
             const float v = (COEF[0 * 10 * H + e] + COEF[1 * 10 * H + e]) + (COEF[2 * 10 * H + e] + COEF[3 * 10 * H + e]);
             if (k < 4) { if (k < NHT) slab[fz.off_Whead + (size_t)k * H + jj] = v; }
-            else if (k < 8) slab[fz.off_Wt + (size_t)jj * 4 + (k - 4)] = v;
-            else if (k == 8) slab[fz.off_bt + jj] = v;
+            else if (k < 8) { if (ftorso) slab[fz.off_Wt + (size_t)jj * 4 + (k - 4)] = v; }
+            else if (k == 8) { if (ftorso) slab[fz.off_bt + jj] = v; }
             else if (jj < NHT) slab[fz.off_bhead + jj] = v;
         }
     }
@@ -484,19 +486,20 @@ static int launch_bwdt(const float* dhead, const float* W_head, const float* W_h
     return check_launch("lstm_bwd(tc)");
 }
 
-// partials != nullptr: head and torso gradients fused (needs Fin == 4, NH <= 4; dx is not written and may be null)
+// partials != nullptr: head gradients fused (NH <= 4); with dx == nullptr also the torso gradients (Fin == 4) and dx is never stored
 int launch_bwd_tc_fused(const float* dhead, const float* W_head, const float* W_hh, const float* W_ih, float* gates,
                         const float* c, const float* cx0, float* dx, const float* u, const float* Wt, const float* bt,
                         float* partials, long long P, long long off_Wt, long long off_bt, long long off_Whead, long long off_bhead,
                         int B, int T, int Fin, int NH, int sms, void* stream) {
     B200RL_REQUIRE((long long)B * T < (1LL << 31), "lstm_bwd(tc): B*T must be below 2^31");
     B200RL_REQUIRE(W_ih != nullptr, "lstm_bwd(tc): needs W_ih");
-    BwdFuse fz{u, Wt, bt, partials, P, off_Wt, off_bt, off_Whead, off_bhead};
+    BwdFuse fz{u, Wt, bt, partials, P, off_Wt, off_bt, off_Whead, off_bhead, dx == nullptr ? 1 : 0};
     if (partials == nullptr) {
         B200RL_REQUIRE(dx != nullptr, "lstm_bwd(tc): needs the dx workspace");
         return launch_bwdt<0>(dhead, W_head, W_hh, W_ih, gates, c, cx0, dx, B, T, NH, fz, sms, stream);
     }
-    B200RL_REQUIRE(Fin == 4 && NH >= 1 && NH <= 4 && u && Wt && bt, "lstm_bwd(tc, fused gradients): needs Fin == 4 and NH <= 4 (Fin=%d NH=%d)", Fin, NH);
+    B200RL_REQUIRE(NH >= 1 && NH <= 4, "lstm_bwd(tc, fused gradients): needs NH <= 4 (NH=%d)", NH);
+    B200RL_REQUIRE(dx != nullptr || (Fin == 4 && u && Wt && bt), "lstm_bwd(tc, fused torso gradients): needs Fin == 4 (Fin=%d)", Fin);
     const int ntiles = (B + btk::TB - 1) / btk::TB;
     B200RL_REQUIRE((ntiles < sms ? ntiles : sms) >= 1, "lstm_bwd(tc): empty grid");
     switch (NH) {

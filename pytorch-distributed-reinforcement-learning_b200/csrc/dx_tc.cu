@@ -510,6 +510,7 @@ int launch_torso_from_dx(const float* dx, const float* u, const float* Wt, const
         B200RL_LAUNCH(kern, nparts, 512, tsm, stream, dx, u, Wt, bt, partials, P, off_Wt, off_bt, rows, Fin);
     }
     if (check_launch("lstm_wgrad(torso from dx)")) return 1;
+    if (h == nullptr) return 0;                          // (the head gradients were accumulated by the backward kernel)
     return launch_head_grad(h, dhead, partials, nparts, P, off_Whead, off_bhead, rows, NH, stream);
 }
 

@@ -93,7 +93,7 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
     for (int i = tid; i < H * 4; i += NT) { const int j = i >> 2, g = i & 3; BI[i] = b_ih[g * H + j] + b_hh[g * H + j]; }
     for (int i = tid; i < H * MAXF; i += NT) { const int j = i >> 3, f = i & 7; WT[i] = f < Fin ? Wt[j * Fin + f] : 0.f; }
     for (int i = tid; i < H; i += NT) BT[i] = bt[i];
-    for (int i = tid; i < H * 4; i += NT) { const int j = i >> 2, o = i & 3; WH[i] = o < NH ? W_head[o * H + j] : 0.f; }
+    for (int i = tid; i < H * 4; i += NT) { const int j = i >> 2, o = i & 3; WH[i] = (head_part != nullptr && o < NH) ? W_head[o * H + j] : 0.f; }
     if (tid == 0) {
         tc::mbar_init(b_full, NC / 32); tc::mbar_init(acc_done, NI); tc::mbar_init(acc_free, NC / 32); tc::mbar_init(x_done, NI);
         tc::mbar_init(x_full, NC / 32); tc::mbar_init(x_full + 1, NC / 32);
@@ -128,7 +128,7 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
                 tc::tmem_st16(tc::tmem_addr(tmem, st_lane, (which ? TM_IH : TM_HH) + mt * H + k0 + hh * 16), hi);
 #pragma unroll
                 for (int e = 0; e < 16; e += 2)
-                    lo16[hh * 8 + e / 2] = __uint_as_float((unsigned)tc::bf16_bits(lo[e]) | ((unsigned)tc::bf16_bits(lo[e + 1]) << 16));
+                    lo16[hh * 8 + e / 2] = __uint_as_float((unsigned)tc::bf16_bits_rn(lo[e]) | ((unsigned)tc::bf16_bits_rn(lo[e + 1]) << 16));
             }
             tc::tmem_st16(tc::tmem_addr(tmem, st_lane, (which ? TM_IHL : TM_HHL) + mt * (H / 2) + k0 / 2), lo16);
         }
@@ -230,7 +230,7 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
             tc::split_tf32(v, hi, lo);
             *reinterpret_cast<float*>(op + tf(r)) = hi;
             *reinterpret_cast<float*>(op + B_BYTES + tf(r)) = lo;
-            *reinterpret_cast<unsigned short*>(op + bf(r)) = tc::bf16_bits(hi);
+            *reinterpret_cast<unsigned short*>(op + bf(r)) = tc::bf16_bits_rn(hi);
         };
         const float4 bias = ld4(BI + j * 4);
         uint32_t n = 0;

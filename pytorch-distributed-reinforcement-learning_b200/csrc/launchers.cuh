@@ -22,9 +22,6 @@ int launch_fwd_fused(const float* u, const float* hx0, const float* cx0, const f
                      const float* W_hh, const float* b_ih, const float* b_hh, const float* W_head, const float* b_head,
                      float* gates, float* c, float* h, float* head_part, float* head_out,
                      int B, int T, int Fin, int NH, int sms, void* stream);
-// fwd_tc2.cu: the same with two 16-sequence groups per CTA in ping-pong (tensor core of one group under the cell phase of the other)
-int launch_fwd_tc2(float* xg, const float* hx0, const float* cx0, const float* W_hh, float* c, float* h,
-                   int B, int T, int sms, void* stream);
 // dx_tc.cu: torso gradients from a stored dx (written by bwd_tc.cu) + head gradients
 int launch_torso_from_dx(const float* dx, const float* u, const float* Wt, const float* bt,
                          const float* h, const float* dhead, float* partials, int nparts, long long P,

@@ -32,6 +32,7 @@ constexpr int KC = 2 * H;     // 128 = [x | h] concatenated K
 constexpr int TM = 32;        // sequences per CTA tile
 constexpr int NT = 256;       // threads per CTA
 constexpr int DS = 36;        // row stride of r-minor (transposed) tiles: 16B aligned, bank-skewed
+constexpr int HM = TM / 2;    // sequences per independent half-CTA (backward kernel)
 constexpr int MAXF = 32;      // max torso input width
 
 // thread -> (4 rows, 2 hidden units).  A shared-memory LDS.128 is served one quarter-warp
@@ -230,293 +231,6 @@ lstm_fwd_kernel(const float* __restrict__ u, const float* __restrict__ hx0, cons
 #pragma unroll
                 for (int e = 0; e < (TM * MAXF + NT - 1) / NT; ++e) {
                     int i = e * NT + tid;
-                    if (i < nU) Ud[i] = upre[e];
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
-
-// ------------------------------------------------- forward, recurrent half only (variant 2, default)
-// gates_t = xproj_t + h_{t-1} . W_hh^T : the input projection (incl. both biases) was computed for all
-// timesteps by lstm_xproj_tc_kernel (xproj_tc.cu, tcgen05).  Only W_hh (64 KB) stays in shared memory,
-// the K loop is 64 deep, and the accumulators start from the prefetched xproj row segment.
-// `xg` is BOTH input and output: xg[b,t,j,:] holds the projection until the thread that owns (b,t,j)
-// overwrites those 16 bytes with the gate activations (no extra 0.5 GB buffer, no extra traffic).
-static inline size_t fwdx_smem_bytes() { return sizeof(float) * (size_t)(H * G + 2 * H * TM); }
-
-// The CTA is two INDEPENDENT halves of 128 threads, 16 sequences each, sharing only the read-only W_hh
-// tile: each half synchronises with itself through a named barrier, so the halves drift apart and one
-// half's FFMA-bound GEMM phase overlaps the other's MUFU-bound cell phase (with all eight warps in
-// lock-step the two pipes took turns idling: ncu r1g, 9.9K cycles per timestep for 4.1K FMA cycles).
-constexpr int HM = TM / 2;                  // sequences per half
-
-__global__ void __launch_bounds__(NT, 1)
-lstm_fwdx_kernel(float* xg, const float* __restrict__ hx0, const float* __restrict__ cx0,
-                 const float* __restrict__ W_hh, float* __restrict__ c_out,
-                 float* __restrict__ h_out, int B, int T) {
-    B200RL_DYN_SMEM(float, smem);
-    float* Wp = smem;                       // Wp[k*256 + j*4 + g] = W_hh[g*64 + j][k]
-    const int tid = threadIdx.x, half = tid >> 7, ht = tid & 127, lane = tid & 31, hw = ht >> 5;
-    float* HT = Wp + H * G + half * 2 * H * HM;     // HT[buf][k*16 + r] = h_{t-1} of this half
-    const int r0 = (lane >> 3) * 4;                 // 4 of the half's 16 rows
-    const int j0 = hw * 8 + (lane & 7), j1 = j0 + 32;
-    {
-        const int n = tid, g = n >> 6, j = n & 63, pc = j * 4 + g;
-        for (int k4 = 0; k4 < H; k4 += 4) {
-            float4 b = ld4(W_hh + (size_t)n * H + k4);
-            Wp[(k4 + 0) * G + pc] = b.x; Wp[(k4 + 1) * G + pc] = b.y;
-            Wp[(k4 + 2) * G + pc] = b.z; Wp[(k4 + 3) * G + pc] = b.w;
-        }
-    }
-    __syncthreads();
-    const int ntiles = (B + TM - 1) / TM;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int b0 = tile * TM + half * HM;
-        tc::named_bar_sync(1 + half, 128);           // previous tile of this half finished with HT
-        int brow[4]; bool bok[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { int b = b0 + r0 + i; bok[i] = b < B; brow[i] = bok[i] ? b : B - 1; }
-        float cst[4][2];
-        {
-            float hv0[4], hv1[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                cst[i][0] = cx0[(size_t)brow[i] * H + j0]; cst[i][1] = cx0[(size_t)brow[i] * H + j1];
-                hv0[i] = hx0[(size_t)brow[i] * H + j0];    hv1[i] = hx0[(size_t)brow[i] * H + j1];
-            }
-            st4(HT + j0 * HM + r0, make_float4(hv0[0], hv0[1], hv0[2], hv0[3]));
-            st4(HT + j1 * HM + r0, make_float4(hv1[0], hv1[1], hv1[2], hv1[3]));
-        }
-        float4 xp[4][2];                     // projection of the step being processed (loaded one step ahead)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const size_t o = ((size_t)brow[i] * T + 0) * G;
-            xp[i][0] = ld4(xg + o + j0 * 4); xp[i][1] = ld4(xg + o + j1 * 4);
-        }
-        tc::named_bar_sync(1 + half, 128);
-
-        for (int t = 0; t < T; ++t) {
-            const float* Hc = HT + (t & 1) * H * HM;
-            float* Hn = HT + ((t + 1) & 1) * H * HM;
-            f2 acc2[4][4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                acc2[i][0] = f2_make(xp[i][0].x, xp[i][0].y); acc2[i][1] = f2_make(xp[i][0].z, xp[i][0].w);
-                acc2[i][2] = f2_make(xp[i][1].x, xp[i][1].y); acc2[i][3] = f2_make(xp[i][1].z, xp[i][1].w);
-            }
-            if (t + 1 < T) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const size_t o = ((size_t)brow[i] * T + (t + 1)) * G;
-                    xp[i][0] = ld4(xg + o + j0 * 4); xp[i][1] = ld4(xg + o + j1 * 4);
-                }
-            }
-#pragma unroll 4
-            for (int k = 0; k < H; ++k) {
-                const float4 a = ld4(Hc + k * HM + r0);
-                f2 w00, w01, w10, w11;
-                f2_ld2(Wp + k * G + j0 * 4, w00, w01);
-                f2_ld2(Wp + k * G + j1 * 4, w10, w11);
-                const f2 av[4] = {f2_make(a.x, a.x), f2_make(a.y, a.y), f2_make(a.z, a.z), f2_make(a.w, a.w)};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    f2_fma(acc2[i][0], av[i], w00); f2_fma(acc2[i][1], av[i], w01);
-                    f2_fma(acc2[i][2], av[i], w10); f2_fma(acc2[i][3], av[i], w11);
-                }
-            }
-            float hn[4][2];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-#pragma unroll
-                for (int jj = 0; jj < 2; ++jj) {
-                    const float ig = sigm(f2_lo(acc2[i][jj * 2])), fg = sigm(f2_hi(acc2[i][jj * 2]));
-                    const float gg = tanh_(f2_lo(acc2[i][jj * 2 + 1])), og = sigm(f2_hi(acc2[i][jj * 2 + 1]));
-                    const float cn = fmaf(fg, cst[i][jj], ig * gg);
-                    const float hh = og * tanh_(cn);
-                    cst[i][jj] = cn; hn[i][jj] = hh;
-                    if (bok[i]) {
-                        const int j = jj ? j1 : j0;
-                        const size_t o = ((size_t)brow[i] * T + t) * H + j;
-                        st4(xg + o * 4, make_float4(ig, fg, gg, og));
-                        c_out[o] = cn; h_out[o] = hh;
-                    }
-                }
-            }
-            st4(Hn + j0 * HM + r0, make_float4(hn[0][0], hn[1][0], hn[2][0], hn[3][0]));
-            st4(Hn + j1 * HM + r0, make_float4(hn[0][1], hn[1][1], hn[2][1], hn[3][1]));
-            tc::named_bar_sync(1 + half, 128);
-        }
-    }
-}
-
-// ------------------------------------------------------------------ forward, 16-warp variant
-// Same tiling, but 512 threads: warp group 0 multiplies the x half of K (k < 64), group 1 the
-// h half; each thread then hands the partial sums of the unit it does NOT own to its partner
-// through shared memory and finishes the 4 cells (4 rows x 1 unit) it owns.  Four warps per
-// scheduler instead of two hide the LDS latency the 8-warp kernel stalls on (ncu r1a/r1c:
-// short-scoreboard, 52 % of the FP32 pipe).
-constexpr int NT16 = 512;
-static inline size_t fwd16_smem_bytes(int Fin) {
-    return fwd_smem_bytes(Fin) + sizeof(float4) * (size_t)(4 * 2 * 256);
-}
-
-__global__ void __launch_bounds__(NT16, 1)
-lstm_fwd16_kernel(const float* __restrict__ u, const float* __restrict__ hx0, const float* __restrict__ cx0,
-                  const float* __restrict__ Wt, const float* __restrict__ bt,
-                  const float* __restrict__ W_ih, const float* __restrict__ W_hh,
-                  const float* __restrict__ b_ih, const float* __restrict__ b_hh,
-                  float* __restrict__ gates, float* __restrict__ c_out, float* __restrict__ h_out,
-                  int B, int T, int Fin) {
-    B200RL_DYN_SMEM(float, smem);
-    float* Wp = smem;
-    float* AT = Wp + KC * G;
-    float* bsum = AT + 2 * KC * TM;
-    float* bts = bsum + G;
-    float* WtS = bts + H;
-    float* U = WtS + Fin * H;
-    float4* X = reinterpret_cast<float4*>(U + 2 * TM * Fin + ((4 - ((2 * TM * Fin) & 3)) & 3));   // 16-byte aligned exchange buffer
-    const int tid = threadIdx.x, grp = tid >> 8, t8 = tid & 255;
-    const int lane = tid & 31, warp8 = t8 >> 5;
-    const int r0 = ((warp8 & 1) * 4 + (lane >> 3)) * 4;
-    const int j0 = (warp8 >> 1) * 8 + (lane & 7), j1 = j0 + 32;
-    const int jown = grp ? j1 : j0;
-
-    if (tid < G) {
-        const int n = tid, g = n >> 6, j = n & 63, pc = j * 4 + g;
-        for (int k4 = 0; k4 < H; k4 += 4) {
-            float4 a = ld4(W_ih + (size_t)n * H + k4);
-            float4 b = ld4(W_hh + (size_t)n * H + k4);
-            Wp[(k4 + 0) * G + pc] = a.x; Wp[(k4 + 1) * G + pc] = a.y;
-            Wp[(k4 + 2) * G + pc] = a.z; Wp[(k4 + 3) * G + pc] = a.w;
-            Wp[(H + k4 + 0) * G + pc] = b.x; Wp[(H + k4 + 1) * G + pc] = b.y;
-            Wp[(H + k4 + 2) * G + pc] = b.z; Wp[(H + k4 + 3) * G + pc] = b.w;
-        }
-        bsum[pc] = b_ih[n] + b_hh[n];
-    }
-    if (tid < H) bts[tid] = bt[tid];
-    for (int i = tid; i < Fin * H; i += NT16) { int q = i / H, jj = i % H; WtS[i] = Wt[jj * Fin + q]; }
-
-    const int ntiles = (B + TM - 1) / TM;
-    const int nU = TM * Fin;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int b0 = tile * TM;
-        __syncthreads();
-        int brow[4]; bool bok[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { int b = b0 + r0 + i; bok[i] = b < B; brow[i] = bok[i] ? b : B - 1; }
-        float cst[4];
-        {
-            float hv[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { cst[i] = cx0[(size_t)brow[i] * H + jown]; hv[i] = hx0[(size_t)brow[i] * H + jown]; }
-            st4(AT + (H + jown) * TM + r0, make_float4(hv[0], hv[1], hv[2], hv[3]));
-        }
-        for (int i = tid; i < nU; i += NT16) {
-            int r = i / Fin, q = i % Fin; int b = b0 + r < B ? b0 + r : B - 1;
-            U[i] = u[((size_t)b * T + 0) * Fin + q];
-            if (T > 1) U[nU + i] = u[((size_t)b * T + 1) * Fin + q];
-        }
-        __syncthreads();
-        {
-            float x[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float a = bts[jown];
-                for (int q = 0; q < Fin; ++q) a = fmaf(U[(r0 + i) * Fin + q], WtS[q * H + jown], a);
-                x[i] = fmaxf(a, 0.f);
-            }
-            st4(AT + jown * TM + r0, make_float4(x[0], x[1], x[2], x[3]));
-        }
-        __syncthreads();
-
-        for (int t = 0; t < T; ++t) {
-            const float* Ac = AT + (t & 1) * KC * TM;
-            float* An = AT + ((t + 1) & 1) * KC * TM;
-            float upre[(TM * MAXF + NT16 - 1) / NT16];
-            const bool do_pre = t + 2 < T;
-            if (do_pre) {
-#pragma unroll
-                for (int e = 0; e < (TM * MAXF + NT16 - 1) / NT16; ++e) {
-                    int i = e * NT16 + tid;
-                    if (i < nU) {
-                        int r = i / Fin, q = i % Fin; int b = b0 + r < B ? b0 + r : B - 1;
-                        upre[e] = __ldg(u + ((size_t)b * T + (t + 2)) * Fin + q);
-                    }
-                }
-            }
-            float acc[4][8];
-            {
-                float4 b0v = make_float4(0.f, 0.f, 0.f, 0.f), b1v = b0v;
-                if (grp == 0) { b0v = ld4(bsum + j0 * 4); b1v = ld4(bsum + j1 * 4); }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    acc[i][0] = b0v.x; acc[i][1] = b0v.y; acc[i][2] = b0v.z; acc[i][3] = b0v.w;
-                    acc[i][4] = b1v.x; acc[i][5] = b1v.y; acc[i][6] = b1v.z; acc[i][7] = b1v.w;
-                }
-            }
-            const float* Ak = Ac + grp * H * TM;
-            const float* Wk = Wp + grp * H * G;
-#pragma unroll 4
-            for (int k = 0; k < H; ++k) {
-                float4 a = ld4(Ak + k * TM + r0);
-                float4 w0 = ld4(Wk + k * G + j0 * 4);
-                float4 w1 = ld4(Wk + k * G + j1 * 4);
-                const float av[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    acc[i][0] = fmaf(av[i], w0.x, acc[i][0]); acc[i][1] = fmaf(av[i], w0.y, acc[i][1]);
-                    acc[i][2] = fmaf(av[i], w0.z, acc[i][2]); acc[i][3] = fmaf(av[i], w0.w, acc[i][3]);
-                    acc[i][4] = fmaf(av[i], w1.x, acc[i][4]); acc[i][5] = fmaf(av[i], w1.y, acc[i][5]);
-                    acc[i][6] = fmaf(av[i], w1.z, acc[i][6]); acc[i][7] = fmaf(av[i], w1.w, acc[i][7]);
-                }
-            }
-            // hand over the partial sums of the unit the partner owns
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int o = grp ? 0 : 4;
-                X[(i * 2 + grp) * 256 + t8] = make_float4(acc[i][o], acc[i][o + 1], acc[i][o + 2], acc[i][o + 3]);
-            }
-            __syncthreads();
-            float pre[4][4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 v = X[(i * 2 + (grp ^ 1)) * 256 + t8];
-                const int o = grp ? 4 : 0;
-                pre[i][0] = acc[i][o] + v.x; pre[i][1] = acc[i][o + 1] + v.y;
-                pre[i][2] = acc[i][o + 2] + v.z; pre[i][3] = acc[i][o + 3] + v.w;
-            }
-            float hn[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float ig = sigm(pre[i][0]), fg = sigm(pre[i][1]), gg = tanh_(pre[i][2]), og = sigm(pre[i][3]);
-                float cn = fmaf(fg, cst[i], ig * gg);
-                float hh = og * tanh_(cn);
-                cst[i] = cn; hn[i] = hh;
-                if (bok[i]) {
-                    const size_t o = ((size_t)brow[i] * T + t) * H + jown;
-                    st4(gates + o * 4, make_float4(ig, fg, gg, og));
-                    c_out[o] = cn; h_out[o] = hh;
-                }
-            }
-            st4(An + (H + jown) * TM + r0, make_float4(hn[0], hn[1], hn[2], hn[3]));
-            if (t + 1 < T) {
-                const float* Un = U + ((t + 1) & 1) * nU;
-                float x[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float a = bts[jown];
-                    for (int q = 0; q < Fin; ++q) a = fmaf(Un[(r0 + i) * Fin + q], WtS[q * H + jown], a);
-                    x[i] = fmaxf(a, 0.f);
-                }
-                st4(An + jown * TM + r0, make_float4(x[0], x[1], x[2], x[3]));
-            }
-            if (do_pre) {
-                float* Ud = U + (t & 1) * nU;
-#pragma unroll
-                for (int e = 0; e < (TM * MAXF + NT16 - 1) / NT16; ++e) {
-                    int i = e * NT16 + tid;
                     if (i < nU) Ud[i] = upre[e];
                 }
             }
@@ -1071,32 +785,13 @@ extern "C" int b200rl_lstm_fwd(const float* u, const float* hx0, const float* cx
                                int B, int T, int Fin, int variant, void* stream) {
     B200RL_REQUIRE(B >= 1 && T >= 1, "lstm_fwd: bad shape B=%d T=%d", B, T);
     B200RL_REQUIRE(Fin >= 1 && Fin <= MAXF, "lstm_fwd: Fin=%d out of range [1,%d]", Fin, MAXF);
-    B200RL_REQUIRE(variant >= 0 && variant <= 4, "lstm_fwd: unknown variant %d", variant);
+    B200RL_REQUIRE(variant == 0 || variant == 3, "lstm_fwd: unknown variant %d (0 = FFMA reference kernel, 3 = tcgen05 projection + tcgen05 recurrence)", variant);
     const int ntiles = (B + TM - 1) / TM;
     const int grid = ntiles < sm_count() ? ntiles : sm_count();
-    if (variant == 4) {
-        // as 3, recurrent kernel with two sequence groups per CTA in ping-pong
-        if (launch_xproj_tc(u, Wt, bt, W_ih, b_ih, b_hh, gates, B, T, Fin, sm_count(), stream)) return 1;
-        return launch_fwd_tc2(gates, hx0, cx0, W_hh, c, h, B, T, sm_count(), stream);
-    }
     if (variant == 3) {
-        // input projection AND the recurrent GEMM on tcgen05
+        // input projection AND the recurrent GEMM on tcgen05 (two kernels; variant 5 = b200rl_lstm_fwd_fused is ONE)
         if (launch_xproj_tc(u, Wt, bt, W_ih, b_ih, b_hh, gates, B, T, Fin, sm_count(), stream)) return 1;
         return launch_fwd_tc(gates, hx0, cx0, W_hh, c, h, B, T, sm_count(), stream);
-    }
-    if (variant == 2) {
-        // input projection on tcgen05 for all (b,t), staged in the (not yet written) `gates` buffer
-        if (launch_xproj_tc(u, Wt, bt, W_ih, b_ih, b_hh, gates, B, T, Fin, sm_count(), stream)) return 1;
-        const size_t smx = fwdx_smem_bytes();
-        if (set_smem(lstm_fwdx_kernel, smx, "lstm_fwd(recurrent)")) return 1;
-        B200RL_LAUNCH(lstm_fwdx_kernel, grid, NT, smx, stream, gates, hx0, cx0, W_hh, c, h, B, T);
-        return check_launch("lstm_fwd(recurrent)");
-    }
-    if (variant == 1) {
-        const size_t smem16 = fwd16_smem_bytes(Fin) + 16;
-        if (set_smem(lstm_fwd16_kernel, smem16, "lstm_fwd16")) return 1;
-        B200RL_LAUNCH(lstm_fwd16_kernel, grid, NT16, smem16, stream, u, hx0, cx0, Wt, bt, W_ih, W_hh, b_ih, b_hh, gates, c, h, B, T, Fin);
-        return check_launch("lstm_fwd16");
     }
     const size_t smem = fwd_smem_bytes(Fin);
     if (set_smem(lstm_fwd_kernel, smem, "lstm_fwd")) return 1;
@@ -1138,12 +833,12 @@ extern "C" int b200rl_lstm_bwd(const float* dhead, const float* W_head, const fl
 extern "C" int b200rl_lstm_bwd_fused(const float* dhead, const float* W_head, const float* W_hh, const float* W_ih,
                                      float* gates, const float* c, const float* cx0, const float* u, const float* Wt, const float* bt,
                                      float* partials, int nparts, long long P, long long off_Wt, long long off_bt,
-                                     long long off_Whead, long long off_bhead, int B, int T, int Fin, int NH, void* stream) {
+                                     long long off_Whead, long long off_bhead, float* dx, int B, int T, int Fin, int NH, void* stream) {
     B200RL_REQUIRE(B >= 1 && T >= 1, "lstm_bwd_fused: bad shape B=%d T=%d", B, T);
     B200RL_REQUIRE(partials != nullptr, "lstm_bwd_fused: needs the partial-gradient slabs");
     const int ntiles = (B + 31) / 32;
     B200RL_REQUIRE(nparts >= (ntiles < sm_count() ? ntiles : sm_count()), "lstm_bwd_fused: nparts=%d below the grid size", nparts);
-    return launch_bwd_tc_fused(dhead, W_head, W_hh, W_ih, gates, c, cx0, nullptr, u, Wt, bt, partials, P, off_Wt, off_bt, off_Whead, off_bhead,
+    return launch_bwd_tc_fused(dhead, W_head, W_hh, W_ih, gates, c, cx0, dx, u, Wt, bt, partials, P, off_Wt, off_bt, off_Whead, off_bhead,
                                B, T, Fin, NH, sm_count(), stream);
 }
 
@@ -1156,7 +851,7 @@ extern "C" int b200rl_lstm_wgrad(const float* dpre, const float* h, const float*
     B200RL_REQUIRE(B >= 1 && T >= 1, "lstm_wgrad: bad shape B=%d T=%d", B, T);
     B200RL_REQUIRE(Fin >= 1 && Fin <= MAXF && NH >= 1 && NH <= B200RL_MAX_HEADS, "lstm_wgrad: Fin=%d NH=%d out of range", Fin, NH);
     B200RL_REQUIRE(H * Fin <= WG_E * NT && NH * H <= WG_E * NT, "lstm_wgrad: head/torso too wide");
-    B200RL_REQUIRE(variant >= 0 && variant <= 4, "lstm_wgrad: unknown variant %d", variant);
+    B200RL_REQUIRE(variant >= 0 && variant <= 5, "lstm_wgrad: unknown variant %d", variant);
     B200RL_REQUIRE(nparts >= 1, "lstm_wgrad: nparts=%d", nparts);
     B200RL_REQUIRE((off_Wih % 4) == 0 && (off_Whh % 4) == 0 && (P % 4) == 0, "lstm_wgrad: W_ih/W_hh offsets and P must be multiples of 4 floats");
     const size_t smem = wgrad_smem_bytes(Fin, NH);
@@ -1167,6 +862,13 @@ extern "C" int b200rl_lstm_wgrad(const float* dpre, const float* h, const float*
         // lstm_bwd_fused already accumulated the head and torso gradients: only dW_ih / dW_hh / db_ih / db_hh are left
         B200RL_REQUIRE((long long)nparts * 32 <= (long long)B * T + 31, "lstm_wgrad: nparts=%d exceeds the number of 32-row stages", nparts);
         return launch_wgrad_tc(dpre, h, hx0, u, Wt, bt, partials, nparts, P, off_Wih, off_Whh, off_bih, off_bhh, B, T, Fin, stream);
+    }
+    if (variant == 5) {
+        // lstm_bwd_fused accumulated the head gradients and stored dx: tcgen05 dW + the torso pass over dx
+        B200RL_REQUIRE(dx != nullptr && du == nullptr, "lstm_wgrad: variant 5 needs dx and does not produce du");
+        B200RL_REQUIRE((long long)nparts * 32 <= (long long)B * T + 31, "lstm_wgrad: nparts=%d exceeds the number of 32-row stages", nparts);
+        if (launch_wgrad_tc(dpre, h, hx0, u, Wt, bt, partials, nparts, P, off_Wih, off_Whh, off_bih, off_bhh, B, T, Fin, stream)) return 1;
+        return launch_torso_from_dx(dx, u, Wt, bt, nullptr, dhead, partials, np_misc, P, off_Wt, off_bt, off_Whead, off_bhead, B, T, Fin, NH, stream);
     }
     if (variant == 3) {
         // dx was already produced by lstm_bwd variant 1: tcgen05 dW + a bandwidth-bound torso pass over dx

@@ -38,6 +38,8 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 }
 // fp32 -> bf16 bits by truncation (used for the small third split term only) / back
 __host__ __device__ inline unsigned short bf16_bits(float f) { unsigned u; memcpy(&u, &f, 4); return (unsigned short)(u >> 16); }
+// fp32 -> bf16 bits, round to nearest even: zero-mean error (truncation is one-sided, and a recurrence accumulates the bias)
+__host__ __device__ inline unsigned short bf16_bits_rn(float f) { unsigned u; memcpy(&u, &f, 4); return (unsigned short)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16); }
 
 #ifndef B200RL_EMUL
 // ------------------------------------------------------------------------------ device

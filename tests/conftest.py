@@ -1,6 +1,13 @@
 import os
 import sys
 
+# The loopback tests run several "ranks" as threads of this process on ONE GPU, each on its own stream, with kernels that
+# wait for each other (the peer step).  CUDA maps streams onto CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8):
+# with more streams than queues two ranks can share a queue and the spinning kernel of one blocks the kernels of the other
+# behind it -- a false dependency that never resolves.  Must be set before the CUDA context exists.  (Test-only: a real
+# job is one process per GPU with one compute stream.)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np
 import pytest
 import torch
