@@ -82,8 +82,53 @@ class LearnerBase(SMInterFace):
         self.pub_socket.bind(f"tcp://{learner_ip}:{int(learner_port) + 1}")
 
     def pub_model(self, model_state_dict):
-        if self.pub_socket is not None:
+        """Publish the model to the workers (reference learner.py:92-93: pickle + blosc2 + ZeroMQ PUB, every update).
+
+        `args.publish_interval` = k > 1 publishes every k-th update only; `args.publish_async` moves pickle + compress + send
+        to a single worker thread fed through a one-slot mailbox that always holds the NEWEST state dict (workers only ever
+        want the latest model; an older unsent snapshot is dropped), so the learner loop never waits for the wire format
+        (SURVEY.md 8f-3).  Defaults (k = 1, synchronous) are the reference's behaviour."""
+        if self.pub_socket is None:
+            return
+        k = int(getattr(self.args, "publish_interval", 1) or 1)
+        self._pub_count = getattr(self, "_pub_count", 0) + 1
+        if k > 1 and (self._pub_count - 1) % k != 0:
+            return
+        if not getattr(self.args, "publish_async", False):
             self.pub_socket.send_multipart([*encode(Protocol.Model, model_state_dict)])
+            return
+        if getattr(self, "_pub_thread", None) is None:
+            import threading
+            self._pub_box, self._pub_cv, self._pub_stop = [None], threading.Condition(), False
+            self.pub_dropped = 0
+
+            def worker():
+                while True:
+                    with self._pub_cv:
+                        while self._pub_box[0] is None and not self._pub_stop:
+                            self._pub_cv.wait()
+                        if self._pub_box[0] is None:
+                            return
+                        sd, self._pub_box[0] = self._pub_box[0], None
+                    self.pub_socket.send_multipart([*encode(Protocol.Model, sd)])
+            self._pub_thread = threading.Thread(target=worker, daemon=True)
+            self._pub_thread.start()
+        with self._pub_cv:
+            if self._pub_box[0] is not None:
+                self.pub_dropped += 1
+            # the state dict views a pinned snapshot buffer that is reused two updates later: the mailbox owns a copy
+            self._pub_box[0] = {k_: v.clone() for k_, v in model_state_dict.items()}
+            self._pub_cv.notify()
+
+    def pub_flush(self):
+        """Wait until the asynchronous publisher has sent what is in its mailbox and stop it."""
+        t = getattr(self, "_pub_thread", None)
+        if t is not None:
+            with self._pub_cv:
+                self._pub_stop = True
+                self._pub_cv.notify()
+            t.join()
+            self._pub_thread = None
 
     # -------------------------------------------------------------------- logging
     def log_loss_tensorboard(self, timer, loss, detached_losses):
@@ -167,6 +212,8 @@ class LearnerBase(SMInterFace):
                 else:
                     await self.batch_queue.put(self.sample_batch_from_sh_memory(sampling_method="on-policy"))
                 self.reset_data_num()
+                await asyncio.sleep(0)         # a batch was just handed over: look again at once (the reference's fixed 1 ms nap
+                continue                       # per batch is as long as a whole update here)
             await asyncio.sleep(0.001)
 
     # ----------------------------------------------------------------- coroutines
@@ -285,4 +332,6 @@ class LearnerSeperate(LearnerBase):
         while not self.stop_event.is_set():
             if self.is_sh_ready():
                 await self.batch_buffer.put(self.sample_batch_from_sh_memory(sampling_method="off-policy"))
+                await asyncio.sleep(0)
+                continue
             await asyncio.sleep(0.001)

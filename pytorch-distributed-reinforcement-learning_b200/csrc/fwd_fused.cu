@@ -166,25 +166,34 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
             const uint32_t Ahh = tmem + TM_HH + mt * H, Ahhl = tmem + TM_HHL + mt * (H / 2);
             const uint32_t Aih = tmem + TM_IH + mt * H, Aihl = tmem + TM_IHL + mt * (H / 2);
 #if B200RL_FWD3_SEP
+            F3P_INIT
             if (iw >= NI) {                                  // input-projection issuer: runs one step ahead of the cell phase
                 uint32_t xc[2] = {0, 0};
                 long long N = 0;
                 for (int tl = 0; tl < my_tiles; ++tl)
                     for (int t = 0; t < T; ++t, ++N) {
                         const int p = t & 1;
+                        F3P(11, NC + 32 * NI);
                         tc::mbar_wait(x_full + p, xc[p] & 1); ++xc[p];
+                        F3P(12, NC + 32 * NI);
                         if (N > 0) tc::mbar_wait(acc_free, (uint32_t)(N - 1) & 1);
                         tc::fence_after_sync();
+                        F3P(13, NC + 32 * NI);
                         issue(D, Aih, Aihl, OPX + p * OP_BYTES, kh, true);
                         tc::mma_commit(x_done);
+                        F3P(14, NC + 32 * NI);
                     }
             } else {
                 for (long long N = 0; N < nsteps; ++N) {
+                    F3P(7, NC);
                     tc::mbar_wait(b_full, (uint32_t)N & 1);  // h_{t-1} operand written
+                    F3P(8, NC);
                     tc::mbar_wait(x_done, (uint32_t)N & 1);  // the input projection of this step sits in the accumulator
                     tc::fence_after_sync();
+                    F3P(9, NC);
                     issue(D, Ahh, Ahhl, OPH, kh, false);
                     tc::mma_commit(acc_done);
+                    F3P(10, NC);
                 }
             }
 #else

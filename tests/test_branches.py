@@ -467,3 +467,54 @@ def test_peer_step_single_rank_equals_clip_rmsprop(backend):
         _close(gout.cpu(), g.cpu(), rtol=1e-6, atol=1e-7, what="clipped gradient")
         _close(no2.cpu(), no.cpu(), rtol=1e-6, what="norm")
         assert sout.cpu().tolist() == list(range(8))
+
+
+# ------------------------------------------------------------------------------------------- model publish (f3)
+def test_publish_interval_and_async_mailbox(monkeypatch):
+    """`pub_model` with publish_interval = k sends every k-th state dict; with publish_async the wire encoding runs on a worker
+    thread behind a newest-wins mailbox: the last published model always arrives, frames decode to the reference's wire format
+    (pickle(Protocol.Model), compressed pickle of the state dict -- utils/utils.py:244-245)."""
+    import pickle
+    import sys
+    import threading
+    import time
+    import types
+    from types import SimpleNamespace
+    from b200rl.agents import learner as LM
+    from b200rl.utils.utils import Protocol
+    fake = types.ModuleType("blosc2")
+    fake.compress = lambda b, clevel=1: b[::-1]               # (blosc2 is not installed in the test image: any invertible stand-in)
+    monkeypatch.setitem(sys.modules, "blosc2", fake)
+
+    class Sock:
+        def __init__(self, delay=0.0):
+            self.frames, self.delay = [], delay
+
+        def send_multipart(self, parts):
+            time.sleep(self.delay)
+            self.frames.append(parts)
+
+    def decode(parts):
+        proto, payload = parts
+        return pickle.loads(proto), pickle.loads(payload[::-1])
+
+    lb = LM.LearnerBase.__new__(LM.LearnerBase)
+    lb.args = SimpleNamespace(publish_interval=3, publish_async=False)
+    lb.pub_socket = Sock()
+    for i in range(7):
+        lb.pub_model({"w": torch.full((2,), float(i))})
+    assert [float(decode(f)[1]["w"][0]) for f in lb.pub_socket.frames] == [0.0, 3.0, 6.0]
+    assert decode(lb.pub_socket.frames[0])[0] == Protocol.Model
+
+    lb2 = LM.LearnerBase.__new__(LM.LearnerBase)
+    lb2.args = SimpleNamespace(publish_interval=1, publish_async=True)
+    lb2.pub_socket = Sock(delay=0.02)
+    buf = torch.zeros(2)
+    for i in range(20):
+        buf.fill_(float(i))                                  # the caller reuses its snapshot buffer
+        lb2.pub_model({"w": buf})
+    lb2.pub_flush()
+    got = [float(decode(f)[1]["w"][0]) for f in lb2.pub_socket.frames]
+    assert got == sorted(got) and got[-1] == 19.0 and len(got) + lb2.pub_dropped == 20 and lb2.pub_dropped > 0
+    lb2.pub_socket = None                                     # (__del__ closes real sockets only)
+    lb.pub_socket = None
