@@ -13,31 +13,27 @@
 // Split precision: A_hi (TF32) lives in tensor memory (256 columns) and meets dpre_hi and dpre_lo (TF32, K-major B
 // operands in shared memory, rewritten every step by the cell phase) in two kind::tf32 MMAs per K-step; the third term
 // A_lo . dpre_hi is ~2^-11 of the result, so it runs in bf16 (kind::f16, K = 16: half the MMAs): A_lo as bf16 pairs
-// is 128 more TMEM columns and dpre_hi gets a bf16 copy.  Its error is 2^-9 of a 2^-11 term, i.e. ~2^-20 relative, the
-// same order as the dropped lo*lo term.  (With A_lo in TF32 the last 64 K columns did not fit in tensor memory and
-// ran as SS-form MMAs that pull 4 KB of A through shared memory each: +0.06 ms for 8 of them.)  96 MMAs per step; one thread gets a small tcgen05.mma out only every ~60-120 cycles while issues from
-// different threads overlap (tools/tc_probe3.cu), so TWO issuer warps split K into halves with an accumulator each and
-// the readers sum the partials.  Measured alternatives (tools/bwd_prof.cu, same shape): 1 issuer 0.68 ms, 2 issuers
-// 0.43 ms, 3 issuers (A_lo: 160 columns in TMEM) 0.50 ms, 4 issuers (128 columns) 0.59 ms -- every extra accumulator
-// pushes 32 more K columns of A_lo out of tensor memory into SS-form MMAs that pull 4 KB each through shared memory.
+// is 128 more TMEM columns and dpre_hi gets a bf16 copy.  80 MMAs per step; one thread gets a small tcgen05.mma out only
+// every ~60-120 cycles while issues from different threads overlap (tools/tc_probe3.cu), so TWO issuer warps split K
+// into halves with an accumulator each and the readers sum the partials (1 / 2 / 3 / 4 issuers: 0.68 / 0.43 / 0.50 / 0.59 ms --
+// every extra accumulator pushes 32 more K columns of A_lo out of tensor memory into SS-form MMAs).
 //
-// Cell phase: TMEM lanes are bound to the warp's quarter, so dh_rec (lanes 0-63) is only visible to warps
-// with id % 4 in {0, 1} -- and those share two of the four SM sub-partitions.  The work is therefore split:
-//   HELPER warps (id % 4 in {2, 3}; same unit and sequences as their partner) own everything that does not
-//   depend on dh: the global loads of the saved activations, tanh(c_t), dhead . W_head and the products
-//   P_o = tc o(1-o), Q = o(1-tc^2), P_i = g i(1-i), P_f = c_{t-1} f(1-f), P_g = i(1-g^2), f -- computed for
-//   step t-1 WHILE the tensor core runs step t, and handed over through shared memory; they also drain the
-//   dx lanes of the accumulator to `dx`.
-//   CRITICAL warps (id % 4 in {0, 1}) wait for the accumulator and publish dh_rec of half of their cells to the
-//   partner; then BOTH threads of a pair finish four cells each with 7 flops per cell:
-//   dh = D + dhW ; d_o' = dh P_o ; dct = dh Q + dc ; (dct P_i, dct P_f, dct P_g) ; dc = dct f,
-//   store dpre (global + B operand hi/lo) and hand the step to the issuers.
+// Cell phase -- SYMMETRIC since round 2.  TMEM lanes are bound to the warp's quarter: dh_rec (lanes 0-63) is only visible
+// to warps with id % 4 in {0, 1} ("A"), dx (lanes 64-127) only to {2, 3} ("B"), and the two kinds sit on different SM
+// sub-partitions.  Round 1 gave the B warps ("helpers") ALL the dh-independent work of a step for the 8 sequences of a
+// group (loads, tanh, seven coefficients per cell through shared memory) and measured them as the bottleneck: 6.7K
+// cycles per step of helper instructions while the A warps idled ~4.7K waiting (tools/bwd_prof.cu).  Now thread A(unit j)
+// and thread B(unit j) of a group each OWN 4 of its 8 sequences end to end: they prefetch their cells' saved activations
+// and dhead rows, turn them into seven per-cell coefficients IN REGISTERS while the tensor core runs the previous step,
+// and after the accumulator lands do 7 flops per cell.  The only exchange is dh_rec of B's four cells (A reads it from
+// tensor memory, hands it over through 512 bytes of shared memory); B also drains dx.  Half the instructions per
+// thread, no coefficient traffic through shared memory, both sub-partition pairs equally loaded.
 //
-// Fused small gradients (`fuse`, Fin == 4 and NH <= 4): the helper threads also own
-//   dW_head[o][j] += dhead[b,t,o] h[b,t,j], db_head[o] += dhead[b,t,o]     (h = o tanh(c) is recomputed: tanh(c) is already there)
-//   dWt[j][f] += dxm obs[b,t,f], dbt[j] += dxm, dxm = dx[b,t,j] [x[b,t,j] > 0]   (dx straight from the accumulator, x from the 4-wide obs)
-// in registers across all T steps and write ONE slab row per CTA at the end: the head_grad pass (re-reads 134 MB of h) and the
-// torso_grad pass (134 MB of dx written here, read back there) of round 1 disappear, and dx never goes to HBM.
+// Fused small gradients (template NHT > 0, i.e. NH <= 4 known at compile time): every cell thread also accumulates
+//   dW_head[o][j] += dhead[b,t,o] h[b,t,j] (h = o tanh(c) is recomputed), db_head[o] += dhead[b,t,o]
+// and, with `fz.torso`, the B threads
+//   dWt[j][f] += dxm obs[b,t,f], dbt[j] += dxm, dxm = dx[b,t,j] [x[b,t,j] > 0]   (dx straight from the accumulator)
+// in registers across all T steps; ONE slab row per CTA is written at the end.
 #include "common.cuh"
 #include "tc05.cuh"
 #include "launchers.cuh"
@@ -58,7 +54,7 @@ namespace btk {
 #ifndef B200RL_BWD_NI
 #define B200RL_BWD_NI 2
 #endif
-constexpr int H = 64, G = 256, TB = 32, NC = 512, NI = B200RL_BWD_NI, NT = NC + 32 * NI;    // 8 critical + 8 helper warps, NI MMA issuer warps
+constexpr int H = 64, G = 256, TB = 32, NC = 512, NI = B200RL_BWD_NI, NT = NC + 32 * NI;    // 8 A + 8 B cell warps, NI MMA issuer warps
 constexpr int B_LBO = 144, B_SBO = 9216;                            // B: 64 core matrices along K, 16-byte skew -> conflict-free 16-byte stores
 constexpr int B_BYTES = (TB / 8) * B_SBO;                           // 36864 per hi / lo
 static_assert(63 * B_LBO + 128 <= B_SBO, "core matrices of one 8-row group must fit below SBO");
@@ -67,12 +63,13 @@ constexpr int C_BYTES = (TB / 8) * C_SBO;                           // 18432
 static_assert(31 * C_LBO + 128 <= C_SBO, "core matrices of one 8-row group must fit below SBO");
 constexpr int TM_D = 0, TM_AH = NI * TB, TM_AL = TM_AH + G, TM_COLS = 512;     // accumulator i at columns 32 i ; A_lo: bf16 pairs, G/2 columns
 static_assert(TM_AL + G / 2 <= TM_COLS, "tensor memory budget");
-constexpr int NCOEF = 7;                                            // dhW, P_o, Q, P_i, P_f, P_g, f
-constexpr int CELLS = TB * H;
+constexpr int CT = 4;                                               // cells (sequences) a thread owns
+constexpr int RED = 4 * 10 * H;                                     // end-of-kernel reduction scratch: [sequence group][10][unit]
 }  // namespace btk
 
 static inline size_t bwdt_smem_bytes(int NH) {
-    return 2 * (size_t)btk::B_BYTES + btk::C_BYTES + sizeof(float) * (size_t)(btk::NCOEF * btk::CELLS + NH * btk::H + 8 * 8 * NH + 8 * 4 * 32 + 8 * 32 + btk::H * 4 + btk::H) + 64;
+    return 2 * (size_t)btk::B_BYTES + btk::C_BYTES
+         + sizeof(float) * (size_t)(NH * btk::H + 16 * btk::CT * NH + 8 * btk::CT * 32 + 8 * 32 + btk::H * 4 + btk::H + btk::RED) + 64;
 }
 
 struct BwdFuse {                 // fused head / torso gradients (null partials = off)
@@ -93,14 +90,14 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
     unsigned char* B_hi = smem;
     unsigned char* B_lo = smem + B_BYTES;
     unsigned char* B_16 = smem + 2 * B_BYTES;                        // dpre_hi again, as bf16 (K-major, 8 per core-matrix row)
-    float* COEF = reinterpret_cast<float*>(B_16 + C_BYTES);          // COEF[(k*8 + pair)*256 + i*32 + lane]
-    float* WhS = COEF + NCOEF * CELLS;                               // WhS[c*64 + j]
-    float* DHS = WhS + NH * H;                                       // DHS[helper pair][8 sequences * NH]: dhead rows of the step being prepared
-    float* DHX = DHS + 8 * 8 * NH;                                   // DHX[pair][4][lane]: dh_rec of the cells the helper finishes
-    float* OBS = DHX + 8 * 4 * 32;                                   // OBS[helper pair][8 sequences * 4]: observations of the step whose dx is drained next
+    float* WhS = reinterpret_cast<float*>(B_16 + C_BYTES);           // WhS[c*64 + j]
+    float* DHS = WhS + NH * H;                                       // DHS[cell warp][4 sequences * NH]: dhead rows of the step being prepared
+    float* DHX = DHS + 16 * CT * NH;                                 // DHX[pair][4][lane]: dh_rec of the cells the B thread finishes
+    float* OBS = DHX + 8 * CT * 32;                                  // OBS[pair][8 sequences * 4]: observations of the step whose dx is drained next
     float* WTS = OBS + 8 * 32;                                       // Wt[j][0..3]
     float* BTS = WTS + H * 4;                                        // bt[j]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(BTS + H);                   // (8-byte aligned: an even number of floats precedes for every NH)
+    float* REDS = BTS + H;                                           // end-of-kernel reduction scratch
+    uint64_t* bars = reinterpret_cast<uint64_t*>(REDS + RED);        // (8-byte aligned: an even number of floats precedes for every NH)
     uint64_t* b_full = bars, *acc_done = bars + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
 
@@ -186,11 +183,14 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
             }
         }
     } else {
-        const bool helper = q >= 2;
-        const int j = (q & 1) * 32 + lane;                           // LSTM unit (critical / helper) = dx column (helper, TMEM side)
-        const int pair = (q & 1) * 4 + cg;
-        float* CO = COEF + pair * 256 + lane;                        // + (k*8)*256 + i*32
-        float* DX = DHX + pair * 128 + lane;                         // + i*32
+        const bool isB = q >= 2;                                     // B threads see the dx lanes, A threads the dh_rec lanes
+        const int half = q & 1;
+        const int j = half * 32 + lane;                              // LSTM unit (cell math) = dx column (B, TMEM side)
+        const int pair = half * 4 + cg;                              // the A and the B warp of (unit half, sequence group)
+        const int mine = isB ? CT : 0;                               // my 4 of the group's 8 sequences
+        float* DX = DHX + pair * (CT * 32) + lane;                   // + i*32
+        float* dhs = DHS + warp * (CT * NH);                         // my warp's dhead rows [i*NH + c]
+        float* obs_s = OBS + pair * 32;
         auto read_acc = [&](float (&d)[8]) {                         // my lane's 8 sequences: the NI partial accumulators summed
             uint32_t u[NI][8];                                       // all loads in flight, one wait
 #pragma unroll
@@ -204,8 +204,8 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
             }
         };
         uint32_t nb = 0;                                             // accumulator batches waited for so far
-        // fused small gradients, helper threads, summed over every step of every tile of this CTA: dW_head[o][j], dWt[j][f], dbt[j],
-        // db_head[lane] (lanes < NH of the half-0 warps)
+        // fused small gradients, summed over every step of every tile of this CTA: dW_head[o][j], db_head[lane] (lanes < NH of the
+        // half-0 warps), and on B threads dWt[j][f], dbt[j]
         float aWh[NHT > 0 ? NHT : 1], aWt[4], abt = 0.f, abh = 0.f;
 #pragma unroll
         for (int o = 0; o < (NHT > 0 ? NHT : 1); ++o) aWh[o] = 0.f;
@@ -213,27 +213,140 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
         for (int f = 0; f < 4; ++f) aWt[f] = 0.f;
         BWP_INIT
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int b0 = tile * TB + cg * 8;
-            auto seq = [&](int i) { const int b = b0 + i; return b < B ? b : B - 1; };
+            const int b0 = tile * TB + cg * 8;                       // first sequence of the group ; mine: b0 + mine + i
+            auto seq = [&](int i) { const int b = b0 + mine + i; return b < B ? b : B - 1; };
             auto rowof = [&](int i) { return (unsigned)seq(i) * (unsigned)T; };   // B*T < 2^31 (checked by the launcher)
-            // the dh-dependent tail of the cell backward for cells i0 .. i0+3 of (unit j, this sequence group): 7 flops per
-            // cell from the prepared coefficients, dpre to global memory and to the B operand (hi / lo)
-            auto cell_phase = [&](int t, int i0, const float (&dh4)[4], float (&dc)[4], float4 (&dps)[4]) {
+            auto ok = [&](int i) { return b0 + mine + i < B; };
+            float4 gcur[CT]; float ccur[CT], cprev[CT];
+            float cf_w[CT], cf_po[CT], cf_q[CT], cf_pi[CT], cf_pf[CT], cf_pg[CT], cf_f[CT];    // the step's coefficients, in registers
+            auto load_step = [&](int t) {                            // saved activations of step t and c_{t-1}, my 4 cells
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int ii = i0 + i;
-                    float cf[NCOEF];
+                for (int i = 0; i < CT; ++i) {
+                    const size_t o = (size_t)(rowof(i) + t) * H + j;
+                    gcur[i] = ld4(gates + o * 4);
+                    cprev[i] = t > 0 ? c_sav[o - H] : cx0[(size_t)seq(i) * H + j];
+                }
+            };
+            auto fetch_dhead = [&](int t) {                          // asynchronous: lands in shared memory, no registers held
+                __syncwarp();                                        // the previous step's values have been consumed by every lane
+                for (int e = lane; e < CT * NH; e += 32) {
+                    const int i = e / NH, c = e - i * NH;
+                    const int bb = b0 + mine + i;
+                    cp_async4(dhs + e, dhead + ((size_t)(bb < B ? bb : B - 1) * T + t) * NH + c);
+                }
+            };
+            auto fetch_obs = [&](int t) {                            // (B, fused torso) observations of step t for the group's 8 sequences
+                __syncwarp();
+                const int bb = b0 + (lane >> 2);
+                cp_async4(obs_s + lane, fz.u + ((size_t)(bb < B ? bb : B - 1) * T + t) * 4 + (lane & 3));
+            };
+            auto torso = [&](const float (&dxv)[8]) {                // dWt, dbt from dx of the step whose observations sit in obs_s
+                const float4 w = ld4(WTS + j * 4);
+                const float btj = BTS[j];
 #pragma unroll
-                    for (int k = 0; k < NCOEF; ++k) cf[k] = CO[k * 2048 + ii * 32];
-                    const float dh = dh4[i] + cf[0];
-                    const float dct = fmaf(dh, cf[2], dc[i]);
-                    const float4 dp = make_float4(dct * cf[3], dct * cf[4], dct * cf[5], dh * cf[1]);
-                    dc[i] = dct * cf[6];
+                for (int i = 0; i < 8; ++i) {
+                    const float4 o4 = ld4(obs_s + i * 4);
+                    const float x = fmaf(w.x, o4.x, fmaf(w.y, o4.y, fmaf(w.z, o4.z, fmaf(w.w, o4.w, btj))));
+                    const float d = (x > 0.f && b0 + i < B) ? dxv[i] : 0.f;
+                    aWt[0] = fmaf(d, o4.x, aWt[0]); aWt[1] = fmaf(d, o4.y, aWt[1]);
+                    aWt[2] = fmaf(d, o4.z, aWt[2]); aWt[3] = fmaf(d, o4.w, aWt[3]);
+                    abt += d;
+                }
+            };
+            auto coefs = [&]() {                                     // everything of the loaded step that does not need dh
+                cp_async_wait_all();
+                __syncwarp();
+                float tch[CT];
+#pragma unroll
+                for (int i = 0; i < CT; ++i) { cf_w[i] = 0.f; tch[i] = tanh_(ccur[i]); }
+                if (fuse) {
+                    // compile-time head count: fully unrolled ; dW_head[c][j] += dhead[b,t,c] h[b,t,j] rides on the same dhead values
+#pragma unroll
+                    for (int c = 0; c < (NHT > 0 ? NHT : 1); ++c) {
+                        const float w = WhS[c * H + j];
+                        float a = 0.f;
+#pragma unroll
+                        for (int i = 0; i < CT; ++i) {
+                            const float d = dhs[i * NHT + c];
+                            cf_w[i] = fmaf(d, w, cf_w[i]);
+                            a = fmaf(ok(i) ? d : 0.f, gcur[i].w * tch[i], a);
+                        }
+                        aWh[c] += a;
+                    }
+                    if (half == 0 && lane < NHT) {
+#pragma unroll
+                        for (int i = 0; i < CT; ++i) abh += ok(i) ? dhs[i * NHT + lane] : 0.f;
+                    }
+                } else {
+                    // head index outermost: ONE runtime loop with independent FMA chains inside
+                    for (int c = 0; c < NH; ++c) {
+                        const float w = WhS[c * H + j];
+#pragma unroll
+                        for (int i = 0; i < CT; ++i) cf_w[i] = fmaf(dhs[i * NH + c], w, cf_w[i]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < CT; ++i) {
+                    const float4 g4 = gcur[i];                       // i, f, g, o (post-activation)
+                    const float th = tch[i];
+                    cf_po[i] = th * g4.w * (1.f - g4.w);
+                    cf_q[i] = g4.w * (1.f - th * th);
+                    cf_pi[i] = g4.z * g4.x * (1.f - g4.x);
+                    cf_pf[i] = cprev[i] * g4.y * (1.f - g4.y);
+                    cf_pg[i] = g4.x * (1.f - g4.z * g4.z);
+                    cf_f[i] = g4.y;
+                }
+            };
+#pragma unroll
+            for (int i = 0; i < CT; ++i) ccur[i] = c_sav[(size_t)(rowof(i) + T - 1) * H + j];
+            load_step(T - 1);
+            fetch_dhead(T - 1);
+            coefs();
+            float dc[CT];
+#pragma unroll
+            for (int i = 0; i < CT; ++i) dc[i] = 0.f;
+            for (int t = T - 1; t >= 0; --t) {
+                BWP(0, 0); BWP(8, 64);
+                // next step's inputs: c_{t-1} becomes c_t ; the loads fly during this step's hand-over and are consumed by coefs() below
+#pragma unroll
+                for (int i = 0; i < CT; ++i) ccur[i] = cprev[i];
+                if (t > 0) { load_step(t - 1); fetch_dhead(t - 1); }
+                float acc[8];                                        // A: dh_rec of the group's 8 sequences ; B: dx_{t+1} of them
+                if (t < T - 1) {
+                    tc::mbar_wait(acc_done, nb & 1); ++nb;
+                    tc::fence_after_sync();
+                    BWP(1, 0); BWP(9, 64);
+                    read_acc(acc);
+                    tc::fence_before_sync();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+                }
+                BWP(2, 0); BWP(10, 64);
+                float dh4[CT];
+                if (!isB) {
+#pragma unroll
+                    for (int i = 0; i < CT; ++i) { DX[i * 32] = acc[CT + i]; dh4[i] = acc[i]; }
+                    tc::named_bar_sync(1 + pair, 64);
+                } else {
+                    tc::named_bar_sync(1 + pair, 64);                // the A thread has published dh_rec of my cells
+#pragma unroll
+                    for (int i = 0; i < CT; ++i) dh4[i] = DX[i * 32];
+                }
+                BWP(3, 0); BWP(11, 64);
+                // the dh-dependent tail: 7 flops per cell from the register coefficients ; dpre to the B operand (hi / lo / bf16)
+                float4 dps[CT];
+#pragma unroll
+                for (int i = 0; i < CT; ++i) {
+                    const float dh = dh4[i] + cf_w[i];
+                    const float dct = fmaf(dh, cf_q[i], dc[i]);
+                    const float4 dp = make_float4(dct * cf_pi[i], dct * cf_pf[i], dct * cf_pg[i], dh * cf_po[i]);
+                    dc[i] = dct * cf_f[i];
                     dps[i] = dp;
                     float4 hi, lo;
                     tc::split_tf32(dp.x, hi.x, lo.x); tc::split_tf32(dp.y, hi.y, lo.y);
                     tc::split_tf32(dp.z, hi.z, lo.z); tc::split_tf32(dp.w, hi.w, lo.w);
-                    const int r = cg * 8 + ii;
+                    const int r = cg * 8 + mine + i;
                     const int ob = (r & 7) * 16 + (r >> 3) * B_SBO + j * B_LBO;
                     *reinterpret_cast<float4*>(B_hi + ob) = hi;
                     *reinterpret_cast<float4*>(B_lo + ob) = lo;
@@ -241,223 +354,76 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                                                    ((unsigned long long)((unsigned)tc::bf16_bits(hi.z) | ((unsigned)tc::bf16_bits(hi.w) << 16)) << 32);
                     *reinterpret_cast<unsigned long long*>(B_16 + (r & 7) * 16 + (r >> 3) * C_SBO + (j >> 1) * C_LBO + (j & 1) * 8) = h16;
                 }
-            };
-            auto store_dpre = [&](int t, int i0, const float4 (&dps)[4]) {
+                BWP(4, 0); BWP(12, 64);
+                tc::fence_async_smem();
+                tc::mbar_arrive_warp(b_full);
+                BWP(5, 0); BWP(13, 64);
+                // ---- off the serial chain: the tensor core is running this step's GEMM
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (b0 + i0 + i < B) st4(gates + ((size_t)(rowof(i0 + i) + t) * H + j) * 4, dps[i]);
-            };
-            if (helper) {
-                float4 gcur[8]; float ccur[8], cprev[8];
-                auto load_step = [&](int t) {                        // saved activations of step t and c_{t-1}
+                for (int i = 0; i < CT; ++i)
+                    if (ok(i)) st4(gates + ((size_t)(rowof(i) + t) * H + j) * 4, dps[i]);
+                if (isB && t < T - 1) {
+                    if (ftorso) {
+                        torso(acc);                                  // (obs_{t+1} landed before the previous coefs())
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const size_t o = (size_t)(rowof(i) + t) * H + j;
-                        gcur[i] = ld4(gates + o * 4);
-                        cprev[i] = t > 0 ? c_sav[o - H] : cx0[(size_t)seq(i) * H + j];
+                        for (int i = 0; i < 8; ++i) {
+                            const int bb = b0 + i;
+                            if (bb < B) dx[((size_t)bb * T + t + 1) * H + j] = acc[i];
+                        }
                     }
-                };
-                float* dhs = DHS + pair * 8 * NH;
-                auto fetch_dhead = [&](int t) {                      // asynchronous: lands in shared memory, no registers held
-                    __syncwarp();                                    // the previous step's values have been consumed by every lane
-                    for (int e = lane; e < 8 * NH; e += 32) {
-                        const int i = e / NH, c = e - i * NH;
-                        cp_async4(dhs + e, dhead + (size_t)(rowof(i) + t) * NH + c);
-                    }
-                };
-                float* obs_s = OBS + pair * 32;
-                auto fetch_obs = [&](int t) {                        // observations of step t for this warp's 8 sequences (asynchronous)
-                    __syncwarp();
-                    const int bb = b0 + (lane >> 2);
-                    cp_async4(obs_s + lane, fz.u + ((size_t)(bb < B ? bb : B - 1) * T + t) * 4 + (lane & 3));
-                };
-                auto torso = [&](const float (&dxv)[8]) {            // dWt, dbt from dx of the step whose observations sit in obs_s
-                    const float4 w = ld4(WTS + j * 4);
-                    const float btj = BTS[j];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 o4 = ld4(obs_s + i * 4);
-                        const float x = fmaf(w.x, o4.x, fmaf(w.y, o4.y, fmaf(w.z, o4.z, fmaf(w.w, o4.w, btj))));
-                        const float d = (x > 0.f && b0 + i < B) ? dxv[i] : 0.f;
-                        aWt[0] = fmaf(d, o4.x, aWt[0]); aWt[1] = fmaf(d, o4.y, aWt[1]);
-                        aWt[2] = fmaf(d, o4.z, aWt[2]); aWt[3] = fmaf(d, o4.w, aWt[3]);
-                        abt += d;
-                    }
-                };
-                auto coefs = [&](int t) {                            // everything of step t that does not need dh
+                }
+                if (isB && ftorso) fetch_obs(t);                     // for dx_t, drained in the next iteration
+                if (t > 0) coefs();                                  // step t-1, from the loads issued at the top of this iteration
+                BWP(6, 0); BWP(14, 64);
+            }
+            tc::mbar_wait(acc_done, nb & 1); ++nb;                   // batch of step 0 (dx_0)
+            tc::fence_after_sync();
+            if (isB) {
+                float d[8];
+                read_acc(d);
+                if (ftorso) {
                     cp_async_wait_all();
                     __syncwarp();
-                    BWP(13, 64);
-#ifdef B200RL_BWDPROF
-                    if (gcur[0].x == 1234.5f && cprev[7] == 1234.5f && gcur[7].w == 1234.5f) ccur[0] = 0.f;   // force the prefetched loads to have landed
-                    BWP(14, 64);
-#endif
-                    // dhead . W_head with the head index outermost: ONE runtime loop with eight independent FMA chains inside (the
-                    // per-cell form compiled to a branchy unroll cascade per cell that kept the eight cells from overlapping: 4.2K cycles)
-                    float dhw[8], tch[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) { dhw[i] = 0.f; tch[i] = tanh_(ccur[i]); }
-                    if (fuse) {
-                        // compile-time head count: fully unrolled; the head gradient dW_head[c][j] += dhead[b,t,c] h[b,t,j] rides on the
-                        // same dhead values (h = o tanh(c) recomputed)
-#pragma unroll
-                        for (int c = 0; c < (NHT > 0 ? NHT : 1); ++c) {
-                            const float w = WhS[c * H + j];
-                            float a = 0.f;
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float d = dhs[i * NHT + c];
-                                dhw[i] = fmaf(d, w, dhw[i]);
-                                a = fmaf((b0 + i < B) ? d : 0.f, gcur[i].w * tch[i], a);
-                            }
-                            aWh[c] += a;
-                        }
-                        if (q == 2 && lane < NHT) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) abh += (b0 + i < B) ? dhs[i * NHT + lane] : 0.f;
-                        }
-                    } else {
-                        for (int c = 0; c < NH; ++c) {
-                            const float w = WhS[c * H + j];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) dhw[i] = fmaf(dhs[i * NH + c], w, dhw[i]);
-                        }
-                    }
+                    torso(d);
+                    __syncwarp();                                    // (the next tile's first fetch_obs overwrites the slot)
+                } else {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const float4 g4 = gcur[i];                   // i, f, g, o (post-activation)
-                        const float th = tch[i];
-                        float* co = CO + i * 32;
-                        co[0 * 2048] = dhw[i];
-                        co[1 * 2048] = th * g4.w * (1.f - g4.w);
-                        co[2 * 2048] = g4.w * (1.f - th * th);
-                        co[3 * 2048] = g4.z * g4.x * (1.f - g4.x);
-                        co[4 * 2048] = cprev[i] * g4.y * (1.f - g4.y);
-                        co[5 * 2048] = g4.x * (1.f - g4.z * g4.z);
-                        co[6 * 2048] = g4.y;
+                        const int bb = b0 + i;
+                        if (bb < B) dx[(size_t)bb * T * H + j] = d[i];
                     }
-                };
-#pragma unroll
-                for (int i = 0; i < 8; ++i) ccur[i] = c_sav[(size_t)(rowof(i) + T - 1) * H + j];
-                load_step(T - 1);
-                fetch_dhead(T - 1);
-                coefs(T - 1);
-                float dc[4];                                         // cells 4..7 of this (unit, sequence group) are finished here
-#pragma unroll
-                for (int i = 0; i < 4; ++i) dc[i] = 0.f;
-                for (int t = T - 1; t >= 0; --t) {
-                    BWP(8, 64);
-                    // next step's inputs: c_{t-1} becomes c_t, loads fly during this step's hand-over
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) ccur[i] = cprev[i];
-                    if (t > 0) { load_step(t - 1); fetch_dhead(t - 1); }
-                    float dxs[8];                                    // dx_{t+1}: lanes 64..127 of both accumulators
-                    if (t < T - 1) {
-                        tc::mbar_wait(acc_done, nb & 1); ++nb;
-                        tc::fence_after_sync();
-                        BWP(9, 64);
-                        read_acc(dxs);
-                        tc::fence_before_sync();
-                    }
-                    tc::named_bar_sync(1 + pair, 64);                // the critical thread has published dh_rec of my cells
-                    BWP(10, 64);
-                    float dh4[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) dh4[i] = DX[i * 32];
-                    float4 dps[4];
-                    cell_phase(t, 4, dh4, dc, dps);
-                    tc::fence_async_smem();
-                    tc::mbar_arrive_warp(b_full);
-                    store_dpre(t, 4, dps);                           // (HBM stores overlap the tensor core's step)
-                    tc::named_bar_sync(1 + pair, 64);                // both threads have read their coefficients: the slots are free for step t-1
-                    BWP(11, 64);
-                    if (t < T - 1) {
-                        if (ftorso) {
-                            torso(dxs);                              // (obs_{t+1} landed before the previous coefs())
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                if (b0 + i < B) dx[(size_t)(rowof(i) + t + 1) * H + j] = dxs[i];
-                        }
-                    }
-                    if (ftorso) fetch_obs(t);                        // for dx_t, drained in the next iteration
-                    if (t > 0) coefs(t - 1);
-                    BWP(12, 64);
                 }
-                tc::mbar_wait(acc_done, nb & 1); ++nb;               // dx_0
-                tc::fence_after_sync();
-                {
-                    float d[8];
-                    read_acc(d);
-                    if (ftorso) {
-                        cp_async_wait_all();
-                        __syncwarp();
-                        torso(d);
-                        __syncwarp();                                // (the next tile's first fetch_obs overwrites the slot)
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            if (b0 + i < B) dx[(size_t)rowof(i) * H + j] = d[i];
-                    }
-                    tc::fence_before_sync();
-                }
-            } else {
-                float dc[4];                                         // cells 0..3
-#pragma unroll
-                for (int i = 0; i < 4; ++i) dc[i] = 0.f;
-                for (int t = T - 1; t >= 0; --t) {
-                    float dhr[8];
-                    BWP(0, 0);
-                    if (t < T - 1) {
-                        tc::mbar_wait(acc_done, nb & 1); ++nb;
-                        tc::fence_after_sync();
-                        BWP(1, 0);
-                        read_acc(dhr);
-                        tc::fence_before_sync();
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) dhr[i] = 0.f;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) DX[i * 32] = dhr[4 + i];
-                    BWP(2, 0);
-                    tc::named_bar_sync(1 + pair, 64);
-                    BWP(3, 0);
-                    const float dh4[4] = {dhr[0], dhr[1], dhr[2], dhr[3]};
-                    float4 dps[4];
-                    cell_phase(t, 0, dh4, dc, dps);
-                    BWP(5, 0);
-                    tc::fence_async_smem();
-                    tc::mbar_arrive_warp(b_full);
-                    store_dpre(t, 0, dps);
-                    tc::named_bar_sync(1 + pair, 64);
-                    BWP(6, 0);
-                }
-                tc::mbar_wait(acc_done, nb & 1); ++nb;               // batch of step 0 (dx_0): keeps the phase count in step
             }
+            tc::fence_before_sync();
         }
         if (fuse) {
-            // hand the register accumulators to the CTA-wide reduction below (COEF is free once every warp has left its loops)
-            __syncthreads();
-            if (q >= 2) {
-                float* red = COEF + cg * (10 * H) + j;
+            // hand the register accumulators to the CTA-wide reduction below: A and B threads of a (group, unit) own different
+            // sequences, so both contribute
+            float* red = REDS + cg * (10 * H) + j;
+            if (!isB) {
 #pragma unroll
                 for (int o = 0; o < 4; ++o) red[o * H] = o < NHT ? aWh[o < NHT ? o : 0] : 0.f;
+                red[9 * H] = abh;
+            }
+            tc::named_bar_sync(1 + pair, 64);
+            if (isB) {
+#pragma unroll
+                for (int o = 0; o < 4; ++o) red[o * H] += o < NHT ? aWh[o < NHT ? o : 0] : 0.f;
 #pragma unroll
                 for (int f = 0; f < 4; ++f) red[(4 + f) * H] = aWt[f];
                 red[8 * H] = abt;
-                red[9 * H] = abh;
+                red[9 * H] += abh;
             }
         }
-    } 
-    if (fuse && !cellw) __syncthreads();                             // (issuer warps: match the cell warps' extra barrier)
+    }
     tc::fence_before_sync();
     __syncthreads();
     if (fuse) {
         float* slab = fz.partials + (size_t)blockIdx.x * fz.P;
         for (int e = tid; e < 10 * H; e += NT) {
             const int k = e / H, jj = e - k * H;
-            const float v = (COEF[0 * 10 * H + e] + COEF[1 * 10 * H + e]) + (COEF[2 * 10 * H + e] + COEF[3 * 10 * H + e]);
+            const float v = (REDS[0 * 10 * H + e] + REDS[1 * 10 * H + e]) + (REDS[2 * 10 * H + e] + REDS[3 * 10 * H + e]);
             if (k < 4) { if (k < NHT) slab[fz.off_Whead + (size_t)k * H + jj] = v; }
             else if (k < 8) { if (ftorso) slab[fz.off_Wt + (size_t)jj * 4 + (k - 4)] = v; }
             else if (k == 8) { if (ftorso) slab[fz.off_bt + jj] = v; }
@@ -500,8 +466,6 @@ int launch_bwd_tc_fused(const float* dhead, const float* W_head, const float* W_
     }
     B200RL_REQUIRE(NH >= 1 && NH <= 4, "lstm_bwd(tc, fused gradients): needs NH <= 4 (NH=%d)", NH);
     B200RL_REQUIRE(dx != nullptr || (Fin == 4 && u && Wt && bt), "lstm_bwd(tc, fused torso gradients): needs Fin == 4 (Fin=%d)", Fin);
-    const int ntiles = (B + btk::TB - 1) / btk::TB;
-    B200RL_REQUIRE((ntiles < sms ? ntiles : sms) >= 1, "lstm_bwd(tc): empty grid");
     switch (NH) {
         case 1: return launch_bwdt<1>(dhead, W_head, W_hh, W_ih, gates, c, cx0, dx, B, T, NH, fz, sms, stream);
         case 2: return launch_bwdt<2>(dhead, W_head, W_hh, W_ih, gates, c, cx0, dx, B, T, NH, fz, sms, stream);

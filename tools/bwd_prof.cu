@@ -48,11 +48,11 @@ int main(int argc, char** argv) {
     return 0;
 #endif
     const double steps = (B / 32.0) * T;
-    printf("bwd_tc (fused mode %d) %.3f ms; cycles/step critical thread: loop top %.0f | wait acc_done %.0f | tmem ld %.0f | wait coefs %.0f | read coefs + bar %.0f | 8 cells %.0f | fence+arrive %.0f\n",
+    printf("bwd_tc (fused mode %d) %.3f ms; cycles/step A thread: loads issue %.0f | wait acc_done %.0f | tmem ld %.0f | publish + pair barrier %.0f | 4 cells + operand %.0f | fence + arrive %.0f | stores + coefs(t-1) %.0f\n",
            mode, ms, z[0] / steps, z[1] / steps, z[2] / steps, z[3] / steps, z[4] / steps, z[5] / steps, z[6] / steps);
-    printf("   helper: loop top %.0f | issue loads + wait acc_done %.0f | drain dx %.0f | arrive + 2 pair barriers %.0f | coefs(t-1) %.0f  [before it: dx stores + cp.async wait %.0f | prefetched loads land %.0f]\n",
+    printf("   B thread: loads issue %.0f | wait acc_done %.0f | tmem ld %.0f | pair barrier + read dh %.0f | 4 cells + operand %.0f | fence + arrive %.0f | stores + dx + coefs(t-1) %.0f\n",
            z[8] / steps, z[9] / steps, z[10] / steps, z[11] / steps, z[12] / steps, z[13] / steps, z[14] / steps);
-    printf("   issuer: loop top %.0f | wait b_full %.0f | issue 48 MMAs + commit %.0f\n", z[16] / steps, z[17] / steps, z[18] / steps);
+    printf("   issuer: loop top %.0f | wait b_full %.0f | issue 40 MMAs + commit %.0f\n", z[16] / steps, z[17] / steps, z[18] / steps);
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
