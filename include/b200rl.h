@@ -251,6 +251,11 @@ int b200rl_sac_cont_critic_head(const float* tq1, const float* tq2, const float*
 int b200rl_sac_alpha_step(double* state, const double* scalars, double* out, double denominator,
                           double target_entropy, double lr, int step, void* stream);
 
+/* ---- host -> device batch path (reference agents/learner.py:197-233 + utils/utils.py:101-103) ----------
+ * rows of `width_bytes` at stride `src_pitch_bytes` in PAGE-LOCKED host memory -> contiguous device rows, one async 2-D DMA:
+ * hx / cx = [:, 0] of the (B, T, H) shared arrays go to the device without a host-side gather.                          */
+int b200rl_h2d_rows(void* dst, const void* src, long long width_bytes, long long rows, long long src_pitch_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

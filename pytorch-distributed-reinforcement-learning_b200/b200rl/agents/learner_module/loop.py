@@ -103,9 +103,14 @@ async def run_learning(parent, timer, queue_name, update, losses, publish_state,
                     if pending is not None and queue.empty():
                         # nothing to overlap with: the feeder is slower than the learner (the normal case with real workers), so
                         # publish / log iteration i NOW instead of after the next batch has been collected -- otherwise the
-                        # workers would gather all of batch i+1 under model i-1
-                        finish(*pending)
-                        pending = None
+                        # workers would gather all of batch i+1 under model i-1.  The wait for the GPU is cooperative: the
+                        # batching coroutine keeps running (it ships the next batch while this update computes); if a batch
+                        # arrives first, the update for it is enqueued before the host side of iteration i is finished.
+                        while not engine.snapshot_ready(pending[1]) and queue.empty():
+                            await asyncio.sleep(0)
+                        if queue.empty():
+                            finish(*pending)
+                            pending = None
                     batch_args = await _next_batch(queue, parent.stop_event)
             if batch_args is not None:
                 with timer.timer("learner-forward-time"):

@@ -101,6 +101,7 @@ class PeerChannel:
         self.scal_views = [_view(data(self.base, p) + n * 4, 8, torch.float64, device) for p in (0, 1)]
         self.status = _view(self.base + 5120, 1, torch.int32, device)
         self.grid = GRID
+        self.pre_step = None           # test-only hook (LoopbackWorld): called right before the kernel is launched
 
     def begin(self):
         """Start the next step: returns (gradient buffer, loss-sum buffer) this rank must fill before `step()`."""
@@ -112,6 +113,8 @@ class PeerChannel:
              adam_step, stream):
         p = self.epoch & 1
         self.gsync_target += self.grid
+        if self.pre_step is not None:
+            self.pre_step()
         ptr = native.ptr
         self.lib.call("b200rl_peer_step", optimizer, ptr(param), ptr(s1), ptr(s2), ptr(mask), ptr(grad_out),
                       self._grad_ptrs[p], self._scal_ptrs[p], self._flag_ptrs, self.base, self.base + 2048, self.base + 4096,
@@ -223,6 +226,10 @@ class _LoopbackComm:
         # all "ranks" share ONE GPU here: keep the spinning peer kernels small enough that whole SMs stay free for the other
         # ranks' recurrent kernels (which need an SM to themselves)
         ch.grid = max(1, min(GRID, -(-(n // 4) // (256 * 4))))
+        # ... and let every rank drain its stream and meet the others before the handshake kernels are launched: with all "ranks"
+        # in one process their streams share the device's launch queues, and a handshake kernel that spins while another rank's
+        # producer kernels are still queued behind it can wait for ever.  (One process per GPU has no such coupling.)
+        ch.pre_step = self.barrier
         return ch
 
     def close(self):

@@ -202,6 +202,10 @@ class OnPolicyEngine:
             ev.record(torch.cuda.current_stream(self.device))
         return (b, ev, with_losses)
 
+    def snapshot_ready(self, handle):
+        """True once the snapshot's copies have landed (never blocks)."""
+        return handle[1] is None or handle[1].query()
+
     def snapshot_wait(self, handle):
         b, ev, with_losses = handle
         if ev is not None:

@@ -40,6 +40,7 @@ SIGNATURES = {
     "b200rl_vmpo_dual_step": [_P] * 4 + [C.c_double] * 9 + [_P],
     "b200rl_clip_rmsprop": [_P, _P, _P, _L] + [_F] * 5 + [_P, _P],
     "b200rl_clip_adam": [_P, _P, _P, _P, _L] + [_F] * 6 + [_I, _P, _P, _P],
+    "b200rl_h2d_rows": [_P, _P, _L, _L, _L, _P],
     "b200rl_peer_alloc": [_L, _P, _P],
     "b200rl_peer_open": [_P, _P],
     "b200rl_peer_close": [_P],
