@@ -22,7 +22,11 @@ HYPER = dict(hidden_size=64, gamma=0.99, lmbda=0.95, eps_clip=0.1, policy_loss_c
              coef_alpha_upper=0.01, coef_alpha_below=0.005, K_epoch=1)
 
 
+ITERS = int(os.environ.get("SCAN_BENCH_ITERS", "0"))      # > 0: fixed small iteration count (under ncu)
+
+
 def timeit(fn, iters=20):
+    iters = ITERS or iters
     fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
