@@ -50,7 +50,8 @@ constexpr int NG = 4, RW = TB / NG, CT = RW / 2;          // sequence groups, se
 #endif
 constexpr int NI = 4;                                      // issuers per operand: (M tile) x (even / odd K-steps), one accumulator each
 constexpr int NIW = B200RL_FWD3_SEP ? 2 * NI : NI;         // issuer warps
-constexpr int NC = NG * 128, NT = NC + 32 * NIW;
+constexpr int NPW = 4;                                     // producer warps: the torso output x_t as a K-major operand, two steps ahead
+constexpr int NC = NG * 128, NT = NC + 32 * NIW + 32 * NPW;
 constexpr int TM_D = 0, TM_HH = 128, TM_IH = 256, TM_HHL = 384, TM_IHL = 448, TM_COLS = 512;
 constexpr int B_LBO = 144, B_SBO = 2304;                   // TF32 B operand: 16 core matrices (4 k) along K, 16-byte skew -> conflict-free 4-byte scatter
 constexpr int B_BYTES = (TB / 8) * B_SBO;                  // 9216 per hi / lo
@@ -58,7 +59,7 @@ constexpr int C_LBO = 144, C_SBO = 1152;                   // bf16 B operand: 8 
 constexpr int C_BYTES = (TB / 8) * C_SBO;                  // 4608
 constexpr int OP_BYTES = 2 * B_BYTES + C_BYTES;            // one operand set: hi | lo | bf16(hi)
 constexpr int EXF = 2 * NG * 2 * RW * 32;                  // swap buffer [pair][direction][slot][lane] floats
-constexpr int NBAR = 8;
+constexpr int NBAR = 8;                                    // b_full, acc_done, acc_free, x_done, x_full[2], x_free[2]
 static_assert(15 * B_LBO + 128 <= B_SBO && 7 * C_LBO + 128 <= C_SBO, "core matrices of one 8-row group must fit below SBO");
 static_assert(RW == 8 && CT == 4, "cell phase layout");
 }  // namespace ffk
@@ -84,11 +85,12 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
     float* BT = WT + H * MAXF;                              // bt[j]
     float* WH = BT + H;                                     // WH[j*4 + o]
     uint64_t* bars = reinterpret_cast<uint64_t*>(WH + H * 4);
-    uint64_t* b_full = bars, *acc_done = bars + 1, *acc_free = bars + 2, *x_done = bars + 3, *x_full = bars + 4;   // x_full[2]
+    uint64_t* b_full = bars, *acc_done = bars + 1, *acc_free = bars + 2, *x_done = bars + 3, *x_full = bars + 4, *x_free = bars + 6;   // x_full[2], x_free[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool compute = warp < NC / 32;
+    const bool producer = warp >= NC / 32 + NIW;
 
     for (int i = tid; i < H * 4; i += NT) { const int j = i >> 2, g = i & 3; BI[i] = b_ih[g * H + j] + b_hh[g * H + j]; }
     for (int i = tid; i < H * MAXF; i += NT) { const int j = i >> 3, f = i & 7; WT[i] = f < Fin ? Wt[j * Fin + f] : 0.f; }
@@ -96,7 +98,8 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
     for (int i = tid; i < H * 4; i += NT) { const int j = i >> 2, o = i & 3; WH[i] = (head_part != nullptr && o < NH) ? W_head[o * H + j] : 0.f; }
     if (tid == 0) {
         tc::mbar_init(b_full, NC / 32); tc::mbar_init(acc_done, NI); tc::mbar_init(acc_free, NC / 32); tc::mbar_init(x_done, NI);
-        tc::mbar_init(x_full, NC / 32); tc::mbar_init(x_full + 1, NC / 32);
+        tc::mbar_init(x_full, NPW); tc::mbar_init(x_full + 1, NPW);
+        tc::mbar_init(x_free, NI); tc::mbar_init(x_free + 1, NI);
         tc::fence_mbar_init();
     }
     if (warp == NC / 32) tc::tmem_alloc(tmem_slot, TM_COLS);
@@ -155,8 +158,55 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
             tc::mma_bf16_ts(D, Alo + s * 8, tc::make_desc(op + 2 * B_BYTES + s * 2 * C_LBO, C_LBO, C_SBO), idesc16, 1u);
     };
 
-    if (!compute) {
-#if B200RL_FWD3_SEP && !defined(B200RL_EMUL)
+    if (producer) {
+#ifndef B200RL_EMUL
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+#endif
+        // x[r][j] = ReLU(bt[j] + Wt[j] . obs[r, t]) for the tile's 32 sequences: thread = (unit j, 16 of the sequences), element
+        // (r, j) of operand set t & 1 as TF32 hi / lo and bf16(hi)
+        const int pt = tid - (NC + 32 * NIW), j = pt & 63, r0 = (pt >> 6) * 16;
+        auto tf = [&](int r) { return (r & 7) * 16 + (r >> 3) * B_SBO + (j & 3) * 4 + (j >> 2) * B_LBO; };
+        auto bf = [&](int r) { return 2 * B_BYTES + (r & 7) * 16 + (r >> 3) * C_SBO + (j & 7) * 2 + (j >> 3) * C_LBO; };
+        const float btj = BT[j];
+        float wt[MAXF];
+#pragma unroll
+        for (int f = 0; f < MAXF; ++f) wt[f] = WT[j * MAXF + f];
+        uint32_t written[2] = {0, 0};
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int b0 = tile * TB;
+            for (int t = 0; t < T; ++t) {
+                const int p = t & 1;
+                unsigned char* op = OPX + p * OP_BYTES;
+                float xv[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {                          // (the loads of a step do not wait for the operand set)
+                    const int b = b0 + r0 + i;
+                    const size_t row = (size_t)(b < B ? b : B - 1) * T + t;
+                    float x = btj;
+                    if (F4) {
+                        const float4 o = ld4(u + row * 4);
+                        x = fmaf(wt[0], o.x, fmaf(wt[1], o.y, fmaf(wt[2], o.z, fmaf(wt[3], o.w, x))));
+                    } else {
+                        for (int f = 0; f < Fin; ++f) x = fmaf(wt[f], __ldg(u + row * Fin + f), x);
+                    }
+                    xv[i] = fmaxf(x, 0.f);
+                }
+                if (written[p] > 0) tc::mbar_wait(x_free + p, (written[p] - 1) & 1);     // the MMAs that last read this set are done
+                ++written[p];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float hi, lo;
+                    tc::split_tf32(xv[i], hi, lo);
+                    *reinterpret_cast<float*>(op + tf(r0 + i)) = hi;
+                    *reinterpret_cast<float*>(op + B_BYTES + tf(r0 + i)) = lo;
+                    *reinterpret_cast<unsigned short*>(op + bf(r0 + i)) = tc::bf16_bits_rn(hi);
+                }
+                tc::fence_async_smem();
+                tc::mbar_arrive_warp(x_full + p);
+            }
+        }
+    } else if (!compute) {
+#if !defined(B200RL_EMUL)
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
 #endif
         if (lane == 0) {
@@ -181,6 +231,7 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
                         F3P(13, NC + 32 * NI);
                         issue(D, Aih, Aihl, OPX + p * OP_BYTES, kh, true);
                         tc::mma_commit(x_done);
+                        tc::mma_commit(x_free + p);          // (the producers may refill this operand set once these MMAs have read it)
                         F3P(14, NC + 32 * NI);
                     }
             } else {
@@ -206,6 +257,7 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
                     if (N > 0) tc::mbar_wait(acc_free, (uint32_t)(N - 1) & 1);
                     tc::fence_after_sync();
                     issue(D, Aih, Aihl, OPX + p * OP_BYTES, kh, true);
+                    tc::mma_commit(x_free + p);
                     tc::mbar_wait(b_full, (uint32_t)N & 1);
                     tc::fence_after_sync();
                     issue(D, Ahh, Ahhl, OPH, kh, false);
@@ -214,8 +266,8 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
 #endif
         }
     } else {
-#if B200RL_FWD3_SEP && !defined(B200RL_EMUL)
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+#if !defined(B200RL_EMUL)
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
 #endif
         const int q = warp & 3, ch = warp >> 2;                // TMEM lane quarter, sequence group
         const bool fo = q >= 2;                                // false: gates (i, g) ; true: gates (f, o)
@@ -248,34 +300,6 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
             const int b0 = tile * TB;
             auto seq = [&](int i) { const int b = b0 + rbase + mine + i; return b < B ? b : B - 1; };
             auto rowof = [&](int i) { return (unsigned)seq(i) * (unsigned)T; };       // B*T < 2^31 (checked by the launcher)
-            // torso output x[seq i][unit j] at step tt into operand set tt & 1
-            float4 ob[CT];                                     // (F4) observations of the step whose x is produced next
-            auto load_obs = [&](int tt) {
-                if (F4) {
-#pragma unroll
-                    for (int i = 0; i < CT; ++i) ob[i] = ld4(u + (size_t)(rowof(i) + tt) * 4);
-                }
-            };
-            auto make_x = [&](int tt) {
-                unsigned char* op = OPX + (tt & 1) * OP_BYTES;
-                const float btj = BT[j];
-                if (F4) {
-                    const float4 w = ld4(WT + j * MAXF);
-#pragma unroll
-                    for (int i = 0; i < CT; ++i) {
-                        const float x = fmaf(w.x, ob[i].x, fmaf(w.y, ob[i].y, fmaf(w.z, ob[i].z, fmaf(w.w, ob[i].w, btj))));
-                        put(op, rbase + mine + i, fmaxf(x, 0.f));
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < CT; ++i) {
-                        const float* orow = u + (size_t)(rowof(i) + tt) * Fin;
-                        float x = btj;
-                        for (int f = 0; f < Fin; ++f) x = fmaf(WT[j * MAXF + f], __ldg(orow + f), x);
-                        put(op, rbase + mine + i, fmaxf(x, 0.f));
-                    }
-                }
-            };
             float cst[CT];
 #pragma unroll
             for (int i = 0; i < CT; ++i) {
@@ -283,19 +307,9 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
                 cst[i] = cx0[b * H + j];
                 put(OPH, rbase + mine + i, hx0[b * H + j]);
             }
-            load_obs(0);
-            make_x(0);
             tc::fence_async_smem();
             tc::fence_before_sync();
-            tc::mbar_arrive_warp(x_full);
             tc::mbar_arrive_warp(b_full);
-            if (T > 1) {
-                load_obs(1);
-                make_x(1);
-                tc::fence_async_smem();
-                tc::mbar_arrive_warp(x_full + 1);
-            }
-            if (T > 2) load_obs(2);
 
             for (int t = 0; t < T; ++t, ++n) {
                 F3P(0, 0);
@@ -351,12 +365,6 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
                         st4(g_out + o * 4, gsv[i]);
                         c_out[o] = cst[i]; h_out[o] = hsv[i];
                     }
-                }
-                if (t + 2 < T) {                                        // x of step t+2 (its set was last read by the MMAs of step t: done)
-                    make_x(t + 2);
-                    tc::fence_async_smem();
-                    tc::mbar_arrive_warp(x_full + (t & 1));
-                    if (t + 3 < T) load_obs(t + 3);
                 }
                 if (head_part != nullptr) {
                     // heads: v[i*4 + o] = h[seq i][j] * W_head[o][j], folded over the warp's 32 units: lane l ends with slot (l >> 1) & 15

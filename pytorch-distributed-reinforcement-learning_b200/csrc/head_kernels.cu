@@ -55,9 +55,10 @@ struct HeadArgs {
 };
 
 // ------------------------------------------------------------------------------- PPO
-template <bool CONT>
+template <bool CONT, int AT>          // AT > 0: A == AT (discrete) at compile time
 __global__ void __launch_bounds__(kHeadThreads)
 ppo_head_kernel(HeadArgs a) {
+    constexpr int NZ = CONT ? 2 : (AT > 0 ? AT : MAXA);     // head pre-activations after the value
     const int lane = threadIdx.x & 31;
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nw = (gridDim.x * blockDim.x) >> 5;
@@ -80,13 +81,13 @@ ppo_head_kernel(HeadArgs a) {
                 const float* ho = a.head_out + (o + t) * NH;
                 v = __ldg(ho);
 #pragma unroll
-                for (int q = 0; q < MAXA; ++q) if (q < NH - 1) z[q] = __ldg(ho + 1 + q);
+                for (int q = 0; q < NZ; ++q) if (q < NH - 1) z[q] = __ldg(ho + 1 + q);
                 actv = __ldg(a.act + o + t);
-                dist_forward<CONT>(z, A, actv, d);
+                dist_forward<CONT, AT>(z, A, actv, d);
                 if (a.o_logp) a.o_logp[o + t] = d.logp;
                 if (a.o_ent) a.o_ent[o + t] = d.ent;
                 if (!CONT && a.o_logits)
-                    for (int q = 0; q < A; ++q) a.o_logits[(o + t) * A + q] = d.l[q];
+                    for (int q = 0; q < NZ; ++q) if (q < A) a.o_logits[(o + t) * A + q] = d.l[q];
             }
             if (ok) {
                 v1 = __ldg(a.head_out + (o + t + 1) * NH);
@@ -97,7 +98,7 @@ ppo_head_kernel(HeadArgs a) {
             carry = __shfl_sync(kFull, gae, 0);
             float dz[MAXA], dv = 0.f;
 #pragma unroll
-            for (int q = 0; q < MAXA; ++q) dz[q] = 0.f;
+            for (int q = 0; q < NZ; ++q) dz[q] = 0.f;
             if (ok) {
                 const float ratio = expf(d.logp - __ldg(a.blogp + o + t));
                 const float lo = 1.f - a.eps_clip, hi = 1.f + a.eps_clip;
@@ -110,7 +111,7 @@ ppo_head_kernel(HeadArgs a) {
                 const float dlogp = a.c_pol * dratio * ratio;
                 const float dd = v - td;
                 dv = a.c_val * invN * smooth_l1_grad(dd);
-                dist_backward<CONT>(d, A, actv, dlogp, -a.c_ent * invN, dz);
+                dist_backward<CONT, AT>(d, A, actv, dlogp, -a.c_ent * invN, dz);
                 s_pol += (double)(-fminf(s1, s2));
                 s_val += (double)smooth_l1(dd);
                 s_ent += (double)d.ent;
@@ -124,7 +125,7 @@ ppo_head_kernel(HeadArgs a) {
                 float* dh = a.dhead + (o + t) * NH;
                 dh[0] = dv;
 #pragma unroll
-                for (int q = 0; q < MAXA; ++q) if (q < NH - 1) dh[1 + q] = dz[q];
+                for (int q = 0; q < NZ; ++q) if (q < NH - 1) dh[1 + q] = dz[q];
             }
         }
     }
@@ -132,8 +133,10 @@ ppo_head_kernel(HeadArgs a) {
 }
 
 // ---------------------------------------------------------------------------- IMPALA
+template <int AT>
 __global__ void __launch_bounds__(kHeadThreads)
 impala_head_kernel(HeadArgs a) {
+    constexpr int NZ = AT > 0 ? AT : MAXA;
     const int lane = threadIdx.x & 31;
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nw = (gridDim.x * blockDim.x) >> 5;
@@ -155,13 +158,13 @@ impala_head_kernel(HeadArgs a) {
                 const float* ho = a.head_out + (o + t) * NH;
                 v = __ldg(ho);
 #pragma unroll
-                for (int q = 0; q < MAXA; ++q) if (q < NH - 1) z[q] = __ldg(ho + 1 + q);
+                for (int q = 0; q < NZ; ++q) if (q < NH - 1) z[q] = __ldg(ho + 1 + q);
                 actv = __ldg(a.act + o + t);
-                dist_forward<false>(z, A, actv, d);
+                dist_forward<false, AT>(z, A, actv, d);
                 if (a.o_logp) a.o_logp[o + t] = d.logp;
                 if (a.o_ent) a.o_ent[o + t] = d.ent;
                 if (a.o_logits)
-                    for (int q = 0; q < A; ++q) a.o_logits[(o + t) * A + q] = d.l[q];
+                    for (int q = 0; q < NZ; ++q) if (q < A) a.o_logits[(o + t) * A + q] = d.l[q];
             }
             if (ok) {
                 const float rho = expf(d.logp - __ldg(a.blogp + o + t));
@@ -180,14 +183,14 @@ impala_head_kernel(HeadArgs a) {
             const float vs = v + acc;
             float dz[MAXA], dv = 0.f;
 #pragma unroll
-            for (int q = 0; q < MAXA; ++q) dz[q] = 0.f;
+            for (int q = 0; q < NZ; ++q) dz[q] = 0.f;
             if (ok) {
                 const float vs1 = v1 + ((t + 1 == n) ? 0.f : acc_next);
                 const float adv = rc * (rt + disc1 * vs1 - v);
                 const float dlogp = -a.c_pol * adv * invN;
                 const float dd = v - vs;
                 dv = a.c_val * invN * smooth_l1_grad(dd);
-                dist_backward<false>(d, A, actv, dlogp, -a.c_ent * invN, dz);
+                dist_backward<false, AT>(d, A, actv, dlogp, -a.c_ent * invN, dz);
                 s_pol += (double)(-d.logp * adv);
                 s_val += (double)smooth_l1(dd);
                 s_ent += (double)d.ent;
@@ -201,7 +204,7 @@ impala_head_kernel(HeadArgs a) {
                 float* dh = a.dhead + (o + t) * NH;
                 dh[0] = dv;
 #pragma unroll
-                for (int q = 0; q < MAXA; ++q) if (q < NH - 1) dh[1 + q] = dz[q];
+                for (int q = 0; q < NZ; ++q) if (q < NH - 1) dh[1 + q] = dz[q];
             }
         }
     }
@@ -231,8 +234,10 @@ extern "C" int b200rl_ppo_head(const float* head_out, const float* act, const fl
     B200RL_REQUIRE(!continuous || A == 1, "ppo_head: continuous PPO supports act_dim 1 (the reference stores 1-wide actions)");
     HeadArgs a{head_out, act, rew, is_fir, behav_logp, dhead, scalars, logits_norm, logp, entropy, td_target, gae, ratio,
                B, T, A, continuous ? 1 + 2 * A : 1 + A, gamma, lambda_, eps_clip, 0.f, 0.f, c_policy, c_value, c_entropy};
-    if (continuous) { B200RL_LAUNCH(ppo_head_kernel<true>, head_grid(B), kHeadThreads, 0, stream, a); }
-    else { B200RL_LAUNCH(ppo_head_kernel<false>, head_grid(B), kHeadThreads, 0, stream, a); }
+    auto kern = continuous ? ppo_head_kernel<true, 0>
+              : A == 2 ? ppo_head_kernel<false, 2> : A == 3 ? ppo_head_kernel<false, 3> : A == 4 ? ppo_head_kernel<false, 4>
+              : ppo_head_kernel<false, 0>;
+    B200RL_LAUNCH(kern, head_grid(B), kHeadThreads, 0, stream, a);
     return check_launch("ppo_head");
 }
 
@@ -248,6 +253,7 @@ extern "C" int b200rl_impala_head(const float* head_out, const float* act, const
     B200RL_REQUIRE(A >= 1 && A <= MAXA, "impala_head: A=%d out of range [1,%d]", A, MAXA);
     HeadArgs a{head_out, act, rew, is_fir, behav_logp, dhead, scalars, logits_norm, logp, entropy, rho, adv, vs,
                B, T, A, 1 + A, gamma, 0.f, 0.f, rho_bar, c_bar, c_policy, c_value, c_entropy};
-    B200RL_LAUNCH(impala_head_kernel, head_grid(B), kHeadThreads, 0, stream, a);
+    auto kern = A == 2 ? impala_head_kernel<2> : A == 3 ? impala_head_kernel<3> : A == 4 ? impala_head_kernel<4> : impala_head_kernel<0>;
+    B200RL_LAUNCH(kern, head_grid(B), kHeadThreads, 0, stream, a);
     return check_launch("impala_head");
 }

@@ -164,12 +164,14 @@ struct VmpoGradArgs {
     float c_pol, invN;
 };
 
+template <int AT>                    // AT > 0: A == AT at compile time (dist.cuh)
 __global__ void __launch_bounds__(kHeadThreads)
 vmpo_grad_kernel(VmpoGradArgs a) {
+    constexpr int NZ = AT > 0 ? AT : MAXA;
     const int lane = threadIdx.x & 31;
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nw = (gridDim.x * blockDim.x) >> 5;
-    const int T = a.T, n = T - 1, NH = a.NH, A = a.A;
+    const int T = a.T, n = T - 1, NH = a.NH, A = AT > 0 ? AT : a.A;
     const int nslab = (n + 31) >> 5;
     const float inv = 1.0f / ((float)exp(a.duals[0]) + 1e-7f);
     const float alpha32 = (float)exp(a.duals[1]);
@@ -209,29 +211,29 @@ vmpo_grad_kernel(VmpoGradArgs a) {
             const float* ho = a.head_out + (o + t) * NH;
             float z[MAXA];
 #pragma unroll
-            for (int q = 0; q < MAXA; ++q) if (q < A) z[q] = __ldg(ho + 1 + q);
+            for (int q = 0; q < NZ; ++q) if (q < A) z[q] = __ldg(ho + 1 + q);
             const float actv = __ldg(a.act + o + t);
             Dist d;
-            dist_forward<false>(z, A, actv, d);
+            dist_forward<false, AT>(z, A, actv, d);
             // behaviour policy: Categorical(softmax(behaviour_logits)) restated (compute_loss.py:74-77)
             float bl[MAXA], pp[MAXA], bm = -INFINITY, bs = 0.f, bS = 0.f;
 #pragma unroll
-            for (int q = 0; q < MAXA; ++q) if (q < A) { bl[q] = __ldg(a.blogits + (o + t) * A + q); bm = fmaxf(bm, bl[q]); }
+            for (int q = 0; q < NZ; ++q) if (q < A) { bl[q] = __ldg(a.blogits + (o + t) * A + q); bm = fmaxf(bm, bl[q]); }
 #pragma unroll
-            for (int q = 0; q < MAXA; ++q) if (q < A) { pp[q] = expf(bl[q] - bm); bs += pp[q]; }
+            for (int q = 0; q < NZ; ++q) if (q < A) { pp[q] = expf(bl[q] - bm); bs += pp[q]; }
 #pragma unroll
-            for (int q = 0; q < MAXA; ++q) if (q < A) { pp[q] = pp[q] / bs; bS += pp[q]; }
+            for (int q = 0; q < NZ; ++q) if (q < A) { pp[q] = pp[q] / bs; bS += pp[q]; }
             // current policy as the reference sees it: softmax of the normalised log-probs it returns as "logits"
             float lm = -INFINITY, ls = 0.f, q2[MAXA], qS = 0.f;
 #pragma unroll
-            for (int q = 0; q < MAXA; ++q) if (q < A) lm = fmaxf(lm, d.l[q]);
+            for (int q = 0; q < NZ; ++q) if (q < A) lm = fmaxf(lm, d.l[q]);
 #pragma unroll
-            for (int q = 0; q < MAXA; ++q) if (q < A) { q2[q] = expf(d.l[q] - lm); ls += q2[q]; }
+            for (int q = 0; q < NZ; ++q) if (q < A) { q2[q] = expf(d.l[q] - lm); ls += q2[q]; }
 #pragma unroll
-            for (int q = 0; q < MAXA; ++q) if (q < A) { q2[q] = q2[q] / ls; qS += q2[q]; }
+            for (int q = 0; q < NZ; ++q) if (q < A) { q2[q] = q2[q] / ls; qS += q2[q]; }
             float kl = 0.f;
 #pragma unroll
-            for (int q = 0; q < MAXA; ++q) if (q < A) {
+            for (int q = 0; q < NZ; ++q) if (q < A) {
                 const float p = pp[q] / bS, qq = q2[q] / qS;
                 float term = p * (logf(fminf(fmaxf(p, kEps), 1.f - kEps)) - logf(fminf(fmaxf(qq, kEps), 1.f - kEps)));
                 if (qq == 0.f) term = INFINITY;
@@ -249,12 +251,12 @@ vmpo_grad_kernel(VmpoGradArgs a) {
             }
             float dz[MAXA];
 #pragma unroll
-            for (int q = 0; q < MAXA; ++q) dz[q] = 0.f;
-            dist_backward<false>(d, A, actv, -a.c_pol * psi, 0.f, dz);
+            for (int q = 0; q < NZ; ++q) dz[q] = 0.f;
+            dist_backward<false, AT>(d, A, actv, -a.c_pol * psi, 0.f, dz);
             const float kc = alpha32 * a.invN;                     // d(L_alpha)/dKL = alpha.detach() / N
             float* dh = a.dhead + (o + t) * NH;
 #pragma unroll
-            for (int q = 0; q < MAXA; ++q) if (q < A) dh[1 + q] = dz[q] + kc * (d.p[q] / d.S - pp[q] / bS);
+            for (int q = 0; q < NZ; ++q) if (q < A) dh[1 + q] = dz[q] + kc * (d.p[q] / d.S - pp[q] / bS);
         }
     }
     s_pol = warp_sum(s_pol); s_kl = warp_sum(s_kl); s_cnt = warp_sum(s_cnt);
@@ -329,7 +331,8 @@ extern "C" int b200rl_vmpo_grad(const float* head_out, const float* act, const f
                                 float c_policy, double N_global, void* stream) {
     B200RL_REQUIRE(B >= 1 && T >= 2 && A >= 1 && A <= MAXA, "vmpo_grad: bad shape B=%d T=%d A=%d", B, T, A);
     VmpoGradArgs a{head_out, act, behav_logits, gae, thr, colstat, duals, dhead, scalars, tie_cut, B, T, A, 1 + A, row_offset, c_policy, (float)(1.0 / N_global)};
-    B200RL_LAUNCH(vmpo_grad_kernel, vm_grid(B), kHeadThreads, 0, stream, a);
+    auto kern = A == 2 ? vmpo_grad_kernel<2> : A == 3 ? vmpo_grad_kernel<3> : A == 4 ? vmpo_grad_kernel<4> : vmpo_grad_kernel<0>;
+    B200RL_LAUNCH(kern, vm_grid(B), kHeadThreads, 0, stream, a);
     return check_launch("vmpo_grad");
 }
 

@@ -34,7 +34,7 @@ int main(int argc, char** argv) {
 #ifdef B200RL_FWD3PROF
     cudaMemcpyFromSymbol(z, g_fwd3prof, sizeof(z));
     const double steps = (B / 32.0) * T;
-    printf("fwd_fused (heads %d, sep %d) %.3f ms incl. head_combine; cycles/step compute thread 0: loop top %.0f | wait acc_done %.0f | tmem ld + arrive acc_free %.0f | send raw + swap barrier %.0f | 4 cells + operand %.0f | fence + arrive b_full %.0f | stores + x(t+2) + heads %.0f\n",
+    printf("fwd_fused (heads %d, sep %d) %.3f ms incl. head_combine; cycles/step compute thread 0: loop top %.0f | wait acc_done %.0f | tmem ld + arrive acc_free %.0f | send raw + swap barrier %.0f | 4 cells + operand %.0f | fence + arrive b_full %.0f | stores + heads %.0f\n",
            (int)heads, B200RL_FWD3_SEP, ms, z[0] / steps, z[1] / steps, z[2] / steps, z[3] / steps, z[4] / steps, z[5] / steps, z[6] / steps);
     printf("   recurrent issuer: loop top %.0f | wait b_full %.0f | wait x_done %.0f | issue 10 MMAs + commit %.0f\n", z[7] / steps, z[8] / steps, z[9] / steps, z[10] / steps);
     printf("   input-projection issuer: loop top %.0f | wait x_full %.0f | wait acc_free %.0f | issue 10 MMAs + commit %.0f\n", z[11] / steps, z[12] / steps, z[13] / steps, z[14] / steps);
