@@ -187,7 +187,8 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
                         const float4 o = ld4(u + row * 4);
                         x = fmaf(wt[0], o.x, fmaf(wt[1], o.y, fmaf(wt[2], o.z, fmaf(wt[3], o.w, x))));
                     } else {
-                        for (int f = 0; f < Fin; ++f) x = fmaf(wt[f], __ldg(u + row * Fin + f), x);
+#pragma unroll
+                        for (int f = 0; f < MAXF; ++f) if (f < Fin) x = fmaf(wt[f], __ldg(u + row * Fin + f), x);   // (static register indices)
                     }
                     xv[i] = fmaxf(x, 0.f);
                 }
