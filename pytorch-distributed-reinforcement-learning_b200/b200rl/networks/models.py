@@ -180,6 +180,31 @@ class MlpLSTMBase(_FlatNet):
             logits = dist.logits.detach() if hasattr(dist, "logits") else torch.zeros(action.shape)
         return action, logits, dist.log_prob(action).detach(), (hx.detach(), cx.detach())
 
+    def act_batch(self, obs, lstm_hxs, ops=None):
+        """Batched worker-side inference: `act` (reference networks/models.py:37-56, called once per
+        environment step by every worker process, agents/worker.py:105) for N environments at once on the device -- ONE
+        launch of the fused forward kernel with T = 1 (torso, LSTM cell and heads), then the sampling on the (N, A) head
+        outputs.  obs (N, f), lstm_hxs = (hx, cx) each (N, H).  Returns what `act` returns, batched: action (N, 1) /
+        (N, act_dim), logits (N, A) normalised log-probs (zeros for the continuous net), log_prob (N, 1) and the new (hx, cx)."""
+        ops = ops or _ops.default()
+        N = obs.shape[0]
+        hx, cx = lstm_hxs
+        head_out, ws = self.run_lstm(obs.reshape(N, 1, -1).float(), (hx, cx), ops)
+        z = head_out[:, 0, 1:]
+        with torch.no_grad():
+            if self.continuous:
+                dist = Normal(torch.tanh(z[:, :1]), torch.nn.functional.softplus(z[:, 1:2]))
+                action = dist.sample()
+                logits = torch.zeros_like(action)
+                logp = dist.log_prob(action)
+            else:
+                dist = self.CT(torch.softmax(z, dim=-1))
+                a = dist.sample()
+                action = a.unsqueeze(-1).float()
+                logits = dist.logits
+                logp = dist.log_prob(a).unsqueeze(-1)
+        return action, logits, logp, (ws["h"][:, 0].clone(), ws["c"][:, 0].clone())
+
     def forward(self, obs, lstm_hxs, behaviour_acts, ops=None):
         """-> (logits (B,T,A) normalised log-probs, log_probs (B,T,1), entropy (B,T,1), value (B,T,1))."""
         ops = ops or _ops.default()

@@ -518,3 +518,38 @@ def test_publish_interval_and_async_mailbox(monkeypatch):
     assert got == sorted(got) and got[-1] == 19.0 and len(got) + lb2.pub_dropped == 20 and lb2.pub_dropped > 0
     lb2.pub_socket = None                                     # (__del__ closes real sockets only)
     lb.pub_socket = None
+
+
+# --------------------------------------------------------------------------------------- batched inference (f4)
+@pytest.mark.parametrize("cont", [False, True])
+def test_act_batch_matches_per_environment_act(backend, cont):
+    """`act_batch` (N environments, one fused-forward launch with T = 1) against the reference's per-environment `act`
+    math (networks/models.py:37-56): new LSTM state, normalised log-probs, and the log-prob of the sampled action."""
+    from b200rl.networks import models as M
+    ops, dev = backend
+    N, f, A = 37, (2 if cont else 4), (1 if cont else 3)
+    torch.manual_seed(1)
+    model = (M.MlpLSTMSingleContinuous if cont else M.MlpLSTMSingle)(f, A, 5, 64)
+    sd = {k: v.clone() for k, v in model.actor.state_dict().items()}
+    obs, hx, cx = torch.randn(N, f), 0.3 * torch.randn(N, 64), 0.3 * torch.randn(N, 64)
+    # the reference's math, per environment, on the CPU
+    x = torch.relu(obs @ sd["body.0.weight"].T + sd["body.0.bias"])
+    g = x @ sd["lstmcell.weight_ih"].T + sd["lstmcell.bias_ih"] + hx @ sd["lstmcell.weight_hh"].T + sd["lstmcell.bias_hh"]
+    i, fg, gg, o = g.chunk(4, 1)
+    c1 = torch.sigmoid(fg) * cx + torch.sigmoid(i) * torch.tanh(gg)
+    h1 = torch.sigmoid(o) * torch.tanh(c1)
+    z = h1 @ sd["logits.weight"].T + sd["logits.bias"]
+    net = model.to(dev).actor
+    action, logits, logp, (h2, c2) = net.act_batch(obs.to(dev), (hx.to(dev), cx.to(dev)), ops=ops)
+    _close(h2.cpu(), h1, rtol=1e-4, atol=1e-6, what="hx")
+    _close(c2.cpu(), c1, rtol=1e-4, atol=1e-6, what="cx")
+    if cont:
+        zs = h1 @ sd["logits_std.weight"].T + sd["logits_std.bias"]
+        want = torch.distributions.Normal(torch.tanh(z), torch.nn.functional.softplus(zs)).log_prob(action.cpu())
+        assert action.shape == (N, 1) and float(logits.abs().max()) == 0.0
+        _close(logp.cpu(), want, rtol=1e-4, atol=1e-5, what="log_prob of the sampled action")
+    else:
+        want = torch.distributions.Categorical(torch.softmax(z, -1)).logits
+        assert action.shape == (N, 1) and logits.shape == (N, A)
+        _close(logits.cpu(), want, rtol=1e-4, atol=1e-6, what="normalised log-probs")
+        _close(logp.cpu(), want.gather(1, action.cpu().long()), rtol=1e-4, atol=1e-6, what="log_prob of the sampled action")
