@@ -59,15 +59,13 @@ constexpr int C_LBO = 144, C_SBO = 1152;                   // bf16 B operand: 8 
 constexpr int C_BYTES = (TB / 8) * C_SBO;                  // 4608
 constexpr int OP_BYTES = 2 * B_BYTES + C_BYTES;            // one operand set: hi | lo | bf16(hi)
 constexpr int EXF = 2 * NG * 2 * RW * 32;                  // swap buffer [pair][direction][slot][lane] floats
-constexpr int NBAR = 12;                                   // b_full, acc_done, acc_free, x_done, x_full[2], x_free[2], st_full[2], st_free[2]
-constexpr int ST_G = TB * H * 4, ST_C = TB * H;            // staging of one step's saved activations (floats): gates | c | h
-constexpr int ST_FLOATS = ST_G + 2 * ST_C;                 // 48 KB per set, two sets
+constexpr int NBAR = 8;                                    // b_full, acc_done, acc_free, x_done, x_full[2], x_free[2]
 static_assert(15 * B_LBO + 128 <= B_SBO && 7 * C_LBO + 128 <= C_SBO, "core matrices of one 8-row group must fit below SBO");
 static_assert(RW == 8 && CT == 4, "cell phase layout");
 }  // namespace ffk
 
 static inline size_t fwd_fused_smem_bytes() {
-    return 3 * (size_t)ffk::OP_BYTES + sizeof(float) * (2 * ffk::ST_FLOATS + ffk::EXF + ffk::H * 4 + ffk::H * ffk::MAXF + ffk::H + ffk::H * 4) + 8 * ffk::NBAR + 64;
+    return 3 * (size_t)ffk::OP_BYTES + sizeof(float) * (ffk::EXF + ffk::H * 4 + ffk::H * ffk::MAXF + ffk::H + ffk::H * 4) + 8 * ffk::NBAR + 64;
 }
 
 template <bool F4>
@@ -81,15 +79,13 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
     B200RL_DYN_SMEM(unsigned char, smem);
     unsigned char* OPH = smem;                              // h_{t-1}: hi | lo | bf16
     unsigned char* OPX = smem + OP_BYTES;                   // x_t: two sets
-    float* STG = reinterpret_cast<float*>(smem + 3 * OP_BYTES);    // two staging sets of saved activations, drained to HBM by bulk copies
-    float* EX = STG + 2 * ST_FLOATS;
+    float* EX = reinterpret_cast<float*>(smem + 3 * OP_BYTES);
     float* BI = EX + EXF;                                   // BI[j*4 + g] = b_ih[g*64+j] + b_hh[g*64+j]
     float* WT = BI + H * 4;                                 // WT[j*8 + f]
     float* BT = WT + H * MAXF;                              // bt[j]
     float* WH = BT + H;                                     // WH[j*4 + o]
     uint64_t* bars = reinterpret_cast<uint64_t*>(WH + H * 4);
-    uint64_t* b_full = bars, *acc_done = bars + 1, *acc_free = bars + 2, *x_done = bars + 3, *x_full = bars + 4, *x_free = bars + 6,
-              *st_full = bars + 8, *st_free = bars + 10;       // x_full[2], x_free[2], st_full[2], st_free[2]
+    uint64_t* b_full = bars, *acc_done = bars + 1, *acc_free = bars + 2, *x_done = bars + 3, *x_full = bars + 4, *x_free = bars + 6;   // x_full[2], x_free[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -104,8 +100,6 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
         tc::mbar_init(b_full, NC / 32); tc::mbar_init(acc_done, NI); tc::mbar_init(acc_free, NC / 32); tc::mbar_init(x_done, NI);
         tc::mbar_init(x_full, NPW); tc::mbar_init(x_full + 1, NPW);
         tc::mbar_init(x_free, NI); tc::mbar_init(x_free + 1, NI);
-        tc::mbar_init(st_full, NC / 32); tc::mbar_init(st_full + 1, NC / 32);
-        tc::mbar_init(st_free, NPW); tc::mbar_init(st_free + 1, NPW);
         tc::fence_mbar_init();
     }
     if (warp == NC / 32) tc::tmem_alloc(tmem_slot, TM_COLS);
@@ -177,27 +171,7 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
         float wt[MAXF];
 #pragma unroll
         for (int f = 0; f < MAXF; ++f) wt[f] = WT[j * MAXF + f];
-        uint32_t written[2] = {0, 0}, drained[2] = {0, 0};
-        const int pw = pt >> 5;                                       // producer warp: also drains sequences 8 pw .. 8 pw + 7 of every step
-        // saved activations of step `ts` (staging set ts & 1) -> HBM: lane l < 8 copies the 1 KB gate row and the 256-byte c and h
-        // rows of sequence 8 pw + l with three bulk copies on the TMA engine
-        auto drain = [&](int b0, int ts) {
-            const int sp = ts & 1;
-            tc::mbar_wait(st_full + sp, drained[sp] & 1); ++drained[sp];
-            if (lane < 8) {
-                const int r = pw * 8 + lane, b = b0 + r;
-                if (b < B) {
-                    const float* st = STG + sp * ST_FLOATS;
-                    const size_t row = (size_t)b * T + ts;
-                    tc::bulk_store(g_out + row * (H * 4), st + r * (H * 4), H * 16);
-                    tc::bulk_store(c_out + row * H, st + ST_G + r * H, H * 4);
-                    tc::bulk_store(h_out + row * H, st + ST_G + ST_C + r * H, H * 4);
-                }
-                tc::bulk_commit();
-                tc::bulk_wait_read<0>();                                // the engine has read the staging rows: the set may be rewritten
-            }
-            tc::mbar_arrive_warp(st_free + sp);
-        };
+        uint32_t written[2] = {0, 0};
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int b0 = tile * TB;
             for (int t = 0; t < T; ++t) {
@@ -230,12 +204,8 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
                 }
                 tc::fence_async_smem();
                 tc::mbar_arrive_warp(x_full + p);
-                if (t >= 2) drain(b0, t - 2);
             }
-            if (T >= 2) drain(b0, T - 2);
-            drain(b0, T - 1);
         }
-        if (lane < 8) tc::bulk_wait<0>();                              // every copy has landed before the CTA exits
     } else if (!compute) {
 #if !defined(B200RL_EMUL)
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -325,7 +295,7 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
             *reinterpret_cast<unsigned short*>(op + bf(r)) = tc::bf16_bits_rn(hi);
         };
         const float4 bias = ld4(BI + j * 4);
-        uint32_t n = 0, stc[2] = {0, 0};                      // steps done ; uses of each staging set
+        uint32_t n = 0;
         F3P_INIT
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int b0 = tile * TB;
@@ -389,21 +359,13 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
                 }
                 F3P(5, 0);
                 // ---- off the serial chain from here: the tensor core is running step t+1
-                {
-                    // saved activations into staging set t & 1 (drained to HBM by the producer warps' bulk copies)
-                    const int sp = t & 1;
-                    if (stc[sp] > 0) tc::mbar_wait(st_free + sp, (stc[sp] - 1) & 1);  // the copies of its previous use have been read
-                    ++stc[sp];
-                    float* st = STG + sp * ST_FLOATS;
 #pragma unroll
-                    for (int i = 0; i < CT; ++i) {
-                        const int r = rbase + mine + i;
-                        st4(st + (r * H + j) * 4, gsv[i]);
-                        st[ST_G + r * H + j] = cst[i];
-                        st[ST_G + ST_C + r * H + j] = hsv[i];
+                for (int i = 0; i < CT; ++i) {
+                    if (b0 + rbase + mine + i < B) {
+                        const size_t o = (size_t)(rowof(i) + t) * H + j;
+                        st4(g_out + o * 4, gsv[i]);
+                        c_out[o] = cst[i]; h_out[o] = hsv[i];
                     }
-                    tc::fence_async_smem();
-                    tc::mbar_arrive_warp(st_full + sp);
                 }
                 if (head_part != nullptr) {
                     // heads: v[i*4 + o] = h[seq i][j] * W_head[o][j], folded over the warp's 32 units: lane l ends with slot (l >> 1) & 15

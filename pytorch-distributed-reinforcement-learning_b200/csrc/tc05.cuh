@@ -206,16 +206,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&r)[16]) 
 }
 __device__ __forceinline__ uint32_t tmem_addr(uint32_t base, int lane, int col) { return base + ((uint32_t)lane << 16) + (uint32_t)col; }
 
-// ---- bulk asynchronous copies on the TMA engine (UBLKCP): shared memory -> global memory, 16-byte aligned, size % 16 == 0.
-// The writers of the source must have executed fence_async_smem(); the issuing thread groups its copies with bulk_commit()
-// and may reuse the source once bulk_wait_read<N>() says all but the N newest groups have been READ.
-__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
-
 #else
 // --------------------------------------------------------------------------- host twin
 struct SmemDesc { const unsigned char* base; uint32_t lbo, sbo; };
@@ -326,13 +316,6 @@ inline void tmem_ld16(uint32_t taddr, float (&r)[16]) {
     for (int i = 0; i < 16; ++i) r[i] = emul_tmem().d[lane][col + i];
 }
 inline uint32_t tmem_addr(uint32_t base, int lane, int col) { return base + ((uint32_t)lane << 16) + (uint32_t)col; }
-inline void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
-    if ((reinterpret_cast<uintptr_t>(gdst) | reinterpret_cast<uintptr_t>(ssrc) | bytes) & 15) { fprintf(stderr, "emul: misaligned bulk copy\n"); abort(); }
-    memcpy(gdst, ssrc, bytes);
-}
-inline void bulk_commit() {}
-template <int N> inline void bulk_wait_read() {}
-template <int N> inline void bulk_wait() {}
 #endif
 
 }  // namespace tc
