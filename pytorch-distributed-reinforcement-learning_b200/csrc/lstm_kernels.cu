@@ -743,12 +743,33 @@ lstm_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ h, c
     if (tid < NH) out[off_bhead + tid] = acc_hb;
 }
 
+// grad[i] = sum over the slabs: a CTA owns 32 consecutive parameters (one 128-byte line per slab row), its 8 warps take the
+// slabs y, y + 8, ... with four independent loads in flight each, and the eight partial sums are added in a fixed order
+// (deterministic).  (One thread per parameter walking all ~300 slabs serially was a 300-deep dependent-load chain: 16 us.)
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const float* __restrict__ partials, float* __restrict__ grad, int nparts, long long P) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
-        float s = 0.f;
-        for (int p = 0; p < nparts; ++p) s += partials[(size_t)p * P + i];
-        grad[i] = s;
+    __shared__ float red[8][32];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    for (long long i0 = (long long)blockIdx.x * 32; i0 < P; i0 += (long long)gridDim.x * 32) {
+        const long long i = i0 + x;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        if (i < P) {
+            int p = y;
+            for (; p + 24 < nparts; p += 32) {
+                s0 += partials[(size_t)p * P + i]; s1 += partials[(size_t)(p + 8) * P + i];
+                s2 += partials[(size_t)(p + 16) * P + i]; s3 += partials[(size_t)(p + 24) * P + i];
+            }
+            for (; p < nparts; p += 8) s0 += partials[(size_t)p * P + i];
+        }
+        red[y][x] = (s0 + s1) + (s2 + s3);
+        __syncthreads();
+        if (y == 0 && i < P) {
+            float s = red[0][x];
+#pragma unroll
+            for (int k = 1; k < 8; ++k) s += red[k][x];
+            grad[i] = s;
+        }
+        __syncthreads();
     }
 }
 
@@ -899,7 +920,10 @@ extern "C" int b200rl_lstm_wgrad(const float* dpre, const float* h, const float*
 
 extern "C" int b200rl_reduce_partials(const float* partials, float* grad, int nparts, long long P, void* stream) {
     B200RL_REQUIRE(nparts >= 1 && P >= 1, "reduce_partials: bad shape");
-    long long g = (P + 255) / 256;
-    B200RL_LAUNCH(reduce_partials_kernel, (int)(g > 1184 ? 1184 : g), 256, 0, stream, partials, grad, nparts, P);
+    long long g = (P + 31) / 32;
+#ifdef B200RL_EMUL
+    if (g > 4) g = 4;                   // (the host emulator spawns a thread per CUDA thread: keep the grid small)
+#endif
+    B200RL_LAUNCH(reduce_partials_kernel, (int)(g > 148 * 8 ? 148 * 8 : g), 256, 0, stream, partials, grad, nparts, P);
     return check_launch("reduce_partials");
 }
