@@ -256,6 +256,22 @@ int b200rl_sac_alpha_step(double* state, const double* scalars, double* out, dou
  * hx / cx = [:, 0] of the (B, T, H) shared arrays go to the device without a host-side gather.                          */
 int b200rl_h2d_rows(void* dst, const void* src, long long width_bytes, long long rows, long long src_pitch_bytes, void* stream);
 
+/* ---- rollout -> batch assembly, storage side (host code) -----------------------------------------------
+ * RolloutAssembler.push + make_as_array (buffers/rollout_assembler.py:9-82) fused with LearnerStorage.make_batch
+ * (agents/learner_storage.py:123-159): one copy per environment step into a slot-shaped staging block, eight memcpys per
+ * finished trajectory into slot `*count` of the shared arrays, `*count += 1`.  Reference semantics kept: active
+ * trajectories older than max_age_s are dropped at the next push; a step of an unknown episode continues the first-parked
+ * unfinished trajectory (seam marked is_fir = 1); a finished trajectory is dropped when *count == capacity.
+ * asm_push returns 1 (trajectory written), 2 (dropped: batch full), 0 (step stored), < 0 (error).
+ * stats[6] = {active, parked, emitted, dropped_full, dropped_age, spliced}.                                           */
+void* b200rl_asm_create(int seq_len, int obs_width, int action_space, int hidden, double max_age_s);
+int b200rl_asm_destroy(void* h);
+int b200rl_asm_bind(void* h, float* obs, float* act, float* rew, float* logits, float* log_prob, float* is_fir,
+                    float* hx, float* cx, int* count, int capacity);
+int b200rl_asm_push(void* h, long long id, int done, double now_s, const float* obs, float act, float rew,
+                    const float* logits, float log_prob, float is_fir, const float* hx, const float* cx);
+int b200rl_asm_stats(void* h, long long* stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,11 @@ SIGNATURES = {
     "b200rl_vmpo_dual_step": [_P] * 4 + [C.c_double] * 9 + [_P],
     "b200rl_clip_rmsprop": [_P, _P, _P, _L] + [_F] * 5 + [_P, _P],
     "b200rl_clip_adam": [_P, _P, _P, _P, _L] + [_F] * 6 + [_I, _P, _P, _P],
+    "b200rl_asm_create": [_I, _I, _I, _I, C.c_double],
+    "b200rl_asm_destroy": [_P],
+    "b200rl_asm_bind": [_P] * 10 + [_I],
+    "b200rl_asm_push": [_P, _L, _I, C.c_double, _P, _F, _F, _P, _F, _F, _P, _P],
+    "b200rl_asm_stats": [_P, _P],
     "b200rl_h2d_rows": [_P, _P, _L, _L, _L, _P],
     "b200rl_peer_alloc": [_L, _P, _P],
     "b200rl_peer_open": [_P, _P],
@@ -56,7 +61,7 @@ SIGNATURES = {
     "b200rl_sac_cont_critic_head": [_P] * 12 + [_I, _I, _I, _F, _P],
     "b200rl_sac_alpha_step": [_P, _P, _P, C.c_double, C.c_double, C.c_double, _I, _P],
 }
-_RESTYPE = {"b200rl_last_error": C.c_char_p}
+_RESTYPE = {"b200rl_last_error": C.c_char_p, "b200rl_asm_create": C.c_void_p}
 
 
 class NativeError(RuntimeError):

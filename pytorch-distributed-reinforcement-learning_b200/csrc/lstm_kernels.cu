@@ -748,6 +748,27 @@ lstm_wgrad_kernel(const float* __restrict__ dpre, const float* __restrict__ h, c
 // (deterministic).  (One thread per parameter walking all ~300 slabs serially was a 300-deep dependent-load chain: 16 us.)
 __global__ void __launch_bounds__(256)
 reduce_partials_kernel(const float* __restrict__ partials, float* __restrict__ grad, int nparts, long long P) {
+#ifdef B200RL_EMUL
+    // (host emulator: a 256-thread barrier costs a millisecond of context switches -- same sums, the same order per slab
+    // group, without the block-wide exchange)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
+        float part[8];
+        for (int y = 0; y < 8; ++y) {
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            int p = y;
+            for (; p + 24 < nparts; p += 32) {
+                s0 += partials[(size_t)p * P + i]; s1 += partials[(size_t)(p + 8) * P + i];
+                s2 += partials[(size_t)(p + 16) * P + i]; s3 += partials[(size_t)(p + 24) * P + i];
+            }
+            for (; p < nparts; p += 8) s0 += partials[(size_t)p * P + i];
+            part[y] = (s0 + s1) + (s2 + s3);
+        }
+        float s = part[0];
+        for (int k = 1; k < 8; ++k) s += part[k];
+        grad[i] = s;
+    }
+    return;
+#endif
     __shared__ float red[8][32];
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
     for (long long i0 = (long long)blockIdx.x * 32; i0 < P; i0 += (long long)gridDim.x * 32) {

@@ -253,6 +253,68 @@ def init_case():
     print("init_seed0 ok")
 
 
+def assembler_case():
+    """A random stream of per-step worker records through the reference's RolloutAssembler + LearnerStorage.make_batch
+    (buffers/rollout_assembler.py:24-82, agents/learner_storage.py:123-159) under a scripted clock: the stream and the shared
+    arrays it leaves behind pin the native assembler (csrc/assembler.cu)."""
+    import buffers.rollout_assembler as ra
+    from agents.learner_storage import LearnerStorage
+    T, f, A, Hh, cap = 6, 4, 2, 64, 5
+    args = copy.copy(Params)
+    args.seq_len, args.action_space, args.hidden_size = T, A, Hh
+    clock = SimpleNamespace(t=0.0)
+    ra.time = SimpleNamespace(monotonic=lambda: clock.t)            # the module calls time.monotonic()
+    rng = np.random.RandomState(7)
+    ready = asyncio.Queue()
+    asm = ra.RolloutAssembler(args, ready)
+    widths = dict(obs=f, act=1, rew=1, logits=A, log_prob=1, is_fir=1, hx=Hh, cx=Hh)
+    store = SimpleNamespace(args=args, obs_shape=[f], sh_data_num=SimpleNamespace(value=0))
+    for k, w in widths.items():
+        setattr(store, f"sh_{k}_batch", np.zeros(T * cap * w, dtype=np.float32))
+    rec = {k: [] for k in ("id", "done", "now", *widths)}
+    counts = []
+    live = {}                                     # episode id -> steps left
+    next_id = 100
+
+    async def run():
+        nonlocal next_id
+        for step in range(140):
+            clock.t += float(rng.choice([0.01, 0.02, 0.05, 0.3], p=[0.5, 0.3, 0.15, 0.05]))
+            if len(live) < 3 or rng.rand() < 0.1:
+                live[next_id] = int(rng.randint(2, 11))
+                next_id += 1
+            eid = int(rng.choice(list(live)))
+            live[eid] -= 1
+            done = live[eid] == 0
+            if done:
+                del live[eid]
+            data = {k: torch.from_numpy(rng.randn(w).astype(np.float32)) for k, w in widths.items()}
+            data["is_fir"] = torch.FloatTensor([1.0 if rng.rand() < 0.1 else 0.0])
+            for k in widths:
+                rec[k].append(data[k].numpy().copy())
+            rec["id"].append(eid); rec["done"].append(done); rec["now"].append(clock.t)
+            data["id"], data["done"] = eid, torch.FloatTensor([1.0 if done else 0.0])     # (agents/worker.py:108-121)
+            with contextlib.redirect_stdout(io.StringIO()):
+                await asm.push(data)
+            while not ready.empty():
+                LearnerStorage.make_batch(store, ready.get_nowait())
+            counts.append(store.sh_data_num.value)
+            if step == 90:                        # the learner takes the batch: the counter goes back to zero once
+                store.sh_data_num.value = 0
+    asyncio.run(run())
+    out = {"meta": np.array([T, f, A, Hh, cap, 90]), "id": np.array(rec["id"]), "done": np.array(rec["done"]), "now": np.array(rec["now"]),
+           "count_after": np.array(counts)}
+    for k in widths:
+        out[f"in/{k}"] = np.stack(rec[k])
+        out[f"shared/{k}"] = getattr(store, f"sh_{k}_batch")
+    np.savez_compressed(os.path.join(HERE, "assembler_stream.npz"), **out)
+    print("assembler_stream: slots written after each push", counts[-1], "max", max(counts))
+
+
+if __name__ == "__main__" and "--assembler" in sys.argv:
+    assembler_case()
+    sys.exit(0)
+
 if __name__ == "__main__" and "--branches" in sys.argv:
     # round 2: branches the first fixtures never reached -- an ACTIVE clip_grad_norm_ (coef < 1) under RMSprop and under Adam,
     # and K_epoch = 2 (two updates per batch)

@@ -553,3 +553,56 @@ def test_act_batch_matches_per_environment_act(backend, cont):
         assert action.shape == (N, 1) and logits.shape == (N, A)
         _close(logits.cpu(), want, rtol=1e-4, atol=1e-6, what="normalised log-probs")
         _close(logp.cpu(), want.gather(1, action.cpu().long()), rtol=1e-4, atol=1e-6, what="log_prob of the sampled action")
+
+
+# ------------------------------------------------------------------------------------- rollout assembler (f2)
+def test_native_assembler_matches_reference_stream():
+    """The recorded stream of worker step records (tests/golden/make_golden.py --assembler: the reference's RolloutAssembler
+    + LearnerStorage.make_batch under a scripted clock, with age expiry, parked episodes spliced with an is_fir seam, a
+    full shared batch and a counter reset) replayed through the native assembler: same slot counter after every push,
+    same bytes in the shared arrays."""
+    from types import SimpleNamespace
+    from b200rl.agents.storage_module.shared_batch import setup_shared_memory
+    from b200rl.buffers import RolloutAssembler
+    g = load_golden("assembler_stream")
+    T, f, A, H, cap, reset_at = [int(x) for x in g["meta"]]
+    args = SimpleNamespace(seq_len=T, action_space=A, hidden_size=H)
+    shm = setup_shared_memory(args, [f], batch_size=cap)
+    asm = RolloutAssembler(args).bind_shared(shm, [f])
+    fields = ("obs", "act", "rew", "logits", "log_prob", "is_fir", "hx", "cx")
+    for i in range(len(g["id"])):
+        data = {k: torch.from_numpy(g[f"in/{k}"][i]) for k in fields}
+        data["id"], data["done"] = int(g["id"][i]), torch.FloatTensor([float(g["done"][i])])
+        asm.push_now(data, now=float(g["now"][i]))
+        assert shm["batch_index"].value == int(g["count_after"][i]), f"slot counter after push {i}"
+        if i == reset_at:
+            shm["batch_index"].value = 0
+    for k in fields:
+        got = np.frombuffer(shm[f"{k}_batch"][0].get_obj(), dtype=np.float32)
+        np.testing.assert_array_equal(got, g[f"shared/{k}"], err_msg=k)
+    st = asm.stats()
+    assert st["spliced"] > 0 and st["dropped_age"] > 0 and st["emitted"] >= cap, st
+
+
+def test_native_assembler_queue_mode_and_learner_round_trip(backend, tmp_path):
+    """Without shared memory the class behaves like the reference's (`pop()` yields dicts of (T, width) tensors); bound to the
+    learner's shared arrays, T x B pushed steps become one batch the learner's own coroutines consume."""
+    from types import SimpleNamespace
+    from b200rl.buffers import RolloutAssembler
+    ops, dev = backend
+    T, f, A, H = 5, 4, 2, 64
+    args = SimpleNamespace(seq_len=T, action_space=A, hidden_size=H)
+    q = asyncio.Queue()
+    asm = RolloutAssembler(args, q, clock=lambda: 0.0)
+    rng = np.random.RandomState(0)
+    steps = [{k: torch.from_numpy(rng.randn(w).astype(np.float32)) for k, w in
+              dict(obs=f, act=1, rew=1, logits=A, log_prob=1, is_fir=1, hx=H, cx=H).items()} for _ in range(T)]
+
+    async def go():
+        for s in steps:
+            await asm.push(dict(s, id=1, done=torch.FloatTensor([0.0])))
+        return await asm.pop()
+    out = asyncio.run(go())
+    for k in ("obs", "logits", "hx"):
+        np.testing.assert_array_equal(out[k].numpy(), np.stack([s[k].numpy() for s in steps]))
+    assert out["obs"].shape == (T, f) and out["act"].shape == (T, 1)
