@@ -622,11 +622,11 @@ def main():
         bt = dev_batches[0]
         u = bt["obs"]
         gbuf, sbuf = (eng.chan.grad_views[0], eng.chan.scal_views[0]) if eng.chan is not None else (eng.grad, eng.scalars)
+        # the kernels of the update, as the engine launches them (fused variants), each timed alone
         stages = {
-            "lstm_fwd": lambda i: ops.lstm_fwd(L, eng.flat, u, bt["hx"], bt["cx"], eng.ws),
-            "head_fwd": lambda i: ops.head_fwd(L, eng.flat, eng.ws["h"], eng.head_out),
+            "lstm_fwd": lambda i: ops.net_fwd(L, eng.flat, u, bt["hx"], bt["cx"], eng.ws, eng.head_out),          # fused forward + head_combine
             "ppo_head": lambda i: ops.ppo_head(eng.head_out, bt, eng.dhead, sbuf, hp, A, False, None),
-            "lstm_bwd": lambda i: ops.lstm_bwd(L, eng.flat, eng.dhead, eng.ws, bt["cx"]),
+            "lstm_bwd": lambda i: ops.lstm_bwd(L, eng.flat, eng.dhead, eng.ws, bt["cx"], u=u, partials=eng.partials),   # BPTT + head / torso gradients
             "lstm_wgrad": lambda i: ops.lstm_wgrad(L, eng.flat, eng.ws, bt["hx"], u, eng.dhead, eng.partials, variant=eng.wgrad_variant),
             "reduce_partials": lambda i: ops.reduce_partials(eng.partials, gbuf),
         }
@@ -644,17 +644,20 @@ def main():
             fn(0)
         kms = {k: event_time(fn, 10, dev) for k, fn in stages.items()}
         bt_ = B * T
+        fused_bwd = bool(eng.ws.get("small_grads_done"))
         algo_bytes = {
-            "lstm_fwd": 4 * (bt_ * (F + 6 * H) + 2 * B * H + L.P),
-            "head_fwd": 4 * (bt_ * (H + L.NH)),
+            # obs in; gates, c, h out; partial heads out + in, head_out out; initial state; parameters
+            "lstm_fwd": 4 * (bt_ * (F + 6 * H + 4 * L.NH) + 2 * B * H + L.P),
             "ppo_head": 4 * (bt_ * (2 * L.NH + 4)),
-            "lstm_bwd": 4 * (bt_ * (4 * H + H + L.NH + 4 * H + H) + B * H),          # + dx (B,T,H) written by the tcgen05 BPTT kernel
-            "lstm_wgrad": 4 * (bt_ * (4 * H + H + H + F + L.NH) + eng.nparts * L.P),    # dpre, h, dx, u, dhead
+            # gates + c + dhead (+ obs) in, dpre out (+ dx out when the torso gradient is not fused)
+            "lstm_bwd": 4 * (bt_ * (4 * H + H + L.NH + 4 * H + (F if fused_bwd else H)) + B * H),
+            # dpre, h (+ dx, dhead for the separate torso / head passes), u in; one slab row per CTA out
+            "lstm_wgrad": 4 * (bt_ * (4 * H + H + F + (0 if fused_bwd else H + L.NH)) + eng.nparts * L.P),
             "reduce_partials": 4 * (eng.nparts * L.P + L.P),
             "clip_rmsprop": 4 * 6 * L.P,
         }
         # model FLOPs and what the tensor pipe really executes: every GEMM runs as three TF32 passes
-        algo_flop = {"lstm_fwd": 2.0 * bt_ * (F * H + 2 * H * 4 * H), "lstm_bwd": 2.0 * bt_ * (2 * 4 * H * H),
+        algo_flop = {"lstm_fwd": 2.0 * bt_ * (F * H + 2 * H * 4 * H + H * L.NH), "lstm_bwd": 2.0 * bt_ * (2 * 4 * H * H),
                      "lstm_wgrad": 2.0 * bt_ * (2 * 4 * H * H + H * F + H * L.NH)}
         dom = max(kms, key=kms.get)
         peak, peak_src, peaks = load_peaks()
