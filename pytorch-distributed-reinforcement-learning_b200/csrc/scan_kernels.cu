@@ -101,6 +101,70 @@ td_gae_kernel(const float* __restrict__ rew, const float* __restrict__ is_fir,
     }
 }
 
+// ------------------------------------------- td target + GAE, four timesteps per lane
+// The shuffle scan costs ~45 instructions per 32 elements, which is what bounds td_gae_kernel at large B*T (ncu r2j: 3.2 TB/s,
+// issue-bound).  Here a lane owns FOUR consecutive timesteps (one 16-byte load per input row segment), folds them into one
+// affine map serially, and the warp scans 128 timesteps with ONE 5-step shuffle scan.  The (B, T-1) outputs have 4-byte-
+// aligned rows, so the results are transposed through a 1 KB per-warp shared-memory tile and stored as full 128-byte lines.
+// Needs T % 4 == 0 and 16-byte aligned inputs (the launcher falls back to td_gae_kernel otherwise).
+__global__ void __launch_bounds__(kScanThreads)
+td_gae4_kernel(const float* __restrict__ rew, const float* __restrict__ is_fir,
+               const float* __restrict__ value, float* __restrict__ td_out,
+               float* __restrict__ gae, int B, int T, float gamma, float lam) {
+    __shared__ __align__(16) float stage[kScanThreads / 32][2][128];
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    const int n = T - 1;
+    const int nchunk = (T + 127) >> 7;
+    const float k = gamma * lam;
+    float* s_td = stage[wl][0];
+    float* s_g = stage[wl][1];
+    for (int row = wid; row < B; row += nw) {
+        const size_t o = (size_t)row * T, on = (size_t)row * n;
+        float carry = 0.0f;
+        for (int c = nchunk - 1; c >= 0; --c) {
+            const int t0 = c << 7, t = t0 + 4 * lane;
+            float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f), f4 = r4, v4 = r4;
+            if (t < T) { r4 = ld4(rew + o + t); f4 = ld4(is_fir + o + t); v4 = ld4(value + o + t); }
+            float vn = __shfl_down_sync(kFull, v4.x, 1), fn = __shfl_down_sync(kFull, f4.x, 1);
+            if (lane == 31) {
+                const bool more = t0 + 128 < T;
+                vn = more ? __ldg(value + o + t0 + 128) : 0.f;
+                fn = more ? __ldg(is_fir + o + t0 + 128) : 0.f;
+            }
+            const float rr[4] = {r4.x, r4.y, r4.z, r4.w}, vv[5] = {v4.x, v4.y, v4.z, v4.w, vn}, ff[5] = {f4.x, f4.y, f4.z, f4.w, fn};
+            float td[4], dl[4];
+            bool ok[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                ok[e] = t + e < n;
+                td[e] = ok[e] ? rr[e] + (gamma * (1.0f - ff[e + 1])) * vv[e + 1] : 0.f;      // ppo/learning.py:49-52
+                dl[e] = ok[e] ? td[e] - vv[e] : 0.f;
+            }
+            float a = 1.f, b = 0.f;                           // y[t] = a * y[t+4] + b for this lane's four steps
+#pragma unroll
+            for (int e = 3; e >= 0; --e) if (ok[e]) { b = fmaf(k, b, dl[e]); a *= k; }
+            const float y0 = affine_suffix_scan(a, b, carry);
+            float Y = __shfl_down_sync(kFull, y0, 1);
+            if (lane == 31) Y = carry;
+            float g[4];
+#pragma unroll
+            for (int e = 3; e >= 0; --e) { Y = ok[e] ? fmaf(k, Y, dl[e]) : Y; g[e] = Y; }
+            carry = __shfl_sync(kFull, y0, 0);
+            __syncwarp();
+            st4(s_td + 4 * lane, make_float4(td[0], td[1], td[2], td[3]));
+            st4(s_g + 4 * lane, make_float4(g[0], g[1], g[2], g[3]));
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int idx = i * 32 + lane;
+                if (t0 + idx < n) { td_out[on + t0 + idx] = s_td[idx]; gae[on + t0 + idx] = s_g[idx]; }
+            }
+        }
+    }
+}
+
 // -------------------------------------------------------------------------- V-trace
 __global__ void __launch_bounds__(kScanThreads)
 vtrace_kernel(const float* __restrict__ blp, const float* __restrict__ tlp,
@@ -199,7 +263,9 @@ extern "C" int b200rl_td_gae(const float* rew, const float* is_fir, const float*
                              float gamma, float lambda_, void* stream) {
     B200RL_REQUIRE(B >= 0 && T >= 1, "td_gae: bad shape B=%d T=%d", B, T);
     if (B == 0 || T == 1) return 0;
-    B200RL_LAUNCH(td_gae_kernel, scan_grid(B), kScanThreads, 0, stream, rew, is_fir, value, td_target, gae, B, T, gamma, lambda_);
+    const bool vec = (T % 4) == 0 && (((uintptr_t)rew | (uintptr_t)is_fir | (uintptr_t)value) & 15) == 0;
+    if (vec) { B200RL_LAUNCH(td_gae4_kernel, scan_grid(B), kScanThreads, 0, stream, rew, is_fir, value, td_target, gae, B, T, gamma, lambda_); }
+    else { B200RL_LAUNCH(td_gae_kernel, scan_grid(B), kScanThreads, 0, stream, rew, is_fir, value, td_target, gae, B, T, gamma, lambda_); }
     return check_launch("td_gae");
 }
 

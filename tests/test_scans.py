@@ -27,7 +27,8 @@ def test_compute_gae(backend, B, n):
     torch.testing.assert_close(got, want, **TOL)
 
 
-@pytest.mark.parametrize("B,T", [(2, 2), (3, 6), (4, 32), (4, 33), (5, 34), (3, 128), (2, 129), (2, 257)])
+@pytest.mark.parametrize("B,T", [(2, 2), (3, 6), (4, 32), (4, 33), (5, 34), (3, 128), (2, 129), (2, 257),
+                                 (1, 4), (5, 8), (3, 132), (3, 256), (2, 260), (9, 512)])     # (T % 4 == 0: four timesteps per lane)
 def test_td_gae(backend, B, T):
     ops, dev = backend
     x = _rand(B, T, seed=T)
