@@ -165,6 +165,123 @@ td_gae4_kernel(const float* __restrict__ rew, const float* __restrict__ is_fir,
     }
 }
 
+// ----------------------------------------------------- GAE, four timesteps per lane
+// compute_gae's rows have n = T-1 elements (4-byte aligned), so both directions go through the per-warp shared-memory tile:
+// coalesced 4-byte loads in, 16 bytes per lane out of the tile, one shuffle scan per 128 steps, and back the same way.
+__global__ void __launch_bounds__(kScanThreads)
+gae4_kernel(const float* __restrict__ deltas, float* __restrict__ gae, int B, int n, float k) {
+    __shared__ __align__(16) float stage[kScanThreads / 32][128];
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    const int nchunk = (n + 127) >> 7;
+    float* st = stage[wl];
+    for (int row = wid; row < B; row += nw) {
+        const float* d = deltas + (size_t)row * n;
+        float* g = gae + (size_t)row * n;
+        float carry = 0.0f;
+        for (int c = nchunk - 1; c >= 0; --c) {
+            const int t0 = c << 7;
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { const int idx = i * 32 + lane; st[idx] = t0 + idx < n ? __ldg(d + t0 + idx) : 0.f; }
+            __syncwarp();
+            const float4 d4 = ld4(st + 4 * lane);
+            const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
+            const int t = t0 + 4 * lane;
+            float a = 1.f, b = 0.f;
+#pragma unroll
+            for (int e = 3; e >= 0; --e) if (t + e < n) { b = fmaf(k, b, dl[e]); a *= k; }
+            const float y0 = affine_suffix_scan(a, b, carry);
+            float Y = __shfl_down_sync(kFull, y0, 1);
+            if (lane == 31) Y = carry;
+            float y[4];
+#pragma unroll
+            for (int e = 3; e >= 0; --e) { Y = (t + e < n) ? fmaf(k, Y, dl[e]) : Y; y[e] = Y; }
+            carry = __shfl_sync(kFull, y0, 0);
+            __syncwarp();
+            st4(st + 4 * lane, make_float4(y[0], y[1], y[2], y[3]));
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { const int idx = i * 32 + lane; if (t0 + idx < n) g[t0 + idx] = st[idx]; }
+        }
+    }
+}
+
+// ------------------------------------------------- V-trace, four timesteps per lane (T % 4 == 0, 16-byte aligned inputs)
+__global__ void __launch_bounds__(kScanThreads)
+vtrace4_kernel(const float* __restrict__ blp, const float* __restrict__ tlp,
+               const float* __restrict__ is_fir, const float* __restrict__ rew,
+               const float* __restrict__ values, float* __restrict__ rho_out,
+               float* __restrict__ adv_out, float* __restrict__ vs_out,
+               int B, int T, float gamma, float rho_bar, float c_bar) {
+    __shared__ __align__(16) float stage[kScanThreads / 32][2][128];
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nw = (gridDim.x * blockDim.x) >> 5;
+    const int n = T - 1;
+    const int nchunk = (T + 127) >> 7;
+    float* s_rho = stage[wl][0];
+    float* s_adv = stage[wl][1];
+    for (int row = wid; row < B; row += nw) {
+        const size_t o = (size_t)row * T, on = (size_t)row * n;
+        float carry = 0.0f;                                   // acc at the first step of the chunk processed before (later in time)
+        for (int c = nchunk - 1; c >= 0; --c) {
+            const int t0 = c << 7, t = t0 + 4 * lane;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 b4 = z, l4 = z, f4 = z, r4 = z, v4 = z;
+            if (t < T) { b4 = ld4(blp + o + t); l4 = ld4(tlp + o + t); f4 = ld4(is_fir + o + t); r4 = ld4(rew + o + t); v4 = ld4(values + o + t); }
+            float vn = __shfl_down_sync(kFull, v4.x, 1), fn = __shfl_down_sync(kFull, f4.x, 1);
+            if (lane == 31) {
+                const bool more = t0 + 128 < T;
+                vn = more ? __ldg(values + o + t0 + 128) : 0.f;
+                fn = more ? __ldg(is_fir + o + t0 + 128) : 0.f;
+            }
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, ll[4] = {l4.x, l4.y, l4.z, l4.w}, rr[4] = {r4.x, r4.y, r4.z, r4.w};
+            const float vv[5] = {v4.x, v4.y, v4.z, v4.w, vn}, ff[5] = {f4.x, f4.y, f4.z, f4.w, fn};
+            float rc[4], am[4], disc[4], dl[4];
+            bool ok[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                ok[e] = t + e < n;                            // scan / rho / adv are defined for t < T-1
+                const float rho = expf(ll[e] - bb[e]);
+                rc[e] = fminf(fmaxf(rho, 0.1f), rho_bar);     // compute_loss.py:37
+                disc[e] = gamma * (1.0f - ff[e + 1]);
+                am[e] = fminf(rho, c_bar) * disc[e];          // compute_loss.py:43
+                dl[e] = rc[e] * (rr[e] + disc[e] * vv[e + 1] - vv[e]);
+            }
+            float a = 1.f, b = 0.f;
+#pragma unroll
+            for (int e = 3; e >= 0; --e) if (ok[e]) { b = fmaf(am[e], b, dl[e]); a *= am[e]; }
+            const float y0 = affine_suffix_scan(a, b, carry);
+            float Y = __shfl_down_sync(kFull, y0, 1);
+            if (lane == 31) Y = carry;
+            float acc[5];
+            acc[4] = Y;                                       // acc at t + 4
+#pragma unroll
+            for (int e = 3; e >= 0; --e) acc[e] = ok[e] ? fmaf(am[e], acc[e + 1], dl[e]) : (t + e == n ? 0.0f : acc[e + 1]);   // acc[T-1] = 0
+            carry = __shfl_sync(kFull, y0, 0);
+            float adv[4], vs[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                vs[e] = vv[e] + (t + e >= n ? 0.0f : acc[e]);
+                const float vs1 = vv[e + 1] + ((t + e + 1 >= n) ? 0.0f : acc[e + 1]);
+                adv[e] = rc[e] * (rr[e] + disc[e] * vs1 - vv[e]);
+            }
+            if (t < T) st4(vs_out + o + t, make_float4(vs[0], vs[1], vs[2], vs[3]));
+            __syncwarp();
+            st4(s_rho + 4 * lane, make_float4(rc[0], rc[1], rc[2], rc[3]));
+            st4(s_adv + 4 * lane, make_float4(adv[0], adv[1], adv[2], adv[3]));
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int idx = i * 32 + lane;
+                if (t0 + idx < n) { rho_out[on + t0 + idx] = s_rho[idx]; adv_out[on + t0 + idx] = s_adv[idx]; }
+            }
+        }
+    }
+}
+
 // -------------------------------------------------------------------------- V-trace
 __global__ void __launch_bounds__(kScanThreads)
 vtrace_kernel(const float* __restrict__ blp, const float* __restrict__ tlp,
@@ -254,7 +371,8 @@ extern "C" int b200rl_compute_gae(const float* deltas, float* gae, int B, int n,
                                   float gamma, float lambda_, void* stream) {
     B200RL_REQUIRE(B >= 0 && n >= 0, "compute_gae: bad shape B=%d n=%d", B, n);
     if (B == 0 || n == 0) return 0;
-    B200RL_LAUNCH(gae_kernel, scan_grid(B), kScanThreads, 0, stream, deltas, gae, B, n, gamma * lambda_);
+    if (n >= 64) { B200RL_LAUNCH(gae4_kernel, scan_grid(B), kScanThreads, 0, stream, deltas, gae, B, n, gamma * lambda_); }
+    else { B200RL_LAUNCH(gae_kernel, scan_grid(B), kScanThreads, 0, stream, deltas, gae, B, n, gamma * lambda_); }
     return check_launch("compute_gae");
 }
 
@@ -275,8 +393,15 @@ extern "C" int b200rl_compute_v_trace(const float* behav_logp, const float* targ
                                       float gamma, float rho_bar, float c_bar, void* stream) {
     B200RL_REQUIRE(B >= 0 && T >= 1, "compute_v_trace: bad shape B=%d T=%d", B, T);
     if (B == 0) return 0;
-    B200RL_LAUNCH(vtrace_kernel, scan_grid(B), kScanThreads, 0, stream, behav_logp, target_logp, is_fir, rew, values,
-                  rho, adv, vs, B, T, gamma, rho_bar, c_bar);
+    const bool vec = (T % 4) == 0 && (((uintptr_t)behav_logp | (uintptr_t)target_logp | (uintptr_t)is_fir | (uintptr_t)rew |
+                                       (uintptr_t)values | (uintptr_t)vs) & 15) == 0;
+    if (vec) {
+        B200RL_LAUNCH(vtrace4_kernel, scan_grid(B), kScanThreads, 0, stream, behav_logp, target_logp, is_fir, rew, values,
+                      rho, adv, vs, B, T, gamma, rho_bar, c_bar);
+    } else {
+        B200RL_LAUNCH(vtrace_kernel, scan_grid(B), kScanThreads, 0, stream, behav_logp, target_logp, is_fir, rew, values,
+                      rho, adv, vs, B, T, gamma, rho_bar, c_bar);
+    }
     return check_launch("compute_v_trace");
 }
 

@@ -18,7 +18,7 @@ def _rand(B, T, seed=0):
                 value=r(B, T, 1), blp=-torch.rand(B, T, 1, generator=g) * 2, tlp=-torch.rand(B, T, 1, generator=g) * 2)
 
 
-@pytest.mark.parametrize("B,n", [(1, 1), (3, 5), (8, 31), (5, 32), (4, 33), (7, 127), (2, 128), (3, 300), (0, 7), (4, 0)])
+@pytest.mark.parametrize("B,n", [(1, 1), (3, 5), (8, 31), (5, 32), (4, 33), (7, 127), (2, 128), (3, 300), (0, 7), (4, 0), (6, 64), (5, 65), (3, 129), (4, 255), (2, 513)])
 def test_compute_gae(backend, B, n):
     ops, dev = backend
     d = torch.randn(B, n, 1, generator=torch.Generator().manual_seed(B * 1000 + n))
@@ -39,7 +39,8 @@ def test_td_gae(backend, B, T):
     torch.testing.assert_close(ggae.cpu(), want, **TOL)
 
 
-@pytest.mark.parametrize("B,T", [(1, 1), (2, 2), (3, 6), (4, 32), (4, 33), (5, 34), (3, 64), (3, 128), (2, 129), (2, 257)])
+@pytest.mark.parametrize("B,T", [(1, 1), (2, 2), (3, 6), (4, 32), (4, 33), (5, 34), (3, 64), (3, 128), (2, 129), (2, 257),
+                                 (1, 4), (5, 8), (3, 132), (3, 256), (2, 260), (9, 512)])     # (T % 4 == 0: four timesteps per lane)
 def test_compute_v_trace(backend, B, T):
     ops, dev = backend
     x = _rand(B, T, seed=100 + T)
