@@ -51,6 +51,12 @@ def config_dict(world):
             "l2": "per-step working set (saved activations 0.8 GB) >> 126 MB L2; 4 input batches cycled"}
 
 
+def product_hyper():
+    """Hyper-parameters of the product's own parameters.json (the values the reference ships, utils/parameters.json:1-31)."""
+    from b200rl.utils.utils import load_params, hyper_from_args
+    return hyper_from_args(load_params(os.path.join(PKG, "b200rl", "utils", "parameters.json")))
+
+
 def hyper_args(device, algo="PPO", b=B, t=T, a_=A):
     from b200rl.utils.utils import load_params
     a = load_params(os.path.join(PKG, "b200rl", "utils", "parameters.json"))
@@ -215,7 +221,7 @@ def cpu_baseline_and_parity(dev):
     # the same first update on the GPU, fresh weights (same seed -> bit-identical initial state dict, tests/test_oracle_golden.py)
     torch.manual_seed(0)
     model = MlpLSTMSingle(F, A, T, H).to(dev)
-    eng = OnPolicyEngine(model.actor, "PPO", oracle.DEFAULT_HYPER)
+    eng = OnPolicyEngine(model.actor, "PPO", product_hyper())
     eng.update({k: v.to(dev) for k, v in make_rollouts(B, T, F, A, batch_index=0).items()})
     L = eng.losses()
     got = torch.cat([v.reshape(-1) for v in model.actor.views_of(eng.flat).values()]).cpu()
@@ -379,11 +385,11 @@ def dp_parity(dev, rank, world, pg):
         full = make_rollouts(Bs, Ts, 4, 2)
         shard = {k: cut(v) for k, v in full.items()}
         if algo == "V-MPO":
-            eng = VMPOEngine(model.actor, oracle.DEFAULT_HYPER, process_group=pg)
+            eng = VMPOEngine(model.actor, product_hyper(), process_group=pg)
             for _ in range(2):
                 eng.update(shard, 0.0075)
         else:
-            eng = OnPolicyEngine(model.actor, algo, oracle.DEFAULT_HYPER, process_group=pg)
+            eng = OnPolicyEngine(model.actor, algo, product_hyper(), process_group=pg)
             for _ in range(2):
                 eng.update(shard)
         L = eng.losses()
@@ -405,7 +411,7 @@ def dp_parity(dev, rank, world, pg):
     pa = OrderedDict((k, v.clone()) for k, v in model.actor.state_dict().items())
     pc = OrderedDict((k, v.clone()) for k, v in model.critic.state_dict().items())
     model = model.to(dev)
-    eng = SACEngine(model, oracle.DEFAULT_HYPER, True, process_group=pg)
+    eng = SACEngine(model, product_hyper(), True, process_group=pg)
     g = torch.Generator().manual_seed(11)
     batches = [make_rollouts(Bs, Tq, f, Ad, continuous=True, batch_index=i, act_dim=Ad) for i in range(2)]
     noise = [[torch.randn(Bs, Tq, Ad, generator=g), torch.randn(Bs, Tq, Ad, generator=g)] for _ in range(2)]
@@ -432,7 +438,6 @@ def dp_parity(dev, rank, world, pg):
 def other_configs(dev, rank, world, pg, timed, steps=10, warmup=3):
     """The other BASELINE.json configs at their stated per-GPU shapes (cfg4 / cfg5 are 8-GPU configs: 1/8 of the global batch
     per rank, so at N=8 these ARE the stated configs; at other N the global batch is N/8 of it)."""
-    import oracle
     from b200rl.engine import OnPolicyEngine, VMPOEngine, SACEngine
     from b200rl.networks import models as M
     from b200rl.synth import make_rollouts
@@ -449,15 +454,15 @@ def other_configs(dev, rank, world, pg, timed, steps=10, warmup=3):
                                              ("cfg3_ppo_continuous_B2048_T128", "PPO-Continuous", 2048, 128, 2, 1, True),
                                              ("cfg1_ppo_B64_T32", "PPO", 64, 32, 4, 2, False)):
         model = (M.MlpLSTMSingleContinuous if cont else M.MlpLSTMSingle)(f, Aa, Tn, 64).to(dev)
-        eng = OnPolicyEngine(model.actor, algo, oracle.DEFAULT_HYPER, process_group=pg)
+        eng = OnPolicyEngine(model.actor, algo, product_hyper(), process_group=pg)
         bs = [{k: v.to(dev) for k, v in make_rollouts(Bn, Tn, f, Aa, continuous=cont, batch_index=rank * 100 + i).items()} for i in range(2)]
         run(name, eng, bs, Bn, Tn, lambda e, b: e.update(b))
     model = M.MlpLSTMSingle(4, 2, 128, 64).to(dev)
-    eng = VMPOEngine(model.actor, oracle.DEFAULT_HYPER, process_group=pg)
+    eng = VMPOEngine(model.actor, product_hyper(), process_group=pg)
     bs = [{k: v.to(dev) for k, v in make_rollouts(1024, 128, 4, 2, batch_index=rank * 100 + i).items()} for i in range(2)]
     run("cfg4_vmpo_1024_per_gpu_T128", eng, bs, 1024, 128, lambda e, b: e.update(b, 0.0075))
     model = M.MlpLSTMSeperateContinuous(17, 6, 5, 64, act_dim=6).to(dev)
-    eng = SACEngine(model, oracle.DEFAULT_HYPER, True, process_group=pg)
+    eng = SACEngine(model, product_hyper(), True, process_group=pg)
     bs = [{k: v.to(dev) for k, v in make_rollouts(8192, 5, 17, 6, continuous=True, batch_index=rank * 100 + i, act_dim=6).items()} for i in range(2)]
     run("cfg5_sac_continuous_8192_per_gpu_T5_obs17_act6", eng, bs, 8192, 5, lambda e, b: e.update(b))
     return res

@@ -36,7 +36,7 @@ typedef int cudaError_t;
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 
 namespace emul {
 struct WarpCtx {
