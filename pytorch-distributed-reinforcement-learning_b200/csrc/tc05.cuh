@@ -41,6 +41,17 @@ __host__ __device__ inline unsigned short bf16_bits(float f) { unsigned u; memcp
 // fp32 -> bf16 bits, round to nearest even: zero-mean error (truncation is one-sided, and a recurrence accumulates the bias)
 __host__ __device__ inline unsigned short bf16_bits_rn(float f) { unsigned u; memcpy(&u, &f, 4); return (unsigned short)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16); }
 
+// two fp32 -> one 32-bit word of two bf16 (round to nearest even): `e0` in the low half (the lower k), `e1` in the high half
+__device__ __forceinline__ uint32_t pack_bf16x2_rn(float e0, float e1) {
+#ifdef B200RL_EMUL
+    return (uint32_t)bf16_bits_rn(e0) | ((uint32_t)bf16_bits_rn(e1) << 16);
+#else
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(e1), "f"(e0));
+    return r;
+#endif
+}
+
 #ifndef B200RL_EMUL
 // ------------------------------------------------------------------------------ device
 typedef uint64_t SmemDesc;
@@ -108,6 +119,15 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, SmemDesc a, SmemDesc b
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T with bf16 inputs, K = 16, both operands K-major (8 bf16 per 16-byte core-matrix row)
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, SmemDesc a, SmemDesc b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
 }
 // D[tmem] (+)= A[tmem] . B[smem]^T : the A tile (M = 128 lanes x K = 8 columns, one 32-bit cell per tf32 element)
@@ -271,6 +291,21 @@ inline void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, SmemDesc b, uint32_t i
         for (int n = 0; n < N; ++n) {
             float s = accumulate ? t.d[m][d_tmem + n] : 0.f;
             for (int k = 0; k < 8; ++k) s += __uint_as_float(__float_as_uint(t.d[m][a_tmem + k]) & kTf32Mask) * emul_elem(b, bmn, n, k);
+            t.d[m][d_tmem + n] = s;
+        }
+}
+inline void mma_bf16(uint32_t d_tmem, SmemDesc a, SmemDesc b, uint32_t idesc, uint32_t accumulate) {
+    const int M = (int)((idesc >> 24) & 31) << 4, N = (int)((idesc >> 17) & 63) << 3;
+    EmulTmem& t = emul_tmem();
+    auto el = [](const SmemDesc& d, int mn, int k) {
+        unsigned short h;
+        memcpy(&h, d.base + (size_t)(mn % 8) * 16 + (size_t)(mn / 8) * d.sbo + (size_t)(k % 8) * 2 + (size_t)(k / 8) * d.lbo, 2);
+        unsigned u = (unsigned)h << 16; float f; memcpy(&f, &u, 4); return f;
+    };
+    for (int m = 0; m < M; ++m)
+        for (int n = 0; n < N; ++n) {
+            float s = accumulate ? t.d[m][d_tmem + n] : 0.f;
+            for (int k = 0; k < 16; ++k) s += el(a, m, k) * el(b, n, k);
             t.d[m][d_tmem + n] = s;
         }
 }

@@ -7,46 +7,67 @@
 // i.e. the autograd `AddmmBackward` of every nn.LSTMCell step of the reference
 // (networks/models.py:71-75 replayed by loss.backward(), ppo/learning.py:92), as ONE
 // reduction GEMM over all B*T rows:  dW^T[128 x 256] = A^T[128 x BT] . D[BT x 256],
-// A = [x | h_prev].  Each CTA owns every `gridDim`-th stage of 32 rows, accumulates the
+// A = [x | h_prev].  Each CTA owns every `gridDim`-th stage of 16 rows, accumulates the
 // full 128x256 fp32 tile in TMEM (256 columns) and writes one partial slab at the end.
 //
-// Precision: fp32 parity needs more than one TF32 pass, so both operands
-// are split on the fly, v = hi + lo with hi, lo exactly representable in TF32, and three
-// MMAs are issued per K-step: hi*hi + hi*lo + lo*hi (the dropped lo*lo term is ~2^-22).
+// Precision: fp32 parity needs more than one TF32 pass, so both operands are split on the fly,
+// v = hi + lo with hi exactly representable in TF32, and three products are accumulated into the same fp32 tile:
+//     hi*hi          as kind::tf32 (K = 8 per MMA: two per stage),
+//     v*lo + lo*v    with all four factors rounded to bf16, as kind::f16 (K = 16 per MMA, twice the TF32 rate): ONE
+//                    contraction of length 32 per stage over the concatenated operands  A' = [v | lo],  D' = [lo | v]
+// -- the cross terms are 2^-11 of the product, so their bf16 rounding (2^-9) lands at 2^-20 of it, and they carry the
+// dropped lo*lo term twice (2^-21).  Four tensor-pipe units per 16 rows instead of the six of three TF32 passes
+// (ncu r2j: the tensor pipe was 53 % busy and the 6 MMAs read 72 KB of shared memory per stage; now 36 %, 48 KB).
 //
-// Data path per stage (16 rows = 2 K-steps of 8): all 256 threads load fp32 rows from HBM --
-// a quarter-warp takes one full 128-byte line of a row, a warp 4 rows (requests that touch half
-// lines of 8 rows ran at 2.3 TB/s: the SM's outstanding-request budget, not bytes, was the limit,
-// tools/dx_prof.cu) -- recompute x, split hi/lo and scatter the values with 4-byte stores into the
-// canonical no-swizzle K-major UMMA layout, where the contraction index (the row r) is the fast one:
-//     elem(mn, r) at (mn%8)*16 + (mn/8)*SBO + (r%4)*4 + (r/4)*LBO        [bytes]
-// (measured on B200: kind::tf32 with MN-major descriptors returns zeros, K-major is exact
-// -- tools/tc_probe.cu -- so the tile is transposed on the way into shared memory).
-// SBO = 528 B (= 16 B modulo 128 B) makes the 32 lanes of every scatter store (4 rows x 8 float4
-// columns, one element each) hit 32 distinct banks.
+// Data path per stage: all 256 producer threads load fp32 from HBM -- a warp reads 512 contiguous bytes of a dpre row or
+// one full 128-byte line of an h row per instruction (4.7 TB/s for the bare load loop against 4.3 TB/s when a warp
+// instruction touches four rows, and 2.3 TB/s with half lines: tools/wgrad_prof.cu, tools/dx_prof.cu) -- such that EVERY
+// THREAD OWNS FOUR CONSECUTIVE ROWS OF ITS COLUMNS.  In the canonical no-swizzle K-major UMMA layouts the contraction index
+// is the fast one and a 16-byte core-matrix row holds 4 tf32 or 8 bf16 of it:
+//     tf32 tile:  elem(mn, r)  at (mn%8)*16 + (mn/8)*SBO + (r/4)*LBO + (r%4)*4          [bytes], r = row of the stage
+//     bf16 tile:  elem(mn, kk) at (mn%8)*16 + (mn/8)*SBO + (kk/8)*LBO + (kk%8)*2
+// and the order of the contraction index is free as long as both operands agree: the bf16 tiles use
+//     kk = (r/4)*8 + (r%4)      for the first factor of a row ( v of A', lo of D'),   kk + 4 for the second (lo of A', v of D'),
+// so the four rows of one column are ONE 16-byte store into the tf32 tile and ONE 16-byte store AT THE SAME OFFSET into the
+// bf16 tile: 12 conflict-free 16-byte stores per thread and stage instead of 48 scalar scatters.
+// (measured on B200: kind::tf32 with MN-major descriptors returns zeros, K-major is exact -- tools/tc_probe.cu -- so the
+// tile is transposed on the way into shared memory; a raw TMA tile cannot feed these MMAs.)
+// SBO = 528 B (= 16 B modulo 128 B) makes the 8 lanes of every store wavefront hit distinct 16-byte bank groups.
 //
 // Warp-specialised pipeline (no CTA-wide barrier inside the loop): warps 0-7 are PRODUCERS
-// (load / split / scatter a stage, fence.proxy.async, arrive on full[stage]); warp 8 is the MMA
-// ISSUER (one lane waits on full[stage], issues 6 tcgen05.mma, tcgen05.commit -> empty[stage]).
+// (load / split / store a stage, fence.proxy.async, arrive on full[stage]); warp 8 is the MMA
+// ISSUER (one lane waits on full[stage], issues 4 tcgen05.mma, tcgen05.commit -> empty[stage]).
 // A single thread needs ~50-100 cycles per tcgen05.mma issue (tools/tc_probe2.cu), so the
-// issuer must not be one of the filling threads.  3-stage ring, 189 KB of smem.
+// issuer must not be one of the filling threads.  2-stage ring, two CTAs per SM.
 #include "common.cuh"
 #include "tc05.cuh"
 #include "launchers.cuh"
 
 namespace b200rl {
 
+#ifndef B200RL_WGPROBE
+#define B200RL_WGPROBE 0     // tools/wgrad_prof.cu only: 1 loads only, 2 no MMAs, 3 no HBM loads (timing experiments; results invalid)
+#endif
+
+#ifndef B200RL_WG_BF16X
+#define B200RL_WG_BF16X 0    // 1: cross terms v*lo + lo*v as ONE bf16 contraction (4 tensor units per stage, 2^-20); 0: two more TF32 passes (6 units, 2^-22)
+#endif
+
 namespace wtc {
+constexpr int kProbe = B200RL_WGPROBE;
+constexpr bool kBf16X = B200RL_WG_BF16X != 0;
 constexpr int H = 64, G = 256, KC = 128, NP = 256, NT = NP + 32;   // producers + issuer warp
-constexpr int SR = 16;                          // rows per stage (2 MMA K-steps of 8)
-constexpr int NSTAGE = 2;                         // two CTAs per SM (2 x 101 KB of stages, 2 x 256 TMEM columns): 4 producer warps per sub-partition
-constexpr int LBO = 128;                        // K direction: next core matrix (4 rows)
+constexpr int SR = 16;                          // rows per stage (2 TF32 K-steps of 8; 2 bf16 K-steps of 16 over [v | lo])
+constexpr int NSTAGE = 2;                       // two CTAs per SM (2 x 101 KB of stages, 2 x 256 TMEM columns): 4 producer warps per sub-partition
+constexpr int LBO = 128;                        // K direction: next core matrix (4 rows of the stage)
 constexpr int SBO = 528;                        // MN direction: next group of 8 mn (4 core matrices + 16 B skew) = 16 B mod 128 B
 constexpr int A_TILE = (KC / 8) * SBO;          // 8448
 constexpr int D_TILE = (G / 8) * SBO;           // 16896
-constexpr int STAGE = 2 * A_TILE + 2 * D_TILE;  // A_hi | A_lo | D_hi | D_lo = 50688 B
+constexpr int O_AH = 0, O_DH = A_TILE, O_AB = O_DH + D_TILE, O_DB = O_AB + A_TILE;   // A_hi | D_hi (tf32) | A' | D' (bf16)
+constexpr int STAGE = O_DB + D_TILE;            // 50688 B
 constexpr int MAXF = 32;
 static_assert((SR / 4 - 1) * LBO + 128 <= SBO, "core matrices of one mn-group must fit below SBO");
+static_assert(STAGE % 16 == 0 && O_DH % 16 == 0 && O_AB % 16 == 0 && O_DB % 16 == 0, "descriptor alignment");
 __device__ __forceinline__ int koff(int mn, int r) { return (mn & 7) * 16 + (mn >> 3) * SBO + (r & 3) * 4 + (r >> 2) * LBO; }
 }  // namespace wtc
 
@@ -71,7 +92,8 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool producer = warp < NP / 32;
-    const int rq = lane >> 3, cq = lane & 7;                         // row inside a group of 4, float4 inside a 128-byte line
+    const int drg = (warp >> 1) & 3, dc4 = (warp & 1) * 32 + lane;   // D tile: row group of 4, float4 column (a warp = half a dpre row)
+    const int ak = tid & 63, arg = (tid >> 6) & 3;                   // A tile: hidden column, row group of 4
 
     for (int i = tid; i < Fin * H; i += NT) { int q = i / H, j = i % H; WtS[i] = Wt[j * Fin + q]; }
     if (tid < H) bts[tid] = bt[tid];
@@ -86,120 +108,164 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
     tc::fence_after_sync();
     const uint32_t tmem = *tmem_slot;
     const uint32_t idesc = tc::make_idesc_tf32(KC, G, false, false);
+    const uint32_t idescb = tc::make_idesc_bf16(KC, G);
 
     const long long rows = (long long)B * T;
     const long long nstages = (rows + SR - 1) / SR;
-    float4 dbacc = make_float4(0.f, 0.f, 0.f, 0.f);               // bias gradient of gate columns (warp*8 + cq)*4 .. +3
+    float4 dbacc = make_float4(0.f, 0.f, 0.f, 0.f);               // bias gradient of gate columns dc4*4 .. +3 over this thread's rows
+    const bool ulane = 4 * Fin <= 32;                              // the 4 x Fin torso inputs of a row group: one per lane
 
-    // Register-staged loads: two register sets; the HBM reads of the CTA's next stage are issued before the current one
-    // is split and scattered (the co-resident second CTA keeps another stage in flight on the same SM).
-    constexpr int UP = 4;                           // torso inputs prefetched in registers when Fin <= UP
-    struct StageRegs { float4 d[4]; float4 h; float u[UP]; bool ok; };
+    // Register-staged loads: two register sets, both in flight except while their own stage is processed (a set is refilled,
+    // two stages ahead, as soon as it has been written to shared memory).  The common case -- a stage with all 16 rows in
+    // range and no sequence start among them -- runs without a single bounds check or row/time division: three running
+    // pointers, immediate offsets.  `mode`: 0 nothing, 1 fast, 2 generic.
+    struct StageRegs { float4 d[4]; float hp[4]; float u; int mode; };
     StageRegs ring[2];
-    auto issue_loads = [&](StageRegs& R, long long stg) {
-        const long long row0 = stg * SR;
-        const bool live = stg < nstages;
+    const long long stride = (long long)gridDim.x * SR;            // rows between two stages of this CTA
+    const float* dptr = dpre + ((size_t)blockIdx.x * SR + drg * 4) * G + dc4 * 4;
+    const float* hptr = h + ((long long)blockIdx.x * SR + arg * 4 - 1) * H + ak;
+    const float* uptr = u + ((size_t)blockIdx.x * SR + arg * 4) * Fin + lane;
+    const unsigned tstep = (unsigned)(stride % T);
+    unsigned tpos = (unsigned)(((long long)blockIdx.x * SR) % T);  // time index of the stage's first row
+    long long lrow = (long long)blockIdx.x * SR;                   // first row of the next stage to load
+    auto issue_loads = [&](StageRegs& R) {
+        const long long row0 = lrow;
+        const bool live = row0 < rows;
+        const bool whole = row0 + SR <= rows;
+        const bool has_t0 = tpos == 0 || tpos + SR > (unsigned)T;  // a row with t == 0 takes h_{t-1} from hx0
+        R.mode = !live ? 0 : (whole && !has_t0) ? 1 : 2;
+        if (kProbe == 3) {
 #pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) {
-            const int c4 = warp * 8 + cq;
-            const long long row = row0 + i4 * 4 + rq;
-            R.d[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live && row < rows) R.d[i4] = *reinterpret_cast<const float4*>(dpre + (size_t)row * G + c4 * 4);
-        }
-        const int c4 = (warp & 1) * 8 + cq;
-        const long long row = row0 + (warp >> 1) * 4 + rq;
-        R.h = make_float4(0.f, 0.f, 0.f, 0.f);
-        R.ok = live && row < rows;
+            for (int j = 0; j < 4; ++j) { R.d[j] = make_float4(1.f, 2.f, 3.f, 4.f); R.hp[j] = 1.f; }
+            R.u = 1.f;
+        } else if (R.mode == 1) {
 #pragma unroll
-        for (int q = 0; q < UP; ++q) R.u[q] = 0.f;
-        if (R.ok) {
-            const unsigned urow = (unsigned)row, b = urow / (unsigned)T, t = urow - b * (unsigned)T;   // 32-bit: B*T < 2^31 is checked by the launcher
-            const float* hp = (t == 0) ? hx0 + (size_t)b * H : h + (size_t)(row - 1) * H;
-            R.h = *reinterpret_cast<const float4*>(hp + c4 * 4);
-            if (Fin <= UP) {
+            for (int j = 0; j < 4; ++j) R.d[j] = *reinterpret_cast<const float4*>(dptr + j * G);
 #pragma unroll
-                for (int q = 0; q < UP; ++q) if (q < Fin) R.u[q] = __ldg(u + (size_t)row * Fin + q);
+            for (int j = 0; j < 4; ++j) R.hp[j] = __ldg(hptr + j * H);
+            R.u = (ulane && lane < 4 * Fin) ? __ldg(uptr) : 0.f;
+        } else {
+            const long long r = row0 + drg * 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                R.d[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live && r + j < rows) R.d[j] = *reinterpret_cast<const float4*>(dptr + j * G);
             }
+            const long long ra = row0 + arg * 4;
+            unsigned b = 0, t = 0;
+            if (live && ra < rows) { const unsigned ur = (unsigned)ra; b = ur / (unsigned)T; t = ur - b * (unsigned)T; }   // 32-bit: B*T < 2^31 is checked by the launcher
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                R.hp[j] = 0.f;
+                if (live && ra + j < rows) R.hp[j] = (t == 0) ? __ldg(hx0 + (size_t)b * H + ak) : __ldg(hptr + j * H);
+                if (++t == (unsigned)T) { t = 0; ++b; }
+            }
+            R.u = 0.f;
+            if (ulane && live && lane < 4 * Fin && ra * Fin + lane < rows * Fin) R.u = __ldg(uptr);
         }
+        dptr += stride * G; hptr += stride * H; uptr += stride * Fin; lrow += stride;
+        tpos += tstep; if (tpos >= (unsigned)T) tpos -= (unsigned)T;
     };
 
-    int it = 0;
-    auto process = [&](const StageRegs& R, long long st) {
-        const int buf = it % NSTAGE, use = it / NSTAGE;
+    // per-thread tile offsets (constant over the stages; the same in the tf32 and in the bf16 tile)
+    const int oD = koff(dc4 * 4, drg * 4);                         // gate columns dc4*4 + e are 16 bytes apart
+    const int oA = koff(ak, arg * 4);
+    constexpr int HK = (H >> 3) * SBO;                             // column H + ak is H/8 mn-groups further
+    // four consecutive rows of one column: the TF32 parts into the tf32 tile; the bf16 roundings of the values and of their
+    // remainders into the bf16 tile (`lo_first`: D' = [lo | v], else A' = [v | lo])
+    auto put4 = [](unsigned char* p_hi, unsigned char* p_b, bool lo_first, float v0, float v1, float v2, float v3) {
+        const float h0 = __uint_as_float(__float_as_uint(v0) & tc::kTf32Mask), h1 = __uint_as_float(__float_as_uint(v1) & tc::kTf32Mask);
+        const float h2 = __uint_as_float(__float_as_uint(v2) & tc::kTf32Mask), h3 = __uint_as_float(__float_as_uint(v3) & tc::kTf32Mask);
+        *reinterpret_cast<float4*>(p_hi) = make_float4(h0, h1, h2, h3);
+        if (!kBf16X) { *reinterpret_cast<float4*>(p_b) = make_float4(v0 - h0, v1 - h1, v2 - h2, v3 - h3); return; }   // the lo tile (the tensor core drops the bits below TF32)
+        const uint32_t a0 = tc::pack_bf16x2_rn(v0, v1), a1 = tc::pack_bf16x2_rn(v2, v3);
+        const uint32_t l0 = tc::pack_bf16x2_rn(v0 - h0, v1 - h1), l1 = tc::pack_bf16x2_rn(v2 - h2, v3 - h3);
+        float4 w;
+        if (lo_first) w = make_float4(__uint_as_float(l0), __uint_as_float(l1), __uint_as_float(a0), __uint_as_float(a1));
+        else w = make_float4(__uint_as_float(a0), __uint_as_float(a1), __uint_as_float(l0), __uint_as_float(l1));
+        *reinterpret_cast<float4*>(p_b) = w;
+    };
+
+    constexpr int UP = 4;                                         // torso widths up to UP keep their weight column in registers
+    const float bk = bts[ak];
+    float wk[UP];
+#pragma unroll
+    for (int q = 0; q < UP; ++q) wk[q] = q < Fin ? WtS[q * H + ak] : 0.f;
+
+    int nproc = 0;
+    long long prow = (long long)blockIdx.x * SR;                  // first row of the next stage to process
+    auto process = [&](const StageRegs& R, int buf) {
+        const int use = nproc >> 1;
         unsigned char* sb = stage0 + (size_t)buf * STAGE;
-        unsigned char* A_hi = sb, *A_lo = sb + A_TILE, *D_hi = sb + 2 * A_TILE, *D_lo = sb + 2 * A_TILE + D_TILE;
-        const long long row0 = st * SR;
+        if (kProbe == 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { dbacc.x += R.d[j].x + R.hp[j]; dbacc.y += R.d[j].y; dbacc.z += R.d[j].z; dbacc.w += R.d[j].w + R.u; }
+            ++nproc; prow += stride;
+            return;
+        }
         if (use >= 1) tc::mbar_wait(&empty[buf], (uint32_t)((use - 1) & 1));  // MMAs of the previous use of this buffer are done
 
-        // ---- D tile: 16 rows x 64 float4.  Thread: rows i4*4 + rq, float4 column warp*8 + cq
-#pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) {
-            const int c4 = warp * 8 + cq;
-            const int r = i4 * 4 + rq;
-            const float4 v = R.d[i4];
-            dbacc.x += v.x; dbacc.y += v.y; dbacc.z += v.z; dbacc.w += v.w;
-            const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float hi, lo;
-                tc::split_tf32(vv[e], hi, lo);
-                const int o = koff(c4 * 4 + e, r);
-                *reinterpret_cast<float*>(D_hi + o) = hi;
-                *reinterpret_cast<float*>(D_lo + o) = lo;
-            }
-        }
-        // ---- A tile: [x_t (k<64) | h_{t-1} (k>=64)], 16 float4 each per row; thread: row (warp>>1)*4 + rq
+        // ---- D tile: thread = rows drg*4 .. +3 of the four gate columns dc4*4 .. +3
         {
-            const int r = (warp >> 1) * 4 + rq, c4 = (warp & 1) * 8 + cq;                // c4 in 0..15
-            const long long row = row0 + r;
-            float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 hv = R.h;
-            if (R.ok) {
-                float4 a = *reinterpret_cast<const float4*>(bts + c4 * 4);
-                if (Fin <= UP) {
+            dbacc.x += (R.d[0].x + R.d[1].x) + (R.d[2].x + R.d[3].x);
+            dbacc.y += (R.d[0].y + R.d[1].y) + (R.d[2].y + R.d[3].y);
+            dbacc.z += (R.d[0].z + R.d[1].z) + (R.d[2].z + R.d[3].z);
+            dbacc.w += (R.d[0].w + R.d[1].w) + (R.d[2].w + R.d[3].w);
+            unsigned char* ph = sb + O_DH + oD, *pb = sb + O_DB + oD;
+            put4(ph, pb, true, R.d[0].x, R.d[1].x, R.d[2].x, R.d[3].x);
+            put4(ph + 16, pb + 16, true, R.d[0].y, R.d[1].y, R.d[2].y, R.d[3].y);
+            put4(ph + 32, pb + 32, true, R.d[0].z, R.d[1].z, R.d[2].z, R.d[3].z);
+            put4(ph + 48, pb + 48, true, R.d[0].w, R.d[1].w, R.d[2].w, R.d[3].w);
+        }
+        // ---- A tile: [x_t (k < 64) | h_{t-1} (k >= 64)]; thread = rows arg*4 .. +3 of column ak of both halves
+        {
+            float x[4];
 #pragma unroll
-                    for (int q = 0; q < UP; ++q) {
-                        if (q < Fin) {
-                            const float4 w = *reinterpret_cast<const float4*>(WtS + q * H + c4 * 4);
-                            a.x = fmaf(R.u[q], w.x, a.x); a.y = fmaf(R.u[q], w.y, a.y); a.z = fmaf(R.u[q], w.z, a.z); a.w = fmaf(R.u[q], w.w, a.w);
-                        }
-                    }
-                } else {
-                    const float* ur = u + (size_t)row * Fin;
-                    for (int q = 0; q < Fin; ++q) {
-                        const float uv = __ldg(ur + q);
-                        const float4 w = *reinterpret_cast<const float4*>(WtS + q * H + c4 * 4);
-                        a.x = fmaf(uv, w.x, a.x); a.y = fmaf(uv, w.y, a.y); a.z = fmaf(uv, w.z, a.z); a.w = fmaf(uv, w.w, a.w);
+            for (int j = 0; j < 4; ++j) x[j] = bk;
+            if (Fin <= UP) {                                       // torso column ak in registers, the 4 x Fin inputs by shuffle
+#pragma unroll
+                for (int q = 0; q < UP; ++q) {
+                    if (q < Fin) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) x[j] = fmaf(__shfl_sync(kFull, R.u, j * Fin + q), wk[q], x[j]);
                     }
                 }
-                xv = make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
-            }
-            const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, hs[4] = {hv.x, hv.y, hv.z, hv.w};
+            } else if (ulane) {
+                for (int q = 0; q < Fin; ++q) {
+                    const float w = WtS[q * H + ak];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float hi, lo;
-                tc::split_tf32(xs[e], hi, lo);
-                int o = koff(c4 * 4 + e, r);
-                *reinterpret_cast<float*>(A_hi + o) = hi;
-                *reinterpret_cast<float*>(A_lo + o) = lo;
-                tc::split_tf32(hs[e], hi, lo);
-                o = koff(H + c4 * 4 + e, r);
-                *reinterpret_cast<float*>(A_hi + o) = hi;
-                *reinterpret_cast<float*>(A_lo + o) = lo;
+                    for (int j = 0; j < 4; ++j) x[j] = fmaf(__shfl_sync(kFull, R.u, j * Fin + q), w, x[j]);
+                }
+            } else {
+                const long long r = prow + arg * 4;
+                for (int q = 0; q < Fin; ++q) {
+                    const float w = WtS[q * H + ak];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (r + j < rows) x[j] = fmaf(__ldg(u + (size_t)(r + j) * Fin + q), w, x[j]);
+                }
             }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.f);
+            if (R.mode != 1) {
+                const long long r = prow + arg * 4;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (r + j >= rows) x[j] = 0.f;
+            }
+            put4(sb + O_AH + oA, sb + O_AB + oA, false, x[0], x[1], x[2], x[3]);
+            put4(sb + O_AH + oA + HK, sb + O_AB + oA + HK, false, R.hp[0], R.hp[1], R.hp[2], R.hp[3]);
         }
         tc::fence_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
         tc::mbar_arrive_warp(&full[buf]);
-        ++it;
+        ++nproc;
+        prow += stride;
     };
 
     if (producer) {
-        const long long g = gridDim.x;
-        long long st = blockIdx.x;
-        issue_loads(ring[0], st);
-        while (st < nstages) {
-            issue_loads(ring[1], st + g); process(ring[0], st); st += g; if (st >= nstages) break;
-            issue_loads(ring[0], st + g); process(ring[1], st); st += g;
+        issue_loads(ring[0]);
+        issue_loads(ring[1]);
+        while (prow < rows) {
+            process(ring[0], 0); issue_loads(ring[0]); if (prow >= rows) break;
+            process(ring[1], 1); issue_loads(ring[1]);
         }
     } else if (lane == 0) {
         // ---- MMA issuer: stage descriptors differ only in their start address (low 14 bits, 16-byte units)
@@ -207,22 +273,24 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
         for (long long st = blockIdx.x; st < nstages; st += gridDim.x, ++n) {
             const int buf = n % NSTAGE, use = n / NSTAGE;
             unsigned char* sb = stage0 + (size_t)buf * STAGE;
-            unsigned char* A_hi = sb, *A_lo = sb + A_TILE, *D_hi = sb + 2 * A_TILE, *D_lo = sb + 2 * A_TILE + D_TILE;
+            if (kProbe == 1) continue;
             tc::mbar_wait(&full[buf], (uint32_t)(use & 1));
             tc::fence_after_sync();
+            if (kProbe == 2) { tc::mbar_arrive(&empty[buf]); continue; }
 #pragma unroll
             for (int s = 0; s < SR / 8; ++s) {
-                const int ko = s * 2 * LBO;                                           // 8 rows = 2 core matrices along K
-                const tc::SmemDesc ah = tc::make_desc(A_hi + ko, LBO, SBO);
-                const tc::SmemDesc al = tc::make_desc(A_lo + ko, LBO, SBO);
-                const tc::SmemDesc dh = tc::make_desc(D_hi + ko, LBO, SBO);
-                const tc::SmemDesc dl = tc::make_desc(D_lo + ko, LBO, SBO);
-                tc::mma_tf32(tmem, ah, dh, idesc, (n > 0 || s > 0) ? 1u : 0u);
-                tc::mma_tf32(tmem, ah, dl, idesc, 1u);
-                tc::mma_tf32(tmem, al, dh, idesc, 1u);
+                const int ko = s * 2 * LBO;                        // 8 rows = 2 core matrices along K (tf32) = 16 of the 32 bf16 contraction steps
+                tc::mma_tf32(tmem, tc::make_desc(sb + O_AH + ko, LBO, SBO), tc::make_desc(sb + O_DH + ko, LBO, SBO), idesc, (n > 0 || s > 0) ? 1u : 0u);
+                if (kBf16X) {
+                    tc::mma_bf16(tmem, tc::make_desc(sb + O_AB + ko, LBO, SBO), tc::make_desc(sb + O_DB + ko, LBO, SBO), idescb, 1u);
+                } else {
+                    tc::mma_tf32(tmem, tc::make_desc(sb + O_AH + ko, LBO, SBO), tc::make_desc(sb + O_DB + ko, LBO, SBO), idesc, 1u);
+                    tc::mma_tf32(tmem, tc::make_desc(sb + O_AB + ko, LBO, SBO), tc::make_desc(sb + O_DH + ko, LBO, SBO), idesc, 1u);
+                }
             }
             tc::mma_commit(&empty[buf]);
         }
+        if (kProbe == 1 || kProbe == 2) tc::mbar_arrive(done); else
         tc::mma_commit(done);
     }
     if (producer) {
@@ -246,24 +314,20 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 const int p = c0 + i, n = (p & 3) * H + (p >> 2);
-                dst[(size_t)n * H] = it > 0 ? r[i] : 0.f;
+                dst[(size_t)n * H] = nproc > 0 ? r[i] : 0.f;
             }
         }
     }
-    // ---- bias gradient: reduce the 4 row-lanes that share a float4 column
+    // ---- bias gradient: the four row groups of a gate column live in four warps -> through the (now idle) stage memory
     {
-        float4 s = dbacc;
-#pragma unroll
-        for (int o = 8; o < 32; o <<= 1) {
-            s.x += __shfl_xor_sync(kFull, s.x, o); s.y += __shfl_xor_sync(kFull, s.y, o);
-            s.z += __shfl_xor_sync(kFull, s.z, o); s.w += __shfl_xor_sync(kFull, s.w, o);
-        }
-        if (rq == 0) {
-            const int c4 = warp * 8 + cq;                  // p = c4*4 + g  ->  j = c4, n = g*64 + c4
-            const float v[4] = {s.x, s.y, s.z, s.w};
-#pragma unroll
-            for (int g = 0; g < 4; ++g) { out[off_bih + g * H + c4] = v[g]; out[off_bhh + g * H + c4] = v[g]; }
-        }
+        float* red = reinterpret_cast<float*>(stage0);                   // red[drg][256 gate columns]
+        *reinterpret_cast<float4*>(red + drg * G + dc4 * 4) = dbacc;
+        tc::named_bar_sync(1, NP);
+        const int p = tid;                                               // p = j*4 + g  ->  n = g*64 + j
+        const float v = (red[p] + red[G + p]) + (red[2 * G + p] + red[3 * G + p]);
+        const int n = (p & 3) * H + (p >> 2);
+        out[off_bih + n] = v;
+        out[off_bhh + n] = v;
     }
     }   // producer
     tc::fence_before_sync();

@@ -24,6 +24,8 @@ struct float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
 static inline float2 make_float2(float a, float b) { return float2{a, b}; }
+struct alignas(8) uint2 { unsigned x, y; };
+static inline uint2 make_uint2(unsigned a, unsigned b) { return uint2{a, b}; }
 
 typedef void* cudaStream_t;
 typedef int cudaError_t;
