@@ -443,7 +443,7 @@ def other_configs(dev, rank, world, pg, timed, steps=10, warmup=3):
     from b200rl.synth import make_rollouts
     res = {}
 
-    def run(name, eng, batches, Bn, Tn, upd):
+    def run(name, eng, batches, Bn, Tn, upd, steps=steps, warmup=warmup):
         ms = timed.run(lambda i: upd(eng, batches[i % len(batches)]), steps, warmup) / steps
         res[name] = {"ms_per_step": ms, "env_steps_per_sec": world * Bn * Tn / (ms * 1e-3), "sequences_per_gpu": Bn, "seq_len": Tn}
         del eng
@@ -463,8 +463,12 @@ def other_configs(dev, rank, world, pg, timed, steps=10, warmup=3):
     run("cfg4_vmpo_1024_per_gpu_T128", eng, bs, 1024, 128, lambda e, b: e.update(b, 0.0075))
     model = M.MlpLSTMSeperateContinuous(17, 6, 5, 64, act_dim=6).to(dev)
     eng = SACEngine(model, product_hyper(), True, process_group=pg)
+    eng_graphs = [eng.graphs]
     bs = [{k: v.to(dev) for k, v in make_rollouts(8192, 5, 17, 6, continuous=True, batch_index=rank * 100 + i, act_dim=6).items()} for i in range(2)]
-    run("cfg5_sac_continuous_8192_per_gpu_T5_obs17_act6", eng, bs, 8192, 5, lambda e, b: e.update(b))
+    # (2 input batches x 2 gradient-buffer parities: each of the 4 launch sequences runs once eagerly and is captured once
+    #  before it is replayed as a CUDA graph -- the warm-up covers that)
+    run("cfg5_sac_continuous_8192_per_gpu_T5_obs17_act6", eng, bs, 8192, 5, lambda e, b: e.update(b), steps=40, warmup=12)
+    res["cfg5_sac_continuous_8192_per_gpu_T5_obs17_act6"]["cuda_graph_replays"] = 0 if eng_graphs[0] is None else eng_graphs[0].replays
     return res
 
 

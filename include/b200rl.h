@@ -235,11 +235,18 @@ int b200rl_sac_critic_head(const float* z, const float* q1, const float* q2, con
                            int B, int T, int A, float gamma, void* stream);
 /* continuous SAC                 agents/learner_module/sac_continuous/learning.py:36-131, networks/models.py:199-231
  *   head_out (B,T,2A) = [mu | raw log-std]; eps / act / logp (B,T,A); q* (B,T,1); du* (B,T,f+A) = dLoss/d[obs|act]   */
-int b200rl_sac_cont_sample(const float* head_out, const float* eps, float* act_out, float* logp_out,
-                           int B, int T, int A, void* stream);
+/* a = tanh(mu + sd*eps), log pi(a).  eps_in given: that noise (tests); null: N(0,1) from Philox4x32-10 under
+ * rng_state = {seed, draw number, ticket} (device memory; the kernel advances the draw number, so a replayed CUDA graph
+ * draws fresh noise), saved to eps_out for the actor gradient.  act_out / act_in have row stride act_ld floats: the action
+ * is written straight into the critic's [obs | act] input (b200rl_sac_cont_pack fills the obs part of the three inputs
+ * of one update and the stored action of the third) -- no torch.cat / torch.randn on the update path.                  */
+int b200rl_sac_cont_sample(const float* head_out, const float* eps_in, float* eps_out, unsigned long long* rng_state,
+                           float* act_out, int act_ld, float* logp_out, int B, int T, int A, void* stream);
+int b200rl_sac_cont_pack(const float* obs, const float* act, float* u1, float* u2, float* u3,
+                         int B, int T, int f, int A, void* stream);
 int b200rl_sac_cont_minq_grad(const float* q1, const float* q2, float* dq1, float* dq2, double* scalars,
                               int B, int T, int A, void* stream);
-int b200rl_sac_cont_actor_grad(const float* head_out, const float* eps, const float* act_in, const float* logp,
+int b200rl_sac_cont_actor_grad(const float* head_out, const float* eps, const float* act_in, int act_ld, const float* logp,
                                const float* du1, const float* du2, const double* log_alpha,
                                float* dhead, double* scalars, int B, int T, int A, int f, void* stream);
 int b200rl_sac_cont_critic_head(const float* tq1, const float* tq2, const float* logp, const float* q1, const float* q2,

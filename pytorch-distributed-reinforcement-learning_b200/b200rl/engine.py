@@ -294,6 +294,35 @@ class VMPOEngine(OnPolicyEngine):
                 "grad-norm": float(self.grad_norm.item())}
 
 
+class _GraphCache:
+    """CUDA graphs of a launch sequence, keyed by the device addresses it reads and writes (launch-bound shapes: one SAC-
+    Continuous update is ~70 tiny kernels, ~20 us of host time each through the C-ABI).  The first call with a key runs
+    eagerly (lazy one-time setup -- workspaces, function attributes -- stays out of the capture), the second captures,
+    later ones replay.  Anything whose arguments change from step to step (the optimizer steps: bias corrections, peer
+    epochs) is launched outside.  `limit` bounds the number of graphs; further keys run eagerly."""
+
+    def __init__(self, limit=12):
+        self.graphs, self.seen, self.limit = {}, set(), limit
+        self.replays = 0
+
+    def run(self, key, fn):
+        g = self.graphs.get(key)
+        if g is not None:
+            g.replay()
+            self.replays += 1
+            return
+        if key not in self.seen or len(self.graphs) >= self.limit:
+            self.seen.add(key)
+            fn()
+            return
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            fn()
+        self.graphs[key] = g
+        g.replay()
+        self.replays += 1
+
+
 class SACEngine:
     """SAC / SAC-Continuous update (reference `sac/learning.py:36-143`,
     `sac_continuous/learning.py:36-131`, optimizers `learner.py:351-367`): actor step, temperature
@@ -342,6 +371,13 @@ class SACEngine:
         self.wgrad_variant = int(os.environ.get("B200RL_WGRAD_VARIANT", "1"))
         self.debug = None
         self.noise_fn = None          # SAC-Continuous: callable (B, T, A) -> (eps1, eps2) replacing the two N(0,1) draws (tests)
+        # Philox state of the in-kernel N(0,1) draws: {seed, draw number, ticket}; every rank draws its own stream
+        seed = (int(torch.initial_seed()) + 0x9E3779B97F4A7C15 * (1 + (0 if self.comm is None else self.comm.rank))) & 0x7FFFFFFFFFFFFFFF
+        self.rng = torch.tensor([seed, 0, 0, 0], dtype=torch.int64, device=dev)
+        # CUDA graphs of the two launch-bound phases (B200RL_GRAPH=1 forces them on, 0 off; default: on for small batches)
+        self.graph_mode = os.environ.get("B200RL_GRAPH", "auto")
+        loopback = type(self.comm).__name__ == "_LoopbackComm"      # (test harness: ranks are threads of one process -- no concurrent captures)
+        self.graphs = _GraphCache(limit=16) if (dev.type == "cuda" and self.graph_mode != "0" and not loopback) else None
 
     @property
     def log_alpha(self):
@@ -366,7 +402,8 @@ class SACEngine:
         self.td = torch.empty(B, T - 1, device=dev)
         if self.cont:
             Fq = self.Lq.Fin
-            self.a_pol = torch.empty(B, T, Ad, device=dev)
+            self.ub = [torch.empty(B, T, Fq, device=dev) for _ in range(3)]     # [obs | action]: policy action (actor phase), fresh policy action, stored action
+            self.eps = torch.empty(B, T, Ad, device=dev)
             self.logp = torch.empty(B, T, Ad, device=dev)
             self.du = [torch.empty(B, T, Fq, device=dev) for _ in range(2)]
             self.scratch = torch.zeros(self.nparts, self.Lq.P, device=dev)
@@ -383,6 +420,8 @@ class SACEngine:
         if grad is not None:
             self.ops.reduce_partials(partials, grad)
 
+    GRAPH_MAX_ROWS = 1 << 16          # B200RL_GRAPH=auto: phases of batches up to this many transitions run as CUDA graphs
+
     def update(self, batch, noise=None):
         ops, hp, lib = self.ops, self.hp, self.ops.lib
         from .native import ptr
@@ -393,7 +432,7 @@ class SACEngine:
         Ad = act.shape[-1] if self.cont else self.La.NH
         self._ws(B, T, Ad)
         ops._chk(act, batch["rew"], batch["is_fir"], batch["hx"], batch["cx"])
-        st = ops._stream(self.device)
+        st_of = lambda: ops._stream(self.device)          # (inside a capture the current stream is the capture stream)
         hx, cx = batch["hx"], batch["cx"]
         uo = obs.reshape(B, T, -1)
         La, Lq, Pq = self.La, self.Lq, self.Lq.P
@@ -403,62 +442,79 @@ class SACEngine:
         # gradient / loss-sum buffers of this update: the peer channels' (read by the other ranks over NVLink) or local ones
         ga, sA = self.chan_a.begin() if self.chan_a is not None else (self.ga, self.scalars)
         gq, sQ = self.chan_q.begin() if self.chan_q is not None else (self.gq, self.scalars)
-        sA.zero_()
-        if sQ is not sA:
-            sQ.zero_()
-
-        if not self.cont:
-            A = La.NH
-            self._net_fwd(La, self.fa, 0, uo, hx, cx, self.wsa, self.hoa)
-            for i in range(2):
-                self._net_fwd(Lq, self.fq, i * Pq, uo, hx, cx, self.wsq[i], self.Q[i])
-            lib.call("b200rl_sac_actor_head", ptr(self.hoa), ptr(self.Q[0]), ptr(self.Q[1]), ptr(self.alpha_state),
-                     ptr(self.dhoa), ptr(sA), B, T, A, st)
-            self._net_bwd(La, self.fa, 0, uo, hx, cx, self.wsa, self.dhoa, self.pa, ga)
-            sc = self._actor_step(ga, sA, mg, lr, st)
-            lib.call("b200rl_sac_alpha_step", ptr(self.alpha_state), ptr(sc), ptr(self.alpha_out), N * self.world, float(A), lr, self.step, st)
-            self._net_fwd(La, self.fa, 0, uo, hx, cx, self.wsa, self.hoa)            # updated actor
-            if self.separate_target:
-                for i in range(2):
-                    self._net_fwd(Lq, self.ftq, i * Pq, uo, hx, cx, self.wsa, self.TQ[i])
-            lib.call("b200rl_sac_critic_head", ptr(self.hoa), ptr(self.Q[0]), ptr(self.Q[1]), ptr(self.TQ[0]), ptr(self.TQ[1]),
-                     ptr(act), ptr(batch["rew"]), ptr(batch["is_fir"]), ptr(self.alpha_state), ptr(self.dQ[0]), ptr(self.dQ[1]),
-                     ptr(self.td), ptr(sQ), B, T, A, hp["gamma"], st)
-            for i in range(2):
-                self._net_bwd(Lq, self.fq, i * Pq, uo, hx, cx, self.wsq[i], self.dQ[i], self.pq[i], gq[i * Pq:(i + 1) * Pq])
-            pol_den = N
-        else:
-            A = Ad
+        A = Ad
+        eps1 = eps2 = None
+        if self.cont:
             if noise is None and self.noise_fn is not None:
                 noise = self.noise_fn(B, T, A)
-            eps1, eps2 = noise if noise is not None else (torch.randn(B, T, A, device=self.device), torch.randn(B, T, A, device=self.device))
-            self._net_fwd(La, self.fa, 0, uo, hx, cx, self.wsa, self.hoa)
-            lib.call("b200rl_sac_cont_sample", ptr(self.hoa), ptr(eps1), ptr(self.a_pol), ptr(self.logp), B, T, A, st)
-            u1 = torch.cat([uo, self.a_pol], -1)
-            for i in range(2):
-                self._net_fwd(Lq, self.fq, i * Pq, u1, hx, cx, self.wsq[i], self.Q[i])
-            lib.call("b200rl_sac_cont_minq_grad", ptr(self.Q[0]), ptr(self.Q[1]), ptr(self.dQ[0]), ptr(self.dQ[1]), ptr(sA), B, T, A, st)
-            for i in range(2):                                                          # dQ/da: critic backward to its input only
-                self._net_bwd(Lq, self.fq, i * Pq, u1, hx, cx, self.wsq[i], self.dQ[i], self.scratch, None, du=self.du[i])
-            lib.call("b200rl_sac_cont_actor_grad", ptr(self.hoa), ptr(eps1), ptr(self.a_pol), ptr(self.logp), ptr(self.du[0]), ptr(self.du[1]),
-                     ptr(self.alpha_state), ptr(self.dhoa), ptr(sA), B, T, A, f, st)
+            if noise is not None:
+                eps1, eps2 = noise
+                ops._chk(eps1, eps2)
+            Fq = f + A
+            ua = [ptr(u) + 4 * f for u in self.ub]        # where the action columns of the three critic inputs start
+
+        def actor_phase():
+            st = st_of()
+            sA.zero_()
+            if sQ is not sA:
+                sQ.zero_()
+            if not self.cont:
+                self._net_fwd(La, self.fa, 0, uo, hx, cx, self.wsa, self.hoa)
+                for i in range(2):
+                    self._net_fwd(Lq, self.fq, i * Pq, uo, hx, cx, self.wsq[i], self.Q[i])
+                lib.call("b200rl_sac_actor_head", ptr(self.hoa), ptr(self.Q[0]), ptr(self.Q[1]), ptr(self.alpha_state),
+                         ptr(self.dhoa), ptr(sA), B, T, A, st)
+            else:
+                lib.call("b200rl_sac_cont_pack", ptr(uo), ptr(act), ptr(self.ub[0]), ptr(self.ub[1]), ptr(self.ub[2]), B, T, f, A, st)
+                self._net_fwd(La, self.fa, 0, uo, hx, cx, self.wsa, self.hoa)
+                lib.call("b200rl_sac_cont_sample", ptr(self.hoa), ptr(eps1), ptr(self.eps), ptr(self.rng), ua[0], Fq, ptr(self.logp), B, T, A, st)
+                for i in range(2):
+                    self._net_fwd(Lq, self.fq, i * Pq, self.ub[0], hx, cx, self.wsq[i], self.Q[i])
+                lib.call("b200rl_sac_cont_minq_grad", ptr(self.Q[0]), ptr(self.Q[1]), ptr(self.dQ[0]), ptr(self.dQ[1]), ptr(sA), B, T, A, st)
+                for i in range(2):                                                      # dQ/da: critic backward to its input only
+                    self._net_bwd(Lq, self.fq, i * Pq, self.ub[0], hx, cx, self.wsq[i], self.dQ[i], self.scratch, None, du=self.du[i])
+                lib.call("b200rl_sac_cont_actor_grad", ptr(self.hoa), ptr(eps1 if eps1 is not None else self.eps), ua[0], Fq, ptr(self.logp),
+                         ptr(self.du[0]), ptr(self.du[1]), ptr(self.alpha_state), ptr(self.dhoa), ptr(sA), B, T, A, f, st)
             self._net_bwd(La, self.fa, 0, uo, hx, cx, self.wsa, self.dhoa, self.pa, ga)
-            sc = self._actor_step(ga, sA, mg, lr, st)
-            lib.call("b200rl_sac_alpha_step", ptr(self.alpha_state), ptr(sc), ptr(self.alpha_out), N * A * self.world, float(A), lr, self.step, st)
-            self._net_fwd(La, self.fa, 0, uo, hx, cx, self.wsa, self.hoa)            # updated actor, fresh noise
-            lib.call("b200rl_sac_cont_sample", ptr(self.hoa), ptr(eps2), ptr(self.a_pol), ptr(self.logp), B, T, A, st)
-            u2 = torch.cat([uo, self.a_pol], -1)
+
+        def critic_phase():
+            st = st_of()
+            self._net_fwd(La, self.fa, 0, uo, hx, cx, self.wsa, self.hoa)            # updated actor (continuous: fresh noise)
+            if not self.cont:
+                if self.separate_target:
+                    for i in range(2):
+                        self._net_fwd(Lq, self.ftq, i * Pq, uo, hx, cx, self.wsa, self.TQ[i])
+                lib.call("b200rl_sac_critic_head", ptr(self.hoa), ptr(self.Q[0]), ptr(self.Q[1]), ptr(self.TQ[0]), ptr(self.TQ[1]),
+                         ptr(act), ptr(batch["rew"]), ptr(batch["is_fir"]), ptr(self.alpha_state), ptr(self.dQ[0]), ptr(self.dQ[1]),
+                         ptr(self.td), ptr(sQ), B, T, A, hp["gamma"], st)
+                uq = uo
+            else:
+                lib.call("b200rl_sac_cont_sample", ptr(self.hoa), ptr(eps2), None, ptr(self.rng), ua[1], Fq, ptr(self.logp), B, T, A, st)
+                for i in range(2):
+                    self._net_fwd(Lq, self.ftq, i * Pq, self.ub[1], hx, cx, self.wsq[i], self.TQ[i])
+                for i in range(2):
+                    self._net_fwd(Lq, self.fq, i * Pq, self.ub[2], hx, cx, self.wsq[i], self.Q[i])
+                lib.call("b200rl_sac_cont_critic_head", ptr(self.TQ[0]), ptr(self.TQ[1]), ptr(self.logp), ptr(self.Q[0]), ptr(self.Q[1]),
+                         ptr(batch["rew"]), ptr(batch["is_fir"]), ptr(self.alpha_state), ptr(self.dQ[0]), ptr(self.dQ[1]), ptr(self.td),
+                         ptr(sQ), B, T, A, hp["gamma"], st)
+                uq = self.ub[2]
             for i in range(2):
-                self._net_fwd(Lq, self.ftq, i * Pq, u2, hx, cx, self.wsq[i], self.TQ[i])
-            u3 = torch.cat([uo, act], -1)
-            for i in range(2):
-                self._net_fwd(Lq, self.fq, i * Pq, u3, hx, cx, self.wsq[i], self.Q[i])
-            lib.call("b200rl_sac_cont_critic_head", ptr(self.TQ[0]), ptr(self.TQ[1]), ptr(self.logp), ptr(self.Q[0]), ptr(self.Q[1]),
-                     ptr(batch["rew"]), ptr(batch["is_fir"]), ptr(self.alpha_state), ptr(self.dQ[0]), ptr(self.dQ[1]), ptr(self.td),
-                     ptr(sQ), B, T, A, hp["gamma"], st)
-            for i in range(2):
-                self._net_bwd(Lq, self.fq, i * Pq, u3, hx, cx, self.wsq[i], self.dQ[i], self.pq[i], gq[i * Pq:(i + 1) * Pq])
-            pol_den = N * A
+                self._net_bwd(Lq, self.fq, i * Pq, uq, hx, cx, self.wsq[i], self.dQ[i], self.pq[i], gq[i * Pq:(i + 1) * Pq])
+
+        use_graph = self.graphs is not None and (self.graph_mode == "1" or B * T <= self.GRAPH_MAX_ROWS)
+        if use_graph:
+            key = tuple(t.data_ptr() for t in (obs, act, batch["rew"], batch["is_fir"], hx, cx, ga, sA, gq, sQ)) + \
+                (B, T, 0 if eps1 is None else eps1.data_ptr(), 0 if eps2 is None else eps2.data_ptr())
+            run = lambda tag, fn: self.graphs.run((tag,) + key, fn)
+        else:
+            run = lambda tag, fn: fn()
+
+        st = st_of()
+        run("actor", actor_phase)
+        sc = self._actor_step(ga, sA, mg, lr, st)
+        pol_den = N * A if self.cont else N
+        lib.call("b200rl_sac_alpha_step", ptr(self.alpha_state), ptr(sc), ptr(self.alpha_out), pol_den * self.world, float(A), lr, self.step, st)
+        run("critic", critic_phase)
         # twin-critic step: exchange #2 + joint clip + Adam
         if self.chan_q is not None:
             self.chan_q.step(1, self.fq, self.mq, self.vq, self.qmask, self.gq, self.sc_q, self.norm_q, 1.0 / self.world, mg, lr,

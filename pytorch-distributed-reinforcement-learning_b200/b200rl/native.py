@@ -55,9 +55,10 @@ SIGNATURES = {
                         + [_F] * 6 + [_I, _P],
     "b200rl_sac_actor_head": [_P] * 6 + [_I, _I, _I, _P],
     "b200rl_sac_critic_head": [_P] * 13 + [_I, _I, _I, _F, _P],
-    "b200rl_sac_cont_sample": [_P] * 4 + [_I, _I, _I, _P],
+    "b200rl_sac_cont_sample": [_P] * 5 + [_I, _P, _I, _I, _I, _P],
+    "b200rl_sac_cont_pack": [_P] * 5 + [_I, _I, _I, _I, _P],
     "b200rl_sac_cont_minq_grad": [_P] * 5 + [_I, _I, _I, _P],
-    "b200rl_sac_cont_actor_grad": [_P] * 9 + [_I, _I, _I, _I, _P],
+    "b200rl_sac_cont_actor_grad": [_P] * 3 + [_I] + [_P] * 6 + [_I, _I, _I, _I, _P],
     "b200rl_sac_cont_critic_head": [_P] * 12 + [_I, _I, _I, _F, _P],
     "b200rl_sac_alpha_step": [_P, _P, _P, C.c_double, C.c_double, C.c_double, _I, _P],
 }

@@ -111,20 +111,71 @@ sac_critic_head_kernel(const float* __restrict__ z, const float* __restrict__ q1
 }
 
 // ----------------------------------------------------------------------- continuous SAC
+// Philox4x32-10 (Salmon et al., SC'11): counter-based, so element i of draw n is a pure function of (seed, n, i) -- no
+// generator state per thread, reproducible for any grid, and safe to replay from a CUDA graph (the draw number lives in
+// device memory).  Replaces the two `torch.randn` of `dist.rsample()` (networks/models.py:213, sac_continuous/learning.py:47,68).
+__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0, p1 = (unsigned long long)0xCD9E8D57u * c2;
+        const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0, n1 = (unsigned)p1, n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1, n3 = (unsigned)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// one N(0,1) per element (Box-Muller on two of the four words)
+__device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned long long draw, unsigned long long i) {
+    unsigned r[4];
+    philox4x32_10((unsigned)i, (unsigned)(i >> 32), (unsigned)draw, (unsigned)(draw >> 32), (unsigned)seed, (unsigned)(seed >> 32), r);
+    const float u0 = ((float)(r[0] >> 8) + 0.5f) * (1.f / 16777216.f);          // (0, 1)
+    const float u1 = ((float)(r[1] >> 8) + 0.5f) * (1.f / 16777216.f);
+    return sqrtf(-2.f * logf(u0)) * cosf(6.283185307179586f * u1);
+}
+
+// a = tanh(mu + sd * eps), log pi(a) ; `eps_in` given: the reference's arithmetic on injected noise (parity tests); null: noise of
+// draw number rng[1] under seed rng[0], written to `eps_out` for the actor gradient, and the LAST CTA to finish advances rng[1]
+// (rng[2] is its ticket counter).  `a_out` has row stride `a_ld` floats: the action lands directly in the critic's [obs | act] input.
 __global__ void __launch_bounds__(256)
-sac_cont_sample_kernel(const float* __restrict__ ho, const float* __restrict__ eps, float* __restrict__ a_out,
+sac_cont_sample_kernel(const float* __restrict__ ho, const float* __restrict__ eps_in, float* __restrict__ eps_out,
+                       unsigned long long* __restrict__ rng, float* __restrict__ a_out, int a_ld,
                        float* __restrict__ logp_out, long long rows, int A) {
+    unsigned long long seed = 0, draw = 0;
+    if (eps_in == nullptr) { seed = rng[0]; draw = rng[1]; }
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows * A; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / A; const int d = (int)(i % A);
         const float mu = __ldg(ho + r * 2 * A + d);
         const float ls = fminf(fmaxf(__ldg(ho + r * 2 * A + A + d), -20.f), 2.f);
         const float sd = expf(ls);
-        const float x = mu + sd * __ldg(eps + i);
+        float e;
+        if (eps_in != nullptr) e = __ldg(eps_in + i);
+        else { e = philox_normal(seed, draw, (unsigned long long)i); if (eps_out != nullptr) eps_out[i] = e; }
+        const float x = mu + sd * e;
         const float a = tanhf(x);
         const float df = x - mu;
         float lp = -(df * df) / (2.f * sd * sd) - logf(sd) - kLogSqrt2Pi;
         lp -= logf(1.f - a * a + 1e-7f);
-        a_out[i] = a; logp_out[i] = lp;
+        a_out[r * a_ld + d] = a; logp_out[i] = lp;
+    }
+    if (eps_in == nullptr) {
+        __syncthreads();                                      // every thread of the CTA has read rng[1]
+        if (threadIdx.x == 0) {
+            __threadfence();
+            unsigned* ticket = reinterpret_cast<unsigned*>(rng + 2);
+            if (atomicAdd(ticket, 1u) == gridDim.x - 1) { *ticket = 0u; rng[1] = draw + 1; __threadfence(); }
+        }
+    }
+}
+
+// the three [obs | action] inputs of the critics in one pass: u1 = [obs | .], u2 = [obs | .] (actions written by the two samples), u3 = [obs | act]
+__global__ void __launch_bounds__(256)
+sac_cont_pack_kernel(const float* __restrict__ obs, const float* __restrict__ act, float* __restrict__ u1, float* __restrict__ u2,
+                     float* __restrict__ u3, long long rows, int f, int A) {
+    const int Fin = f + A;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows * Fin; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / Fin; const int c = (int)(i % Fin);
+        if (c < f) { const float v = __ldg(obs + r * f + c); u1[i] = v; u2[i] = v; u3[i] = v; }
+        else u3[i] = __ldg(act + r * A + (c - f));
     }
 }
 
@@ -145,7 +196,7 @@ sac_cont_minq_grad_kernel(const float* __restrict__ q1, const float* __restrict_
 }
 
 __global__ void __launch_bounds__(256)
-sac_cont_actor_grad_kernel(const float* __restrict__ ho, const float* __restrict__ eps, const float* __restrict__ a_in,
+sac_cont_actor_grad_kernel(const float* __restrict__ ho, const float* __restrict__ eps, const float* __restrict__ a_in, int a_ld,
                            const float* __restrict__ logp, const float* __restrict__ du1, const float* __restrict__ du2,
                            const double* __restrict__ log_alpha, float* __restrict__ dho, double* __restrict__ scalars,
                            long long rows, int T, int A, int f, float invNA) {
@@ -160,7 +211,7 @@ sac_cont_actor_grad_kernel(const float* __restrict__ ho, const float* __restrict
             const float raw = __ldg(ho + r * 2 * A + A + d);
             const float ls = fminf(fmaxf(raw, -20.f), 2.f);
             const float sd = expf(ls);
-            const float a = __ldg(a_in + i), lp = __ldg(logp + i);
+            const float a = __ldg(a_in + r * a_ld + d), lp = __ldg(logp + i);
             const float da = __ldg(du1 + r * Fin + f + d) + __ldg(du2 + r * Fin + f + d);     // dL/da through the twin critics
             const float cl = alpha * invNA;                                                    // dL/dlogp_d
             const float om = 1.f - a * a;
@@ -246,12 +297,22 @@ extern "C" int b200rl_sac_critic_head(const float* z, const float* q1, const flo
     return check_launch("sac_critic_head");
 }
 
-extern "C" int b200rl_sac_cont_sample(const float* head_out, const float* eps, float* act_out, float* logp_out,
-                                      int B, int T, int A, void* stream) {
+extern "C" int b200rl_sac_cont_sample(const float* head_out, const float* eps_in, float* eps_out, unsigned long long* rng_state,
+                                      float* act_out, int act_ld, float* logp_out, int B, int T, int A, void* stream) {
     B200RL_REQUIRE(B >= 1 && T >= 1 && A >= 1 && A <= MAXA, "sac_cont_sample: bad shape");
+    B200RL_REQUIRE(eps_in != nullptr || rng_state != nullptr, "sac_cont_sample: neither noise nor a generator state given");
+    B200RL_REQUIRE(act_ld >= A, "sac_cont_sample: act_ld=%d < A=%d", act_ld, A);
     const long long rows = (long long)B * T;
-    B200RL_LAUNCH(sac_cont_sample_kernel, ew_grid(rows * A), 256, 0, stream, head_out, eps, act_out, logp_out, rows, A);
+    B200RL_LAUNCH(sac_cont_sample_kernel, ew_grid(rows * A), 256, 0, stream, head_out, eps_in, eps_out, rng_state, act_out, act_ld, logp_out, rows, A);
     return check_launch("sac_cont_sample");
+}
+
+extern "C" int b200rl_sac_cont_pack(const float* obs, const float* act, float* u1, float* u2, float* u3,
+                                    int B, int T, int f, int A, void* stream) {
+    B200RL_REQUIRE(B >= 1 && T >= 1 && f >= 1 && A >= 1, "sac_cont_pack: bad shape");
+    const long long rows = (long long)B * T;
+    B200RL_LAUNCH(sac_cont_pack_kernel, ew_grid(rows * (f + A)), 256, 0, stream, obs, act, u1, u2, u3, rows, f, A);
+    return check_launch("sac_cont_pack");
 }
 
 extern "C" int b200rl_sac_cont_minq_grad(const float* q1, const float* q2, float* dq1, float* dq2, double* scalars,
@@ -263,12 +324,12 @@ extern "C" int b200rl_sac_cont_minq_grad(const float* q1, const float* q2, float
     return check_launch("sac_cont_minq_grad");
 }
 
-extern "C" int b200rl_sac_cont_actor_grad(const float* head_out, const float* eps, const float* act_in, const float* logp,
+extern "C" int b200rl_sac_cont_actor_grad(const float* head_out, const float* eps, const float* act_in, int act_ld, const float* logp,
                                           const float* du1, const float* du2, const double* log_alpha,
                                           float* dhead, double* scalars, int B, int T, int A, int f, void* stream) {
     B200RL_REQUIRE(B >= 1 && T >= 2 && A >= 1 && A <= MAXA, "sac_cont_actor_grad: bad shape");
     const long long rows = (long long)B * T;
-    B200RL_LAUNCH(sac_cont_actor_grad_kernel, ew_grid(rows * A), 256, 0, stream, head_out, eps, act_in, logp, du1, du2, log_alpha,
+    B200RL_LAUNCH(sac_cont_actor_grad_kernel, ew_grid(rows * A), 256, 0, stream, head_out, eps, act_in, act_ld, logp, du1, du2, log_alpha,
                   dhead, scalars, rows, T, A, f, (float)(1.0 / ((double)B * (T - 1) * A)));
     return check_launch("sac_cont_actor_grad");
 }

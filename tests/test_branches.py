@@ -606,3 +606,86 @@ def test_native_assembler_queue_mode_and_learner_round_trip(backend, tmp_path):
     for k in ("obs", "logits", "hx"):
         np.testing.assert_array_equal(out[k].numpy(), np.stack([s[k].numpy() for s in steps]))
     assert out["obs"].shape == (T, f) and out["act"].shape == (T, 1)
+
+
+# ---------------------------------------------------------------- SAC-Continuous: in-kernel noise, packed critic inputs, CUDA graphs
+def _philox_normal_ref(seed, draw, n):
+    """Philox4x32-10 + Box-Muller exactly as csrc/sac_kernels.cu states it (numpy, 64-bit integer arithmetic)."""
+    i = np.arange(n, dtype=np.uint64)
+    c = [i & np.uint64(0xFFFFFFFF), i >> np.uint64(32), np.full(n, draw & 0xFFFFFFFF, np.uint64), np.full(n, draw >> 32, np.uint64)]
+    k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64(seed >> 32)
+    M0, M1, m32 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [(p1 >> np.uint64(32)) ^ c[1] ^ k0, p1 & m32, (p0 >> np.uint64(32)) ^ c[3] ^ k1, p0 & m32]
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & m32, (k1 + np.uint64(0xBB67AE85)) & m32
+    u0 = ((c[0] >> np.uint64(8)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
+    u1 = ((c[1] >> np.uint64(8)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
+    return np.sqrt(np.float32(-2.0) * np.log(u0)) * np.cos(np.float32(6.283185307179586) * u1)
+
+
+def test_sac_continuous_in_kernel_noise_and_pack(backend):
+    """b200rl_sac_cont_sample without injected noise draws N(0,1) from Philox4x32-10 (checked against a numpy restatement of the
+    generator), advances the device-side draw counter once per launch, and writes the action into the strided [obs | act]
+    buffer that b200rl_sac_cont_pack prepared (replacing torch.randn / torch.cat of sac_continuous/learning.py:47-72)."""
+    from b200rl.native import ptr
+    ops, dev = backend
+    lib = ops.lib
+    B, T, f, A = 24, 5, 7, 3
+    g = torch.Generator().manual_seed(3)
+    obs, act = torch.randn(B, T, f, generator=g).to(dev), torch.rand(B, T, A, generator=g).to(dev)
+    ho = (0.3 * torch.randn(B, T, 2 * A, generator=g)).to(dev)
+    ub = [torch.full((B, T, f + A), float("nan"), device=dev) for _ in range(3)]
+    st = ops._stream(dev)
+    lib.call("b200rl_sac_cont_pack", ptr(obs), ptr(act), ptr(ub[0]), ptr(ub[1]), ptr(ub[2]), B, T, f, A, st)
+    for k in range(3):
+        assert torch.equal(ub[k][..., :f], obs)
+    assert torch.equal(ub[2][..., f:], act) and torch.isnan(ub[0][..., f:]).all()
+    seed = 0x1234567887654321
+    rng = torch.tensor([seed, 5, 0, 0], dtype=torch.int64, device=dev)
+    eps = [torch.empty(B, T, A, device=dev) for _ in range(2)]
+    logp = torch.empty(B, T, A, device=dev)
+    for k in range(2):
+        lib.call("b200rl_sac_cont_sample", ptr(ho), None, ptr(eps[k]), ptr(rng), ptr(ub[k]) + 4 * f, f + A, ptr(logp), B, T, A, st)
+    assert rng.cpu().tolist() == [seed, 7, 0, 0]
+    for k in range(2):
+        ref = _philox_normal_ref(seed, 5 + k, B * T * A).reshape(B, T, A)
+        np.testing.assert_allclose(eps[k].cpu().numpy(), ref, rtol=2e-5, atol=2e-6)
+        mu, sd = ho[..., :A], ho[..., A:].clamp(-20, 2).exp()
+        np.testing.assert_allclose(ub[k][..., f:].cpu().numpy(), torch.tanh(mu + sd * eps[k]).cpu().numpy(), rtol=1e-5, atol=1e-6)
+        assert torch.equal(ub[k][..., :f], obs)
+    # with injected noise the generator state is untouched
+    lib.call("b200rl_sac_cont_sample", ptr(ho), ptr(eps[0]), None, None, ptr(ub[1]) + 4 * f, f + A, ptr(logp), B, T, A, st)
+    assert torch.equal(ub[1][..., f:], ub[0][..., f:]) and rng.cpu().tolist() == [seed, 7, 0, 0]
+    # statistics of a larger draw
+    n = 1 << 16
+    z = _philox_normal_ref(seed, 99, n)
+    assert abs(z.mean()) < 0.02 and abs(z.std() - 1) < 0.02 and abs(np.corrcoef(z[:-1], z[1:])[0, 1]) < 0.02
+
+
+@pytest.mark.gpu
+def test_sac_phases_as_cuda_graphs_equal_eager(monkeypatch):
+    """The two launch-bound phases of a SAC(-Continuous) update replayed from CUDA graphs give bit-identical parameters to the
+    eager launches (same kernels, same order), including fresh in-kernel noise per replay (the draw counter lives on the device)."""
+    from b200rl.engine import SACEngine
+    from b200rl.networks import models as M
+    from b200rl.synth import make_rollouts
+    dev = torch.device("cuda:0")
+    for cont, (B, T, f, A) in ((True, (64, 5, 17, 6)), (False, (32, 6, 4, 2))):
+        res = {}
+        for mode in ("0", "1"):
+            monkeypatch.setenv("B200RL_GRAPH", mode)
+            torch.manual_seed(4)
+            model = ((M.MlpLSTMSeperateContinuous(f, A, T, 64, act_dim=A)) if cont else M.MlpLSTMSeperate(f, A, T, 64)).to(dev)
+            eng = SACEngine(model, oracle.DEFAULT_HYPER, cont)
+            batch = {k: v.to(dev) for k, v in make_rollouts(B, T, f, A, continuous=cont, act_dim=A if cont else 1).items()}
+            for _ in range(5):
+                eng.update(batch)
+            L = eng.losses()
+            res[mode] = (torch.cat([v.reshape(-1) for v in model.actor.state_dict().values()]).cpu(),
+                         torch.cat([v.reshape(-1) for v in model.critic.state_dict().values()]).cpu(), L,
+                         eng.rng.cpu().tolist(), 0 if eng.graphs is None else eng.graphs.replays)
+        assert res["0"][4] == 0 and res["1"][4] >= 4, (res["0"][4], res["1"][4])
+        assert torch.equal(res["0"][0], res["1"][0]) and torch.equal(res["0"][1], res["1"][1])
+        assert res["0"][2] == res["1"][2]
+        assert res["0"][3] == res["1"][3] and res["0"][3][1] == (10 if cont else 0)
