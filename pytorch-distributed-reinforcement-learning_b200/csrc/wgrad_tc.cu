@@ -66,13 +66,14 @@ constexpr int D_TILE = (G / 8) * SBO;           // 16896
 constexpr int O_AH = 0, O_DH = A_TILE, O_AB = O_DH + D_TILE, O_DB = O_AB + A_TILE;   // A_hi | D_hi (tf32) | A' | D' (bf16)
 constexpr int STAGE = O_DB + D_TILE;            // 50688 B
 constexpr int MAXF = 32;
+constexpr int UP = 4;                           // torso widths up to UP: weight column in registers, inputs by shuffle; wider: inputs staged in shared memory
 static_assert((SR / 4 - 1) * LBO + 128 <= SBO, "core matrices of one mn-group must fit below SBO");
 static_assert(STAGE % 16 == 0 && O_DH % 16 == 0 && O_AB % 16 == 0 && O_DB % 16 == 0, "descriptor alignment");
 __device__ __forceinline__ int koff(int mn, int r) { return (mn & 7) * 16 + (mn >> 3) * SBO + (r & 3) * 4 + (r >> 2) * LBO; }
 }  // namespace wtc
 
 static inline size_t wgrad_tc_smem_bytes(int Fin) {
-    return wtc::NSTAGE * (size_t)wtc::STAGE + sizeof(float) * (size_t)(Fin * wtc::H + wtc::H) + 96;
+    return wtc::NSTAGE * (size_t)wtc::STAGE + sizeof(float) * (size_t)(Fin * wtc::H + wtc::H + (Fin > wtc::UP ? 2 * wtc::SR * Fin : 0)) + 96;
 }
 
 __global__ void __launch_bounds__(wtc::NT, 2)
@@ -86,7 +87,8 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
     unsigned char* stage0 = smem;                                   // 1024-aligned by construction (offset 0)
     float* WtS = reinterpret_cast<float*>(smem + NSTAGE * STAGE);   // WtS[q*64 + j]
     float* bts = WtS + Fin * H;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(bts + H);          // full[NSTAGE] | empty[NSTAGE] | done
+    float* usm = bts + H;                                           // Fin > UP: the stage's 16 x Fin torso inputs, double-buffered
+    uint64_t* bars = reinterpret_cast<uint64_t*>(usm + (Fin > UP ? 2 * SR * Fin : 0));   // full[NSTAGE] | empty[NSTAGE] | done
     uint64_t* full = bars, *empty = bars + NSTAGE, *done = bars + 2 * NSTAGE;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 1);
 
@@ -113,18 +115,19 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
     const long long rows = (long long)B * T;
     const long long nstages = (rows + SR - 1) / SR;
     float4 dbacc = make_float4(0.f, 0.f, 0.f, 0.f);               // bias gradient of gate columns dc4*4 .. +3 over this thread's rows
-    const bool ulane = 4 * Fin <= 32;                              // the 4 x Fin torso inputs of a row group: one per lane
+    const bool ulane = Fin <= UP;                                  // the 4 x Fin torso inputs of a row group: one per lane
+    const int nu = SR * Fin;                                       // wider torsos: the stage's 16 x Fin inputs, up to two per thread
 
     // Register-staged loads: two register sets, both in flight except while their own stage is processed (a set is refilled,
     // two stages ahead, as soon as it has been written to shared memory).  The common case -- a stage with all 16 rows in
     // range and no sequence start among them -- runs without a single bounds check or row/time division: three running
     // pointers, immediate offsets.  `mode`: 0 nothing, 1 fast, 2 generic.
-    struct StageRegs { float4 d[4]; float hp[4]; float u; int mode; };
+    struct StageRegs { float4 d[4]; float hp[4]; float u, u2; int mode; };
     StageRegs ring[2];
     const long long stride = (long long)gridDim.x * SR;            // rows between two stages of this CTA
     const float* dptr = dpre + ((size_t)blockIdx.x * SR + drg * 4) * G + dc4 * 4;
     const float* hptr = h + ((long long)blockIdx.x * SR + arg * 4 - 1) * H + ak;
-    const float* uptr = u + ((size_t)blockIdx.x * SR + arg * 4) * Fin + lane;
+    const float* uptr = ulane ? u + ((size_t)blockIdx.x * SR + arg * 4) * Fin + lane : u + (size_t)blockIdx.x * SR * Fin + tid;
     const unsigned tstep = (unsigned)(stride % T);
     unsigned tpos = (unsigned)(((long long)blockIdx.x * SR) % T);  // time index of the stage's first row
     long long lrow = (long long)blockIdx.x * SR;                   // first row of the next stage to load
@@ -137,13 +140,14 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
         if (kProbe == 3) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) { R.d[j] = make_float4(1.f, 2.f, 3.f, 4.f); R.hp[j] = 1.f; }
-            R.u = 1.f;
+            R.u = R.u2 = 1.f;
         } else if (R.mode == 1) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) R.d[j] = *reinterpret_cast<const float4*>(dptr + j * G);
 #pragma unroll
             for (int j = 0; j < 4; ++j) R.hp[j] = __ldg(hptr + j * H);
-            R.u = (ulane && lane < 4 * Fin) ? __ldg(uptr) : 0.f;
+            if (ulane) R.u = lane < 4 * Fin ? __ldg(uptr) : 0.f;
+            else { R.u = tid < nu ? __ldg(uptr) : 0.f; R.u2 = tid + NP < nu ? __ldg(uptr + NP) : 0.f; }
         } else {
             const long long r = row0 + drg * 4;
 #pragma unroll
@@ -160,8 +164,12 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
                 if (live && ra + j < rows) R.hp[j] = (t == 0) ? __ldg(hx0 + (size_t)b * H + ak) : __ldg(hptr + j * H);
                 if (++t == (unsigned)T) { t = 0; ++b; }
             }
-            R.u = 0.f;
-            if (ulane && live && lane < 4 * Fin && ra * Fin + lane < rows * Fin) R.u = __ldg(uptr);
+            R.u = R.u2 = 0.f;
+            if (ulane) { if (live && lane < 4 * Fin && ra * Fin + lane < rows * Fin) R.u = __ldg(uptr); }
+            else if (live) {
+                if (tid < nu && row0 * Fin + tid < rows * Fin) R.u = __ldg(uptr);
+                if (tid + NP < nu && row0 * Fin + tid + NP < rows * Fin) R.u2 = __ldg(uptr + NP);
+            }
         }
         dptr += stride * G; hptr += stride * H; uptr += stride * Fin; lrow += stride;
         tpos += tstep; if (tpos >= (unsigned)T) tpos -= (unsigned)T;
@@ -186,7 +194,6 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
         *reinterpret_cast<float4*>(p_b) = w;
     };
 
-    constexpr int UP = 4;                                         // torso widths up to UP keep their weight column in registers
     const float bk = bts[ak];
     float wk[UP];
 #pragma unroll
@@ -222,7 +229,7 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
             float x[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) x[j] = bk;
-            if (Fin <= UP) {                                       // torso column ak in registers, the 4 x Fin inputs by shuffle
+            if (ulane) {                                           // torso column ak in registers, the 4 x Fin inputs by shuffle
 #pragma unroll
                 for (int q = 0; q < UP; ++q) {
                     if (q < Fin) {
@@ -230,18 +237,17 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
                         for (int j = 0; j < 4; ++j) x[j] = fmaf(__shfl_sync(kFull, R.u, j * Fin + q), wk[q], x[j]);
                     }
                 }
-            } else if (ulane) {
+            } else {                                               // the stage's inputs through shared memory (broadcast reads)
+                float* us = usm + (nproc & 1) * nu;
+                if (tid < nu) us[tid] = R.u;
+                if (tid + NP < nu) us[tid + NP] = R.u2;
+                tc::named_bar_sync(1, NP);
+                const float* ur = us + arg * 4 * Fin;
+#pragma unroll 4
                 for (int q = 0; q < Fin; ++q) {
                     const float w = WtS[q * H + ak];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) x[j] = fmaf(__shfl_sync(kFull, R.u, j * Fin + q), w, x[j]);
-                }
-            } else {
-                const long long r = prow + arg * 4;
-                for (int q = 0; q < Fin; ++q) {
-                    const float w = WtS[q * H + ak];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) if (r + j < rows) x[j] = fmaf(__ldg(u + (size_t)(r + j) * Fin + q), w, x[j]);
+                    for (int j = 0; j < 4; ++j) x[j] = fmaf(ur[j * Fin + q], w, x[j]);
                 }
             }
 #pragma unroll
