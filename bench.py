@@ -633,7 +633,7 @@ def main():
         gbuf, sbuf = (eng.chan.grad_views[0], eng.chan.scal_views[0]) if eng.chan is not None else (eng.grad, eng.scalars)
         # the kernels of the update, as the engine launches them (fused variants), each timed alone
         stages = {
-            "lstm_fwd": lambda i: ops.net_fwd(L, eng.flat, u, bt["hx"], bt["cx"], eng.ws, eng.head_out),          # fused forward + head_combine
+            "lstm_fwd": lambda i: ops.net_fwd(L, eng.flat, u, bt["hx"], bt["cx"], eng.ws, eng.head_out),          # fused forward (torso + projection + recurrence + heads)
             "ppo_head": lambda i: ops.ppo_head(eng.head_out, bt, eng.dhead, sbuf, hp, A, False, None),
             "lstm_bwd": lambda i: ops.lstm_bwd(L, eng.flat, eng.dhead, eng.ws, bt["cx"], u=u, partials=eng.partials),   # BPTT + head / torso gradients
             "lstm_wgrad": lambda i: ops.lstm_wgrad(L, eng.flat, eng.ws, bt["hx"], u, eng.dhead, eng.partials, variant=eng.wgrad_variant),

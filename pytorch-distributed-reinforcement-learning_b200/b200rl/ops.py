@@ -154,7 +154,7 @@ def _lstm_fwd(self, L, flat, u, hx0, cx0, ws, variant=None):
 
 def _net_fwd(self, L, flat, u, hx0, cx0, ws, head_out, variant=None):
     """Network forward: saved activations into `ws` and head_out (B, T, NH) = h . W_head^T + b_head.  Variant 5 with
-    Fin <= 8 and NH <= 4 is ONE recurrent kernel (+ the 6 us head_combine); everything else is lstm_fwd + head_fwd.
+    Fin <= 8 and NH <= 4 is ONE recurrent kernel (its CTAs fold their own partial heads at the end); everything else is lstm_fwd + head_fwd.
     Returns the number of kernel launches."""
     variant = FWD_VARIANT if variant is None else variant
     B, T, Fin = u.shape
@@ -167,7 +167,7 @@ def _net_fwd(self, L, flat, u, hx0, cx0, ws, head_out, variant=None):
         self.lib.call("b200rl_lstm_fwd_fused", ptr(u), ptr(hx0), ptr(cx0), v("Wt"), v("bt"), v("W_ih"), v("W_hh"),
                       v("b_ih"), v("b_hh"), v("W_head"), v("b_head"), ptr(ws["gates"]), ptr(ws["c"]), ptr(ws["h"]),
                       ptr(hp), ptr(head_out), B, T, Fin, L.NH, self._stream(dev))
-        return 2
+        return 1
     self.lstm_fwd(L, flat, u, hx0, cx0, ws, variant=variant)
     self.head_fwd(L, flat, ws["h"], head_out)
     return 2 if (variant == 5 or variant < 2) else 3

@@ -18,6 +18,12 @@
 #define B200RL_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
 #endif
 
+#ifdef B200RL_EMUL
+#define B200RL_MAXNREG(n)
+#else
+#define B200RL_MAXNREG(n) __maxnreg__(n)
+#endif
+
 namespace b200rl {
 
 constexpr int kWarp = 32;

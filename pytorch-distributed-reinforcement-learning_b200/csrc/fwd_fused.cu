@@ -74,7 +74,8 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
                       const float* __restrict__ Wt, const float* __restrict__ bt, const float* __restrict__ W_ih,
                       const float* __restrict__ W_hh, const float* __restrict__ b_ih, const float* __restrict__ b_hh,
                       const float* __restrict__ W_head, float* __restrict__ g_out, float* __restrict__ c_out,
-                      float* __restrict__ h_out, float* __restrict__ head_part, int B, int T, int Fin, int NH) {
+                      float* __restrict__ h_out, float* __restrict__ head_part, const float* __restrict__ b_head,
+                      float* __restrict__ head_out, int B, int T, int Fin, int NH) {
     using namespace ffk;
     B200RL_DYN_SMEM(unsigned char, smem);
     unsigned char* OPH = smem;                              // h_{t-1}: hi | lo | bf16
@@ -394,15 +395,18 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
     tc::fence_before_sync();
     __syncthreads();
     if (warp == NC / 32) tc::tmem_dealloc(tmem, TM_COLS);
-}
-
-// head_out[r][o] = part[r][0][o] + part[r][1][o] + b_head[o]
-__global__ void __launch_bounds__(256)
-head_combine_kernel(const float* __restrict__ part, const float* __restrict__ b_head, float* __restrict__ head_out, long long n, int NH) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / NH;
-        const int o = (int)(i - r * NH);
-        head_out[i] = part[(r * 2) * NH + o] + part[(r * 2 + 1) * NH + o] + b_head[o];
+    // ---- heads of the CTA's own sequences: head_out[r][o] = (part[r][0][o] + part[r][1][o]) + b_head[o].  The partial sums were
+    // written by this CTA (visible after the barrier, served by L2): all 28 warps fold them in ~2 us instead of a separate kernel.
+    if (head_part != nullptr && head_out != nullptr) {
+        for (int tile = blockIdx.x; tile < (B + TB - 1) / TB; tile += gridDim.x) {
+            const int b0 = tile * TB, nb = (B - b0 < TB) ? B - b0 : TB;
+            const long long base = (long long)b0 * T * NH, n = (long long)nb * T * NH;
+            for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+                const long long r = (base + i) / NH;
+                const int o = (int)((base + i) - r * NH);
+                head_out[base + i] = head_part[(r * 2) * NH + o] + head_part[(r * 2 + 1) * NH + o] + b_head[o];
+            }
+        }
     }
 }
 
@@ -422,23 +426,16 @@ int launch_fwd_fused(const float* u, const float* hx0, const float* cx0, const f
         if (e != cudaSuccess) return set_error("lstm_fwd_fused: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
 #endif
         B200RL_LAUNCH(lstm_fwd_fused_kernel<true>, grid, ffk::NT, smem, stream, u, hx0, cx0, Wt, bt, W_ih, W_hh, b_ih, b_hh, W_head,
-                      gates, c, h, head_part, B, T, Fin, NH);
+                      gates, c, h, head_part, b_head, head_out, B, T, Fin, NH);
     } else {
 #ifndef B200RL_EMUL
         cudaError_t e = cudaFuncSetAttribute(lstm_fwd_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error("lstm_fwd_fused: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
 #endif
         B200RL_LAUNCH(lstm_fwd_fused_kernel<false>, grid, ffk::NT, smem, stream, u, hx0, cx0, Wt, bt, W_ih, W_hh, b_ih, b_hh, W_head,
-                      gates, c, h, head_part, B, T, Fin, NH);
+                      gates, c, h, head_part, b_head, head_out, B, T, Fin, NH);
     }
-    if (check_launch("lstm_fwd_fused")) return 1;
-    if (head_part != nullptr) {
-        const long long n = (long long)B * T * NH;
-        const long long g = (n + 255) / 256;
-        B200RL_LAUNCH(head_combine_kernel, (int)(g > 148 * 8 ? 148 * 8 : g), 256, 0, stream, head_part, b_head, head_out, n, NH);
-        return check_launch("head_combine");
-    }
-    return 0;
+    return check_launch("lstm_fwd_fused");
 }
 
 }  // namespace b200rl

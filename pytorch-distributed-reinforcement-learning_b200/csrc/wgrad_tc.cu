@@ -66,6 +66,7 @@ constexpr int D_TILE = (G / 8) * SBO;           // 16896
 constexpr int O_AH = 0, O_DH = A_TILE, O_AB = O_DH + D_TILE, O_DB = O_AB + A_TILE;   // A_hi | D_hi (tf32) | A' | D' (bf16)
 constexpr int STAGE = O_DB + D_TILE;            // 50688 B
 constexpr int MAXF = 32;
+// (two CTAs of 9 warps per SM: 96 registers per thread is the ceiling -- with 112 only one CTA is resident, measured)
 constexpr int UP = 4;                           // torso widths up to UP: weight column in registers, inputs by shuffle; wider: inputs staged in shared memory
 static_assert((SR / 4 - 1) * LBO + 128 <= SBO, "core matrices of one mn-group must fit below SBO");
 static_assert(STAGE % 16 == 0 && O_DH % 16 == 0 && O_AB % 16 == 0 && O_DB % 16 == 0, "descriptor alignment");
@@ -73,9 +74,10 @@ __device__ __forceinline__ int koff(int mn, int r) { return (mn & 7) * 16 + (mn 
 }  // namespace wtc
 
 static inline size_t wgrad_tc_smem_bytes(int Fin) {
-    return wtc::NSTAGE * (size_t)wtc::STAGE + sizeof(float) * (size_t)(Fin * wtc::H + wtc::H + (Fin > wtc::UP ? 2 * wtc::SR * Fin : 0)) + 96;
+    return wtc::NSTAGE * (size_t)wtc::STAGE + sizeof(float) * (size_t)(Fin * wtc::H + wtc::H + (Fin > wtc::UP ? 2 * wtc::SR * Fin : 0)) + 96;   // (WIDE <=> Fin > UP)
 }
 
+template <bool WIDE>          // WIDE: torso input wider than UP (staged through shared memory); else the 4 x Fin inputs of a row group ride in one register per lane
 __global__ void __launch_bounds__(wtc::NT, 2)
 lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h, const float* __restrict__ hx0,
                      const float* __restrict__ u, const float* __restrict__ Wt, const float* __restrict__ bt,
@@ -87,8 +89,8 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
     unsigned char* stage0 = smem;                                   // 1024-aligned by construction (offset 0)
     float* WtS = reinterpret_cast<float*>(smem + NSTAGE * STAGE);   // WtS[q*64 + j]
     float* bts = WtS + Fin * H;
-    float* usm = bts + H;                                           // Fin > UP: the stage's 16 x Fin torso inputs, double-buffered
-    uint64_t* bars = reinterpret_cast<uint64_t*>(usm + (Fin > UP ? 2 * SR * Fin : 0));   // full[NSTAGE] | empty[NSTAGE] | done
+    float* usm = bts + H;                                           // WIDE: the stage's 16 x Fin torso inputs, double-buffered
+    uint64_t* bars = reinterpret_cast<uint64_t*>(usm + (WIDE ? 2 * SR * Fin : 0));   // full[NSTAGE] | empty[NSTAGE] | done
     uint64_t* full = bars, *empty = bars + NSTAGE, *done = bars + 2 * NSTAGE;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 1);
 
@@ -115,25 +117,27 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
     const long long rows = (long long)B * T;
     const long long nstages = (rows + SR - 1) / SR;
     float4 dbacc = make_float4(0.f, 0.f, 0.f, 0.f);               // bias gradient of gate columns dc4*4 .. +3 over this thread's rows
-    const bool ulane = Fin <= UP;                                  // the 4 x Fin torso inputs of a row group: one per lane
+    constexpr bool ulane = !WIDE;                                  // the 4 x Fin torso inputs of a row group: one per lane
     const int nu = SR * Fin;                                       // wider torsos: the stage's 16 x Fin inputs, up to two per thread
 
     // Register-staged loads: two register sets, both in flight except while their own stage is processed (a set is refilled,
     // two stages ahead, as soon as it has been written to shared memory).  The common case -- a stage with all 16 rows in
     // range and no sequence start among them -- runs without a single bounds check or row/time division: three running
     // pointers, immediate offsets.  `mode`: 0 nothing, 1 fast, 2 generic.
-    struct StageRegs { float4 d[4]; float hp[4]; float u, u2; int mode; };
+    struct StageRegs { float4 d[4]; float hp[4]; float u, u2; int mode; };      // (u2: WIDE only, dead otherwise)
     StageRegs ring[2];
     const long long stride = (long long)gridDim.x * SR;            // rows between two stages of this CTA
+    const unsigned dstep = (unsigned)(stride * G * 4), hstep = (unsigned)(stride * H * 4), ustep = (unsigned)(stride * Fin * 4);   // bytes (< 2^32: the launcher bounds the grid)
+    const int nst = (int)nstages;
     const float* dptr = dpre + ((size_t)blockIdx.x * SR + drg * 4) * G + dc4 * 4;
     const float* hptr = h + ((long long)blockIdx.x * SR + arg * 4 - 1) * H + ak;
     const float* uptr = ulane ? u + ((size_t)blockIdx.x * SR + arg * 4) * Fin + lane : u + (size_t)blockIdx.x * SR * Fin + tid;
     const unsigned tstep = (unsigned)(stride % T);
     unsigned tpos = (unsigned)(((long long)blockIdx.x * SR) % T);  // time index of the stage's first row
-    long long lrow = (long long)blockIdx.x * SR;                   // first row of the next stage to load
+    int lst = blockIdx.x;                                          // the next stage to load
     auto issue_loads = [&](StageRegs& R) {
-        const long long row0 = lrow;
-        const bool live = row0 < rows;
+        const long long row0 = (long long)lst * SR;
+        const bool live = lst < nst;
         const bool whole = row0 + SR <= rows;
         const bool has_t0 = tpos == 0 || tpos + SR > (unsigned)T;  // a row with t == 0 takes h_{t-1} from hx0
         R.mode = !live ? 0 : (whole && !has_t0) ? 1 : 2;
@@ -171,7 +175,10 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
                 if (tid + NP < nu && row0 * Fin + tid + NP < rows * Fin) R.u2 = __ldg(uptr + NP);
             }
         }
-        dptr += stride * G; hptr += stride * H; uptr += stride * Fin; lrow += stride;
+        dptr = reinterpret_cast<const float*>(reinterpret_cast<const char*>(dptr) + dstep);
+        hptr = reinterpret_cast<const float*>(reinterpret_cast<const char*>(hptr) + hstep);
+        uptr = reinterpret_cast<const float*>(reinterpret_cast<const char*>(uptr) + ustep);
+        lst += gridDim.x;
         tpos += tstep; if (tpos >= (unsigned)T) tpos -= (unsigned)T;
     };
 
@@ -200,14 +207,14 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
     for (int q = 0; q < UP; ++q) wk[q] = q < Fin ? WtS[q * H + ak] : 0.f;
 
     int nproc = 0;
-    long long prow = (long long)blockIdx.x * SR;                  // first row of the next stage to process
+    int pst = blockIdx.x;                                         // the next stage to process
     auto process = [&](const StageRegs& R, int buf) {
         const int use = nproc >> 1;
         unsigned char* sb = stage0 + (size_t)buf * STAGE;
         if (kProbe == 1) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) { dbacc.x += R.d[j].x + R.hp[j]; dbacc.y += R.d[j].y; dbacc.z += R.d[j].z; dbacc.w += R.d[j].w + R.u; }
-            ++nproc; prow += stride;
+            ++nproc; pst += gridDim.x;
             return;
         }
         if (use >= 1) tc::mbar_wait(&empty[buf], (uint32_t)((use - 1) & 1));  // MMAs of the previous use of this buffer are done
@@ -253,7 +260,7 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
 #pragma unroll
             for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.f);
             if (R.mode != 1) {
-                const long long r = prow + arg * 4;
+                const long long r = (long long)pst * SR + arg * 4;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) if (r + j >= rows) x[j] = 0.f;
             }
@@ -263,14 +270,14 @@ lstm_wgrad_tc_kernel(const float* __restrict__ dpre, const float* __restrict__ h
         tc::fence_async_smem();          // generic-proxy stores -> visible to the tensor core (async proxy)
         tc::mbar_arrive_warp(&full[buf]);
         ++nproc;
-        prow += stride;
+        pst += gridDim.x;
     };
 
     if (producer) {
         issue_loads(ring[0]);
         issue_loads(ring[1]);
-        while (prow < rows) {
-            process(ring[0], 0); issue_loads(ring[0]); if (prow >= rows) break;
+        while (pst < nst) {
+            process(ring[0], 0); issue_loads(ring[0]); if (pst >= nst) break;
             process(ring[1], 1); issue_loads(ring[1]);
         }
     } else if (lane == 0) {
@@ -347,13 +354,23 @@ int launch_wgrad_tc(const float* dpre, const float* h, const float* hx0, const f
                     int B, int T, int Fin, void* stream) {
     B200RL_REQUIRE(Fin >= 1 && Fin <= wtc::MAXF, "lstm_wgrad(tc): Fin=%d out of range", Fin);
     B200RL_REQUIRE((long long)B * T < (1LL << 31), "lstm_wgrad(tc): B*T must be below 2^31");
+    B200RL_REQUIRE(nparts >= 1 && nparts <= 65536, "lstm_wgrad(tc): nparts=%d out of range (32-bit byte strides)", nparts);
     const size_t smem = wgrad_tc_smem_bytes(Fin);
+    if (Fin > wtc::UP) {
 #ifndef B200RL_EMUL
-    cudaError_t e = cudaFuncSetAttribute(lstm_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return set_error("lstm_wgrad(tc): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+        cudaError_t e = cudaFuncSetAttribute(lstm_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error("lstm_wgrad(tc): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
 #endif
-    B200RL_LAUNCH(lstm_wgrad_tc_kernel, nparts, wtc::NT, smem, stream, dpre, h, hx0, u, Wt, bt, partials, P,
-                  off_Wih, off_Whh, off_bih, off_bhh, B, T, Fin);
+        B200RL_LAUNCH(lstm_wgrad_tc_kernel<true>, nparts, wtc::NT, smem, stream, dpre, h, hx0, u, Wt, bt, partials, P,
+                      off_Wih, off_Whh, off_bih, off_bhh, B, T, Fin);
+    } else {
+#ifndef B200RL_EMUL
+        cudaError_t e = cudaFuncSetAttribute(lstm_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error("lstm_wgrad(tc): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+#endif
+        B200RL_LAUNCH(lstm_wgrad_tc_kernel<false>, nparts, wtc::NT, smem, stream, dpre, h, hx0, u, Wt, bt, partials, P,
+                      off_Wih, off_Whh, off_bih, off_bhh, B, T, Fin);
+    }
     return check_launch("lstm_wgrad(tc)");
 }
 

@@ -71,7 +71,10 @@ def _emul_ops():
             lib = native.Lib(os.path.join(ROOT, "tests", "emul", "_build", "libb200rl_emul.so"), emulated=True)
             _EMUL["ops"] = ops.Ops(lib, allow_cpu=True)
     if _EMUL["ops"] is None:
-        pytest.skip("emulator build failed: " + _EMUL.get("err", ""))
+        import shutil
+        if shutil.which("g++") is None:
+            pytest.skip("no g++: the host emulator cannot be built")
+        pytest.fail("emulator build failed (a kernel source does not compile for the host emulator):\n" + _EMUL.get("err", ""))
     return _EMUL["ops"]
 
 

@@ -18,7 +18,7 @@ raw = run("raw", f"gpurun_out/raw_{tag}.csv")
 rows = [l.split("|") for l in launch.splitlines() if l.startswith("| ") and not l.startswith("| kernel") and "**sum**" not in l]
 ms = {r[1].strip(): float(r[3]) for r in rows}
 pick = lambda sub: [k for k in ms if sub in k]
-stage = {"lstm_fwd": pick("lstm_fwd_fused") + pick("head_combine"), "ppo_head": pick("ppo_head"), "lstm_bwd": pick("lstm_bwdt"),
+stage = {"lstm_fwd": pick("lstm_fwd_fused"), "ppo_head": pick("ppo_head"), "lstm_bwd": pick("lstm_bwdt"),
          "lstm_wgrad": pick("wgrad_tc") + pick("torso_grad") + pick("head_grad"), "reduce_partials": pick("reduce_partials"),
          "clip_rmsprop": pick("peer_step")}
 ntot = sum(ms.values())

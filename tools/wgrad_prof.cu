@@ -30,6 +30,9 @@ int main(int argc, char** argv) {
     cudaEventRecord(e1);
     cudaDeviceSynchronize();
     float ms; cudaEventElapsedTime(&ms, e0, e1);
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lstm_wgrad_tc_kernel<false>, wtc::NT, wgrad_tc_smem_bytes(Fin));
+    printf("CTAs per SM: %d  ", occ);
     printf("wgrad_tc probe %d (bf16 cross terms %d), %d CTAs: %.3f ms  (%.0f GB/s of dpre + h + u)  %s\n", B200RL_WGPROBE, B200RL_WG_BF16X, nparts, ms / 10,
            (double)rows * (256 + 64 + Fin) * 4 / (ms / 10 * 1e-3) / 1e9, cudaGetErrorString(cudaGetLastError()));
     return 0;
