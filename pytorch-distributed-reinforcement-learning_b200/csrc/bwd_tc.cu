@@ -54,6 +54,9 @@ namespace btk {
 #ifndef B200RL_BWD_NI
 #define B200RL_BWD_NI 2
 #endif
+#ifndef B200RL_BWD_CELL_REGS
+#define B200RL_BWD_CELL_REGS 112                          // (NI == 4) 512 x 112 + 128 x 40 <= 64K registers
+#endif
 constexpr int H = 64, G = 256, TB = 32, NC = 512, NI = B200RL_BWD_NI, NT = NC + 32 * NI;    // 8 A + 8 B cell warps, NI MMA issuer warps
 constexpr int B_LBO = 144, B_SBO = 9216;                            // B: 64 core matrices along K, 16-byte skew -> conflict-free 16-byte stores
 constexpr int B_BYTES = (TB / 8) * B_SBO;                           // 36864 per hi / lo
@@ -156,6 +159,9 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
     const int ntiles = (B + TB - 1) / TB;
 
     if (!cellw) {
+#if B200RL_BWD_NI == 4 && !defined(B200RL_EMUL)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");       // the four issuer warps are one warp-group: their registers go to the cell warps
+#endif
         if (lane == 0) {
             const int ii = warp - NC / 32;                           // K-steps [ii 32/NI, (ii+1) 32/NI) into accumulator ii
             const uint32_t D = tmem + TM_D + ii * TB;
@@ -183,6 +189,9 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
             }
         }
     } else {
+#if B200RL_BWD_NI == 4 && !defined(B200RL_EMUL)
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(B200RL_BWD_CELL_REGS));
+#endif
         const bool isB = q >= 2;                                     // B threads see the dx lanes, A threads the dh_rec lanes
         const int half = q & 1;
         const int j = half * 32 + lane;                              // LSTM unit (cell math) = dx column (B, TMEM side)

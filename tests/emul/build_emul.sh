@@ -10,7 +10,7 @@ PIDS=""
 for f in "$SRC"/*.cu; do
   b=$(basename "$f" .cu)
   if [ ! -f "$OUT/$b.o" ] || [ "$f" -nt "$OUT/$b.o" ] || [ -n "$(find "$SRC" "$HERE/cuda_emul.h" -newer "$OUT/$b.o" \( -name '*.cuh' -o -name '*.h' \) | head -1)" ]; then
-    g++ -std=c++20 -O1 -g -fPIC -DB200RL_EMUL -x c++ -c "$f" -o "$OUT/$b.o" -I"$SRC" -I"$HERE/../../include" -Wall -Wno-unknown-pragmas -Wno-unused-variable -Wno-unused-function -Wno-sign-compare &
+    g++ -std=c++20 -O1 -g -fPIC -DB200RL_EMUL $B200RL_EMUL_DEFS -x c++ -c "$f" -o "$OUT/$b.o" -I"$SRC" -I"$HERE/../../include" -Wall -Wno-unknown-pragmas -Wno-unused-variable -Wno-unused-function -Wno-sign-compare &
     PIDS="$PIDS $!"
   fi
   OBJS="$OBJS $OUT/$b.o"

@@ -25,7 +25,7 @@ ntot = sum(ms.values())
 km = b["kernels_ms"]
 tot = sum(km.values())
 out = [f"# {tag} -- PPO B=4096 T=128 obs=4 A=2, one B200\n", "## Launch list of the bench command\n",
-       "`ncu --metrics gpu__time_duration.sum --clock-control none -k regex:<our kernels> -s 27 -c 54 --csv python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-extras`",
+       "`ncu --metrics gpu__time_duration.sum --clock-control none -k regex:<our kernels> -s 18 -c 36 --csv python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-extras`",
        f"(raw: `profiles/{tag}_launches_bench.csv`; per-launch times under ncu are cold-cache and serialised -- compare SHARES).\n", launch,
        f"bench.py's own CUDA-event times of the same kernels, each timed alone (`profiles/{tag}_bench.json` `kernels_ms`):\n",
        "| stage | bench ms | bench share | ncu share |", "|---|---|---|---|"]
@@ -38,7 +38,7 @@ out.append(f"\nbench: value {b['value']:.3e} env-steps/s, {b['ms_per_step']:.3f}
            + (f"CPU {cb.get('kind')} {cb['value']:.3e} on {cb['cores']} cores; " if cb else "")
            + f"parity_in_run {json.dumps(b.get('parity_in_run'))}; clocks {b['clocks']['sm_mhz']} MHz, throttle reasons {b['clocks']['reasons']}.\n")
 out.append("## `ncu --set full` of every kernel of one PPO update\n")
-out.append("`ncu --set full --clock-control none --import-source on -k regex:<our kernels> -s 27 -c 9 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras`")
+out.append("`ncu --set full --clock-control none --import-source on -k regex:<our kernels> -s 18 -c 6 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras`")
 out.append(f"(`gpurun_out/prof_{tag}.ncu-rep` is not committed; table = `ncu -i ... --page raw --csv` through `tools/summarize_ncu.py raw`).\n")
 out.append(raw)
 
