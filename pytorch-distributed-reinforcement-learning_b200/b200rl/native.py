@@ -108,9 +108,10 @@ def get():
     """The product library (loads on first use; raises NativeError if absent)."""
     global _lib
     if _lib is None:
-        _lib = Lib(LIB)
+        path = os.environ.get("B200RL_LIB") or LIB        # (B200RL_LIB: A/B builds of the same sources, tools/build_variant.py)
+        _lib = Lib(path)
         if _lib.missing:
-            raise NativeError(f"{LIB} lacks symbols {_lib.missing}; rebuild")
+            raise NativeError(f"{path} lacks symbols {_lib.missing}; rebuild")
     return _lib
 
 

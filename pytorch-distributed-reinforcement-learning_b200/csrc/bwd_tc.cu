@@ -52,20 +52,25 @@ __device__ unsigned long long g_bwdprof[24];
 
 namespace btk {
 #ifndef B200RL_BWD_NI
-#define B200RL_BWD_NI 2
+#define B200RL_BWD_NI 2                                   // issuer warps of the instantiations without fused torso gradients
+#endif
+#ifndef B200RL_BWD_NI_TORSO
+#define B200RL_BWD_NI_TORSO 4                             // ... of the fully fused ones (measured, B = 4096, T = 128, NH = 3: 0.479 -> 0.459 ms; without the fusion 2 is faster)
 #endif
 #ifndef B200RL_BWD_CELL_REGS
-#define B200RL_BWD_CELL_REGS 112                          // (NI == 4) 512 x 112 + 128 x 40 <= 64K registers
+#define B200RL_BWD_CELL_REGS 104                          // (4 issuers) the CTA owns NT x 96 registers from launch: 512 x 104 + 128 x 40 <= 640 x 96
 #endif
-constexpr int H = 64, G = 256, TB = 32, NC = 512, NI = B200RL_BWD_NI, NT = NC + 32 * NI;    // 8 A + 8 B cell warps, NI MMA issuer warps
+constexpr int H = 64, G = 256, TB = 32, NC = 512;                   // 8 A + 8 B cell warps (+ NI MMA issuer warps)
+constexpr int nthreads(int ni) { return NC + 32 * ni; }
 constexpr int B_LBO = 144, B_SBO = 9216;                            // B: 64 core matrices along K, 16-byte skew -> conflict-free 16-byte stores
 constexpr int B_BYTES = (TB / 8) * B_SBO;                           // 36864 per hi / lo
 static_assert(63 * B_LBO + 128 <= B_SBO, "core matrices of one 8-row group must fit below SBO");
 constexpr int C_LBO = 144, C_SBO = 4608;                            // bf16 copy of dpre_hi (third split term): 32 core matrices (8 k) along K, same skew
 constexpr int C_BYTES = (TB / 8) * C_SBO;                           // 18432
 static_assert(31 * C_LBO + 128 <= C_SBO, "core matrices of one 8-row group must fit below SBO");
-constexpr int TM_D = 0, TM_AH = NI * TB, TM_AL = TM_AH + G, TM_COLS = 512;     // accumulator i at columns 32 i ; A_lo: bf16 pairs, G/2 columns
-static_assert(TM_AL + G / 2 <= TM_COLS, "tensor memory budget");
+constexpr int TM_D = 0, TM_COLS = 512;                              // accumulator i at columns 32 i ; then A_hi (G columns) ; then A_lo: bf16 pairs, G/2 columns
+static_assert(4 * TB + G + G / 2 <= TM_COLS, "tensor memory budget (up to 4 accumulators)");
+static_assert(NC * B200RL_BWD_CELL_REGS + 128 * 40 <= nthreads(4) * 96, "setmaxnreg.inc would wait forever: the CTA's register pool is what it was launched with");
 constexpr int CT = 4;                                               // cells (sequences) a thread owns
 constexpr int RED = 4 * 10 * H;                                     // end-of-kernel reduction scratch: [sequence group][10][unit]
 }  // namespace btk
@@ -81,12 +86,13 @@ struct BwdFuse {                 // fused head / torso gradients (null partials 
     int torso;                   // 1: dWt / dbt accumulated here (dx never stored) ; 0: only the head gradients, dx is stored
 };
 
-template <int NHT>                // 0: runtime NH, small gradients left to their own kernels ; 1..4: NH == NHT at compile time, `fz` gradients fused
-__global__ void __launch_bounds__(btk::NT, 1)
+template <int NHT, int NI>        // NHT 0: runtime NH, small gradients left to their own kernels ; 1..4: NH == NHT at compile time, `fz` gradients fused ; NI: issuer warps
+__global__ void __launch_bounds__(btk::nthreads(NI), 1)
 lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_head, const float* __restrict__ W_hh,
                  const float* __restrict__ W_ih, float* gates, const float* __restrict__ c_sav,
                  const float* __restrict__ cx0, float* __restrict__ dx, int B, int T, int NH, BwdFuse fz) {
     using namespace btk;
+    constexpr int NT = NC + 32 * NI, TM_AH = NI * TB, TM_AL = TM_AH + G;
     constexpr bool fuse = NHT > 0;
     if (fuse) NH = NHT;
     B200RL_DYN_SMEM(unsigned char, smem);
@@ -159,8 +165,8 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
     const int ntiles = (B + TB - 1) / TB;
 
     if (!cellw) {
-#if B200RL_BWD_NI == 4 && !defined(B200RL_EMUL)
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");       // the four issuer warps are one warp-group: their registers go to the cell warps
+#if !defined(B200RL_EMUL)
+        if constexpr (NI == 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");       // the four issuer warps are one warp-group: their registers go to the cell warps
 #endif
         if (lane == 0) {
             const int ii = warp - NC / 32;                           // K-steps [ii 32/NI, (ii+1) 32/NI) into accumulator ii
@@ -189,8 +195,8 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
             }
         }
     } else {
-#if B200RL_BWD_NI == 4 && !defined(B200RL_EMUL)
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(B200RL_BWD_CELL_REGS));
+#if !defined(B200RL_EMUL)
+        if constexpr (NI == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(B200RL_BWD_CELL_REGS));
 #endif
         const bool isB = q >= 2;                                     // B threads see the dx lanes, A threads the dh_rec lanes
         const int half = q & 1;
@@ -448,17 +454,25 @@ int launch_bwd_tc(const float* dhead, const float* W_head, const float* W_hh, co
                                B, T, 0, NH, sms, stream);
 }
 
-template <int NHT>
-static int launch_bwdt(const float* dhead, const float* W_head, const float* W_hh, const float* W_ih, float* gates,
+template <int NHT, int NI>
+static int launch_bwdt_ni(const float* dhead, const float* W_head, const float* W_hh, const float* W_ih, float* gates,
                        const float* c, const float* cx0, float* dx, int B, int T, int NH, BwdFuse fz, int sms, void* stream) {
     const int ntiles = (B + btk::TB - 1) / btk::TB;
     const size_t smem = bwdt_smem_bytes(NH);
 #ifndef B200RL_EMUL
-    cudaError_t e = cudaFuncSetAttribute(lstm_bwdt_kernel<NHT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(lstm_bwdt_kernel<NHT, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error("lstm_bwd(tc): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
 #endif
-    B200RL_LAUNCH(lstm_bwdt_kernel<NHT>, ntiles < sms ? ntiles : sms, btk::NT, smem, stream, dhead, W_head, W_hh, W_ih, gates, c, cx0, dx, B, T, NH, fz);
+    B200RL_LAUNCH((lstm_bwdt_kernel<NHT, NI>), ntiles < sms ? ntiles : sms, btk::nthreads(NI), smem, stream, dhead, W_head, W_hh, W_ih, gates, c, cx0, dx, B, T, NH, fz);
     return check_launch("lstm_bwd(tc)");
+}
+
+template <int NHT>
+static int launch_bwdt(const float* dhead, const float* W_head, const float* W_hh, const float* W_ih, float* gates,
+                       const float* c, const float* cx0, float* dx, int B, int T, int NH, BwdFuse fz, int sms, void* stream) {
+    if (NHT > 0 && fz.torso)
+        return launch_bwdt_ni<NHT, (NHT > 0 ? B200RL_BWD_NI_TORSO : B200RL_BWD_NI)>(dhead, W_head, W_hh, W_ih, gates, c, cx0, dx, B, T, NH, fz, sms, stream);
+    return launch_bwdt_ni<NHT, B200RL_BWD_NI>(dhead, W_head, W_hh, W_ih, gates, c, cx0, dx, B, T, NH, fz, sms, stream);
 }
 
 // partials != nullptr: head gradients fused (NH <= 4); with dx == nullptr also the torso gradients (Fin == 4) and dx is never stored

@@ -44,7 +44,7 @@ int main(int argc, char** argv) {
 #ifdef B200RL_BWDPROF
     cudaMemcpyFromSymbol(z, g_bwdprof, sizeof(z));
 #else
-    printf("bwd_tc (no probes, NI=%d, fused mode %d) %.3f ms\n", btk::NI, mode, ms);
+    printf("bwd_tc (no probes, NI=%d, fused mode %d) %.3f ms\n", (mode == 2 ? B200RL_BWD_NI_TORSO : B200RL_BWD_NI), mode, ms);
     return 0;
 #endif
     const double steps = (B / 32.0) * T;
