@@ -59,7 +59,12 @@ constexpr int C_LBO = 144, C_SBO = 1152;                   // bf16 B operand: 8 
 constexpr int C_BYTES = (TB / 8) * C_SBO;                  // 4608
 constexpr int OP_BYTES = 2 * B_BYTES + C_BYTES;            // one operand set: hi | lo | bf16(hi)
 constexpr int EXF = 2 * NG * 2 * RW * 32;                  // swap buffer [pair][direction][slot][lane] floats
-constexpr int NBAR = 8;                                    // b_full, acc_done, acc_free, x_done, x_full[2], x_free[2]
+constexpr int NBAR = 10;                                   // b_full, acc_done, acc_free, x_done, x_full[2], x_free[2], h_full, h_free
+#ifndef B200RL_FWD_HEADS_PROD
+#define B200RL_FWD_HEADS_PROD 1                            // 1: the heads are computed by the producer warps from the h operand in shared memory ; 0: by the cell warps (shuffle fold + partial heads)
+#endif
+constexpr bool HP = B200RL_FWD_HEADS_PROD != 0;
+constexpr int HLAG = 3;                                    // the producers run ~3 steps ahead of the cell phase with x: the heads of step i - 3 precede x of step i
 static_assert(15 * B_LBO + 128 <= B_SBO && 7 * C_LBO + 128 <= C_SBO, "core matrices of one 8-row group must fit below SBO");
 static_assert(RW == 8 && CT == 4, "cell phase layout");
 }  // namespace ffk
@@ -87,6 +92,7 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
     float* WH = BT + H;                                     // WH[j*4 + o]
     uint64_t* bars = reinterpret_cast<uint64_t*>(WH + H * 4);
     uint64_t* b_full = bars, *acc_done = bars + 1, *acc_free = bars + 2, *x_done = bars + 3, *x_full = bars + 4, *x_free = bars + 6;   // x_full[2], x_free[2]
+    uint64_t* h_full = bars + 8, *h_free = bars + 9;        // (HP) h_t sits in OPH ; the producers have read it
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBAR);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -96,11 +102,14 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
     for (int i = tid; i < H * 4; i += NT) { const int j = i >> 2, g = i & 3; BI[i] = b_ih[g * H + j] + b_hh[g * H + j]; }
     for (int i = tid; i < H * MAXF; i += NT) { const int j = i >> 3, f = i & 7; WT[i] = f < Fin ? Wt[j * Fin + f] : 0.f; }
     for (int i = tid; i < H; i += NT) BT[i] = bt[i];
-    for (int i = tid; i < H * 4; i += NT) { const int j = i >> 2, o = i & 3; WH[i] = (head_part != nullptr && o < NH) ? W_head[o * H + j] : 0.f; }
+    const bool heads = head_part != nullptr;
+    if (HP) { for (int i = tid; i < H * 4; i += NT) { const int o = i >> 6, j = i & 63; WH[i] = (heads && o < NH) ? W_head[o * H + j] : 0.f; } }   // WH[o*64 + j]
+    else { for (int i = tid; i < H * 4; i += NT) { const int j = i >> 2, o = i & 3; WH[i] = (heads && o < NH) ? W_head[o * H + j] : 0.f; } }       // WH[j*4 + o]
     if (tid == 0) {
         tc::mbar_init(b_full, NC / 32); tc::mbar_init(acc_done, NI); tc::mbar_init(acc_free, NC / 32); tc::mbar_init(x_done, NI);
         tc::mbar_init(x_full, NPW); tc::mbar_init(x_full + 1, NPW);
         tc::mbar_init(x_free, NI); tc::mbar_init(x_free + 1, NI);
+        tc::mbar_init(h_full, NC / 32); tc::mbar_init(h_free, NPW);
         tc::fence_mbar_init();
     }
     if (warp == NC / 32) tc::tmem_alloc(tmem_slot, TM_COLS);
@@ -173,11 +182,57 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
 #pragma unroll
         for (int f = 0; f < MAXF; ++f) wt[f] = WT[j * MAXF + f];
         uint32_t written[2] = {0, 0};
+        // (HP) heads of one step from the h operand the cell warps just wrote: thread = (sequence r = 8 * warp + (lane & 7), unit
+        // quarter lane >> 3): h = hi + lo of 16 units as four 16-byte reads each (a quarter-warp reads 128 contiguous bytes),
+        // 4 x 16 FMAs against W_head^T, two shuffle-adds over the quarters, + bias -> head_out (no partial heads, no fold)
+        const int hw = pt >> 5, hrr = lane & 7, hq = lane >> 3, hr = 8 * hw + hrr;
+        long long hn = 0;                                       // head steps done
+        const float bh0 = (heads && NH > 0) ? b_head[0] : 0.f, bh1 = (heads && NH > 1) ? b_head[1] : 0.f;
+        const float bh2 = (heads && NH > 2) ? b_head[2] : 0.f, bh3 = (heads && NH > 3) ? b_head[3] : 0.f;
+        int htile = blockIdx.x, ht = 0;
+        auto do_head = [&]() {
+            tc::mbar_wait(h_full, (uint32_t)hn & 1);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            const unsigned char* base = OPH + hrr * 16 + hw * B_SBO + (hq * 4) * B_LBO;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 vh = *reinterpret_cast<const float4*>(base + q * B_LBO);
+                const float4 vl = *reinterpret_cast<const float4*>(base + B_BYTES + q * B_LBO);
+                const float4 hv = make_float4(vh.x + vl.x, vh.y + vl.y, vh.z + vl.z, vh.w + vl.w);
+                const int j0 = hq * 16 + q * 4;
+                const float4 w0 = ld4(WH + j0), w1 = ld4(WH + H + j0), w2 = ld4(WH + 2 * H + j0), w3 = ld4(WH + 3 * H + j0);
+                a0 = fmaf(hv.x, w0.x, fmaf(hv.y, w0.y, fmaf(hv.z, w0.z, fmaf(hv.w, w0.w, a0))));
+                a1 = fmaf(hv.x, w1.x, fmaf(hv.y, w1.y, fmaf(hv.z, w1.z, fmaf(hv.w, w1.w, a1))));
+                a2 = fmaf(hv.x, w2.x, fmaf(hv.y, w2.y, fmaf(hv.z, w2.z, fmaf(hv.w, w2.w, a2))));
+                a3 = fmaf(hv.x, w3.x, fmaf(hv.y, w3.y, fmaf(hv.z, w3.z, fmaf(hv.w, w3.w, a3))));
+            }
+            tc::mbar_arrive_warp(h_free);                       // (every lane has read its part of the operand: the cell warps may overwrite it)
+#pragma unroll
+            for (int m = 8; m <= 16; m <<= 1) {
+                a0 += __shfl_xor_sync(kFull, a0, m); a1 += __shfl_xor_sync(kFull, a1, m);
+                a2 += __shfl_xor_sync(kFull, a2, m); a3 += __shfl_xor_sync(kFull, a3, m);
+            }
+            const int b = htile * TB + hr;
+            if (hq == 0 && b < B) {
+                float* o = head_out + ((size_t)b * T + ht) * NH;
+                o[0] = a0 + bh0;
+                if (NH > 1) o[1] = a1 + bh1;
+                if (NH > 2) o[2] = a2 + bh2;
+                if (NH > 3) o[3] = a3 + bh3;
+            }
+            ++hn;
+            if (++ht == T) { ht = 0; htile += gridDim.x; }
+        };
+        long long xn = 0;                                       // x steps produced
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int b0 = tile * TB;
             for (int t = 0; t < T; ++t) {
                 const int p = t & 1;
                 unsigned char* op = OPX + p * OP_BYTES;
+                // heads FIRST: the cell phase of step i - 2 waits for them before it frees the accumulators that x_i's operand set
+                // may be waiting on (with an odd T two consecutive steps share a set across a tile boundary)
+                if (HP && heads && xn >= HLAG) do_head();
+                ++xn;
                 float xv[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {                          // (the loads of a step do not wait for the operand set)
@@ -207,6 +262,7 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
                 tc::mbar_arrive_warp(x_full + p);
             }
         }
+        if (HP && heads) while (hn < nsteps) do_head();         // the last HLAG steps
     } else if (!compute) {
 #if !defined(B200RL_EMUL)
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -303,6 +359,7 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
             auto seq = [&](int i) { const int b = b0 + rbase + mine + i; return b < B ? b : B - 1; };
             auto rowof = [&](int i) { return (unsigned)seq(i) * (unsigned)T; };       // B*T < 2^31 (checked by the launcher)
             float cst[CT];
+            if (HP && heads && n > 0) tc::mbar_wait(h_free, (n - 1) & 1);     // the heads of the previous tile's last step have been read out of OPH
 #pragma unroll
             for (int i = 0; i < CT; ++i) {
                 const size_t b = (size_t)seq(i);
@@ -315,6 +372,7 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
 
             for (int t = 0; t < T; ++t, ++n) {
                 F3P(0, 0);
+                if (HP && heads && t > 0) tc::mbar_wait(h_free, (n - 1) & 1);  // (long done: the producers read h_{t-1} while the tensor core ran this step)
                 tc::mbar_wait(acc_done, n & 1);
                 tc::fence_after_sync();
                 F3P(1, 0);
@@ -358,6 +416,7 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
                     tc::fence_before_sync();
                     tc::mbar_arrive_warp(b_full);
                 }
+                if (HP && heads) tc::mbar_arrive_warp(h_full);          // h_t is in shared memory (every step, also the last of a tile)
                 F3P(5, 0);
                 // ---- off the serial chain from here: the tensor core is running step t+1
 #pragma unroll
@@ -368,7 +427,7 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
                         c_out[o] = cst[i]; h_out[o] = hsv[i];
                     }
                 }
-                if (head_part != nullptr) {
+                if (!HP && head_part != nullptr) {
                     // heads: v[i*4 + o] = h[seq i][j] * W_head[o][j], folded over the warp's 32 units: lane l ends with slot (l >> 1) & 15
                     const float4 wh = ld4(WH + j * 4);
                     float v[16];
@@ -397,7 +456,7 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
     if (warp == NC / 32) tc::tmem_dealloc(tmem, TM_COLS);
     // ---- heads of the CTA's own sequences: head_out[r][o] = (part[r][0][o] + part[r][1][o]) + b_head[o].  The partial sums were
     // written by this CTA (visible after the barrier, served by L2): all 28 warps fold them in ~2 us instead of a separate kernel.
-    if (head_part != nullptr && head_out != nullptr) {
+    if (!HP && head_part != nullptr && head_out != nullptr) {
         for (int tile = blockIdx.x; tile < (B + TB - 1) / TB; tile += gridDim.x) {
             const int b0 = tile * TB, nb = (B - b0 < TB) ? B - b0 : TB;
             const long long base = (long long)b0 * T * NH, n = (long long)nb * T * NH;

@@ -296,3 +296,34 @@ def test_full_size_tcgen05_path_agrees_with_ffma_path(monkeypatch):
     L_p, g_p = run(3, 1, 1, perm)
     _close(L_p["loss"], L_tc["loss"], rtol=1e-5, atol=1e-8, what="loss under a permutation of the sequences")
     _close(g_p.cpu(), g_tc.cpu(), rtol=1e-3, atol=2e-5 * float(g_tc.abs().max()), what="gradient under a permutation of the sequences")
+
+
+@pytest.mark.parametrize("tiles,T,f,A", [(5, 5, 4, 2), (5.2, 3, 4, 2), (1.25, 1, 4, 2), (2.2, 2, 3, 3), (9.4, 1, 4, 1)])
+def test_fused_forward_many_tiles_short_and_odd_windows(backend, tiles, T, f, A):
+    """The fused forward's head pipeline (producer warps read h_t from the shared-memory operand three steps behind their own
+    x production; two extra mbarriers against the cell warps) across tile boundaries of a CTA, with an odd window (two
+    consecutive steps share an operand set there -- an ordering that once deadlocked in the emulator), windows shorter than
+    the pipeline depth, ragged last tiles; against the oracle's forward (`networks/models.py:63-87`)."""
+    from b200rl.networks import models as M
+    ops, dev = backend
+    ctas = 4 if dev.type == "cpu" else torch.cuda.get_device_properties(dev).multi_processor_count
+    B = int(round(tiles * ctas * 32))
+    torch.manual_seed(3)
+    model = M.MlpLSTMSingle(f, A, T, 64)
+    sd = {k: v.clone() for k, v in model.actor.state_dict().items()}
+    model = model.to(dev)
+    net = model.actor
+    L, flat = net._layout, net.flat_parameters()
+    u, hx, cx = torch.randn(B, T, f), 0.5 * torch.randn(B, 64), 0.5 * torch.randn(B, 64)
+    ws = dict(gates=torch.empty(B, T, 64, 4, device=dev), c=torch.empty(B, T, 64, device=dev), h=torch.empty(B, T, 64, device=dev))
+    ho = torch.full((B, T, L.NH), float("nan"), device=dev)
+    assert ops.net_fwd(L, flat, u.to(dev), hx.to(dev), cx.to(dev), ws, ho) == 1          # ONE launch
+    from oracle import models as OM
+    hs = OM.lstm_unroll(OM._torso(u, sd), hx, cx, sd)
+    _close(ws["h"].cpu(), hs, rtol=1e-4, atol=2e-6, what="h")
+    got = ho.cpu()
+    assert torch.isfinite(got).all()
+    # the kernel's own head order is the layout's; compare as sets of columns through the layout offsets
+    W_head = flat[L.off["W_head"][0]:L.off["W_head"][0] + L.NH * 64].view(L.NH, 64).cpu()
+    b_head = flat[L.off["b_head"][0]:L.off["b_head"][0] + L.NH].cpu()
+    _close(got, hs @ W_head.t() + b_head, rtol=1e-4, atol=2e-6, what="head_out")
