@@ -170,7 +170,7 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
 
     if (producer) {
 #ifndef B200RL_EMUL
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        if (F4) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");      // (generic torso widths keep the 72 registers of the launch: the 8192 the cell warps gain are exactly what the issuers give back)
 #endif
         // x[r][j] = ReLU(bt[j] + Wt[j] . obs[r, t]) for the tile's 32 sequences: thread = (unit j, 16 of the sequences), element
         // (r, j) of operand set t & 1 as TF32 hi / lo and bf16(hi)
@@ -178,17 +178,15 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
         auto tf = [&](int r) { return (r & 7) * 16 + (r >> 3) * B_SBO + (j & 3) * 4 + (j >> 2) * B_LBO; };
         auto bf = [&](int r) { return 2 * B_BYTES + (r & 7) * 16 + (r >> 3) * C_SBO + (j & 7) * 2 + (j >> 3) * C_LBO; };
         const float btj = BT[j];
-        float wt[MAXF];
+        float wt[F4 ? 4 : 1];                                   // (wider / narrower torsos read their weights from shared memory in the loop: registers)
 #pragma unroll
-        for (int f = 0; f < MAXF; ++f) wt[f] = WT[j * MAXF + f];
+        for (int f = 0; f < (F4 ? 4 : 1); ++f) wt[f] = WT[j * MAXF + f];
         uint32_t written[2] = {0, 0};
         // (HP) heads of one step from the h operand the cell warps just wrote: thread = (sequence r = 8 * warp + (lane & 7), unit
         // quarter lane >> 3): h = hi + lo of 16 units as four 16-byte reads each (a quarter-warp reads 128 contiguous bytes),
         // 4 x 16 FMAs against W_head^T, two shuffle-adds over the quarters, + bias -> head_out (no partial heads, no fold)
         const int hw = pt >> 5, hrr = lane & 7, hq = lane >> 3, hr = 8 * hw + hrr;
         long long hn = 0;                                       // head steps done
-        const float bh0 = (heads && NH > 0) ? b_head[0] : 0.f, bh1 = (heads && NH > 1) ? b_head[1] : 0.f;
-        const float bh2 = (heads && NH > 2) ? b_head[2] : 0.f, bh3 = (heads && NH > 3) ? b_head[3] : 0.f;
         int htile = blockIdx.x, ht = 0;
         auto do_head = [&]() {
             tc::mbar_wait(h_full, (uint32_t)hn & 1);
@@ -215,10 +213,10 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
             const int b = htile * TB + hr;
             if (hq == 0 && b < B) {
                 float* o = head_out + ((size_t)b * T + ht) * NH;
-                o[0] = a0 + bh0;
-                if (NH > 1) o[1] = a1 + bh1;
-                if (NH > 2) o[2] = a2 + bh2;
-                if (NH > 3) o[3] = a3 + bh3;
+                o[0] = a0 + __ldg(b_head);                              // (8 lanes per warp and step; the bias stays in L1)
+                if (NH > 1) o[1] = a1 + __ldg(b_head + 1);
+                if (NH > 2) o[2] = a2 + __ldg(b_head + 2);
+                if (NH > 3) o[3] = a3 + __ldg(b_head + 3);
             }
             ++hn;
             if (++ht == T) { ht = 0; htile += gridDim.x; }
@@ -244,7 +242,7 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
                         x = fmaf(wt[0], o.x, fmaf(wt[1], o.y, fmaf(wt[2], o.z, fmaf(wt[3], o.w, x))));
                     } else {
 #pragma unroll
-                        for (int f = 0; f < MAXF; ++f) if (f < Fin) x = fmaf(wt[f], __ldg(u + row * Fin + f), x);   // (static register indices)
+                        for (int f = 0; f < MAXF; ++f) if (f < Fin) x = fmaf(WT[j * MAXF + f], __ldg(u + row * Fin + f), x);
                     }
                     xv[i] = fmaxf(x, 0.f);
                 }
