@@ -61,7 +61,9 @@ constexpr int OP_BYTES = 2 * B_BYTES + C_BYTES;            // one operand set: h
 constexpr int EXF = 2 * NG * 2 * RW * 32;                  // swap buffer [pair][direction][slot][lane] floats
 constexpr int NBAR = 10;                                   // b_full, acc_done, acc_free, x_done, x_full[2], x_free[2], h_full, h_free
 #ifndef B200RL_FWD_HEADS_PROD
-#define B200RL_FWD_HEADS_PROD 1                            // 1: the heads are computed by the producer warps from the h operand in shared memory ; 0: by the cell warps (shuffle fold + partial heads)
+#define B200RL_FWD_HEADS_PROD 0                            // 0: heads by the cell warps (shuffle fold + partial heads) ; 1: by the producer warps from the h operand in shared
+                                                           // memory -- measured SLOWER (0.309 -> 0.360 ms: the producers lose their run-ahead and their 49 KB of operand reads per
+                                                           // step land in the window in which the tensor core reads the same operand); kept selectable, parity-tested in the emulator
 #endif
 constexpr bool HP = B200RL_FWD_HEADS_PROD != 0;
 constexpr int HLAG = 3;                                    // the producers run ~3 steps ahead of the cell phase with x: the heads of step i - 3 precede x of step i
