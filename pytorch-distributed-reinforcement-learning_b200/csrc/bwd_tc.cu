@@ -60,23 +60,24 @@ namespace btk {
 #ifndef B200RL_BWD_CELL_REGS
 #define B200RL_BWD_CELL_REGS 104                          // (4 issuers) the CTA owns NT x 96 registers from launch: 512 x 104 + 128 x 40 <= 640 x 96
 #endif
-constexpr int H = 64, G = 256, TB = 32, NC = 512;                   // 8 A + 8 B cell warps (+ NI MMA issuer warps)
-constexpr int nthreads(int ni) { return NC + 32 * ni; }
-constexpr int B_LBO = 144, B_SBO = 9216;                            // B: 64 core matrices along K, 16-byte skew -> conflict-free 16-byte stores
-constexpr int B_BYTES = (TB / 8) * B_SBO;                           // 36864 per hi / lo
+constexpr int H = 64, G = 256;
+// tile width TB = sequences per CTA = N of every MMA: 32, or 16 when 32-sequence tiles would leave more than half of the SMs idle
+// (recurrent_tile16, launchers.cuh); NC = 4 lane quarters x TB / 8 sequence groups cell warps (A + B), + NI MMA issuer warps
+constexpr int ncell(int tb) { return (tb / 8) * 128; }
+constexpr int nthreads(int ni, int tb) { return ncell(tb) + 32 * ni; }
+constexpr int B_LBO = 144, B_SBO = 9216;                            // B: 64 core matrices along K, 16-byte skew -> conflict-free 16-byte stores ; (TB / 8) * B_SBO bytes per hi / lo
 static_assert(63 * B_LBO + 128 <= B_SBO, "core matrices of one 8-row group must fit below SBO");
-constexpr int C_LBO = 144, C_SBO = 4608;                            // bf16 copy of dpre_hi (third split term): 32 core matrices (8 k) along K, same skew
-constexpr int C_BYTES = (TB / 8) * C_SBO;                           // 18432
+constexpr int C_LBO = 144, C_SBO = 4608;                            // bf16 copy of dpre_hi (third split term): 32 core matrices (8 k) along K, same skew ; (TB / 8) * C_SBO bytes
 static_assert(31 * C_LBO + 128 <= C_SBO, "core matrices of one 8-row group must fit below SBO");
-constexpr int TM_D = 0, TM_COLS = 512;                              // accumulator i at columns 32 i ; then A_hi (G columns) ; then A_lo: bf16 pairs, G/2 columns
-static_assert(4 * TB + G + G / 2 <= TM_COLS, "tensor memory budget (up to 4 accumulators)");
-static_assert(NC * B200RL_BWD_CELL_REGS + 128 * 40 <= nthreads(4) * 96, "setmaxnreg.inc would wait forever: the CTA's register pool is what it was launched with");
+constexpr int TM_D = 0, TM_COLS = 512;                              // accumulator i at columns TB i ; then A_hi (G columns) ; then A_lo: bf16 pairs, G/2 columns
+static_assert(4 * 32 + G + G / 2 <= TM_COLS, "tensor memory budget (up to 4 accumulators)");
+static_assert(ncell(32) * B200RL_BWD_CELL_REGS + 128 * 40 <= nthreads(4, 32) * 96, "setmaxnreg.inc would wait forever: the CTA's register pool is what it was launched with");
 constexpr int CT = 4;                                               // cells (sequences) a thread owns
 constexpr int RED = 4 * 10 * H;                                     // end-of-kernel reduction scratch: [sequence group][10][unit]
 }  // namespace btk
 
-static inline size_t bwdt_smem_bytes(int NH) {
-    return 2 * (size_t)btk::B_BYTES + btk::C_BYTES
+static inline size_t bwdt_smem_bytes(int NH, int TB) {
+    return 2 * (size_t)(TB / 8) * btk::B_SBO + (TB / 8) * btk::C_SBO
          + sizeof(float) * (size_t)(NH * btk::H + 16 * btk::CT * NH + 8 * btk::CT * 32 + 8 * 32 + btk::H * 4 + btk::H + btk::RED) + 64;
 }
 
@@ -86,13 +87,15 @@ struct BwdFuse {                 // fused head / torso gradients (null partials 
     int torso;                   // 1: dWt / dbt accumulated here (dx never stored) ; 0: only the head gradients, dx is stored
 };
 
-template <int NHT, int NI>        // NHT 0: runtime NH, small gradients left to their own kernels ; 1..4: NH == NHT at compile time, `fz` gradients fused ; NI: issuer warps
-__global__ void __launch_bounds__(btk::nthreads(NI), 1)
+template <int NHT, int NI, int TB> // NHT 0: runtime NH, small gradients left to their own kernels ; 1..4: NH == NHT at compile time, `fz` gradients fused ; NI: issuer warps ; TB: tile width
+__global__ void __launch_bounds__(btk::nthreads(NI, TB), 1)
 lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_head, const float* __restrict__ W_hh,
                  const float* __restrict__ W_ih, float* gates, const float* __restrict__ c_sav,
                  const float* __restrict__ cx0, float* __restrict__ dx, int B, int T, int NH, BwdFuse fz) {
     using namespace btk;
-    constexpr int NT = NC + 32 * NI, TM_AH = NI * TB, TM_AL = TM_AH + G;
+    static_assert(TB == 32 || TB == 16, "tile width");
+    constexpr int NC = (TB / 8) * 128, NG = TB / 8, NT = NC + 32 * NI, TM_AH = NI * TB, TM_AL = TM_AH + G;
+    constexpr int B_BYTES = (TB / 8) * B_SBO, C_BYTES = (TB / 8) * C_SBO;
     constexpr bool fuse = NHT > 0;
     if (fuse) NH = NHT;
     B200RL_DYN_SMEM(unsigned char, smem);
@@ -139,6 +142,7 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
     if (cellw) {
         const int m = 32 * q + lane;
         const float* wsrc = (m < H ? W_hh : W_ih) + (m & (H - 1));
+        for (int cgw = cg; cgw < 4; cgw += NG)                   // (16-sequence tiles have two sequence groups: each fills two column blocks)
         for (int k0 = 0; k0 < 64; k0 += 32) {
             float lo16[16];                                          // 32 bf16 of A_lo = 16 packed columns
 #pragma unroll
@@ -146,15 +150,15 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
                 float hi[16], lo[16];
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
-                    const int p = cg * 64 + k0 + hh * 16 + e, n = (p & 3) * H + (p >> 2);
+                    const int p = cgw * 64 + k0 + hh * 16 + e, n = (p & 3) * H + (p >> 2);
                     tc::split_tf32(wsrc[(size_t)n * H], hi[e], lo[e]);
                 }
-                tc::tmem_st16(tc::tmem_addr(tmem, my_lane, TM_AH + cg * 64 + k0 + hh * 16), hi);
+                tc::tmem_st16(tc::tmem_addr(tmem, my_lane, TM_AH + cgw * 64 + k0 + hh * 16), hi);
 #pragma unroll
                 for (int e = 0; e < 16; e += 2)
                     lo16[hh * 8 + e / 2] = __uint_as_float((unsigned)tc::bf16_bits(lo[e]) | ((unsigned)tc::bf16_bits(lo[e + 1]) << 16));
             }
-            tc::tmem_st16(tc::tmem_addr(tmem, my_lane, TM_AL + (cg * 64 + k0) / 2), lo16);
+            tc::tmem_st16(tc::tmem_addr(tmem, my_lane, TM_AL + (cgw * 64 + k0) / 2), lo16);
         }
     }
     tc::fence_async_smem();
@@ -166,7 +170,7 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
 
     if (!cellw) {
 #if !defined(B200RL_EMUL)
-        if constexpr (NI == 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");       // the four issuer warps are one warp-group: their registers go to the cell warps
+        if constexpr (NI == 4 && TB == 32) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");       // the four issuer warps are one warp-group: their registers go to the cell warps
 #endif
         if (lane == 0) {
             const int ii = warp - NC / 32;                           // K-steps [ii 32/NI, (ii+1) 32/NI) into accumulator ii
@@ -196,7 +200,7 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
         }
     } else {
 #if !defined(B200RL_EMUL)
-        if constexpr (NI == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(B200RL_BWD_CELL_REGS));
+        if constexpr (NI == 4 && TB == 32) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(B200RL_BWD_CELL_REGS));   // (16-sequence tiles: 384 threads, no register shortage)
 #endif
         const bool isB = q >= 2;                                     // B threads see the dx lanes, A threads the dh_rec lanes
         const int half = q & 1;
@@ -438,7 +442,8 @@ lstm_bwdt_kernel(const float* __restrict__ dhead, const float* __restrict__ W_he
         float* slab = fz.partials + (size_t)blockIdx.x * fz.P;
         for (int e = tid; e < 10 * H; e += NT) {
             const int k = e / H, jj = e - k * H;
-            const float v = (REDS[0 * 10 * H + e] + REDS[1 * 10 * H + e]) + (REDS[2 * 10 * H + e] + REDS[3 * 10 * H + e]);
+            float v = REDS[e] + REDS[10 * H + e];
+            if (NG == 4) v += REDS[2 * 10 * H + e] + REDS[3 * 10 * H + e];
             if (k < 4) { if (k < NHT) slab[fz.off_Whead + (size_t)k * H + jj] = v; }
             else if (k < 8) { if (ftorso) slab[fz.off_Wt + (size_t)jj * 4 + (k - 4)] = v; }
             else if (k == 8) { if (ftorso) slab[fz.off_bt + jj] = v; }
@@ -454,25 +459,30 @@ int launch_bwd_tc(const float* dhead, const float* W_head, const float* W_hh, co
                                B, T, 0, NH, sms, stream);
 }
 
-template <int NHT, int NI>
+template <int NHT, int NI, int TB>
 static int launch_bwdt_ni(const float* dhead, const float* W_head, const float* W_hh, const float* W_ih, float* gates,
                        const float* c, const float* cx0, float* dx, int B, int T, int NH, BwdFuse fz, int sms, void* stream) {
-    const int ntiles = (B + btk::TB - 1) / btk::TB;
-    const size_t smem = bwdt_smem_bytes(NH);
+    const int ntiles = (B + TB - 1) / TB;
+    const size_t smem = bwdt_smem_bytes(NH, TB);
 #ifndef B200RL_EMUL
-    cudaError_t e = cudaFuncSetAttribute(lstm_bwdt_kernel<NHT, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(lstm_bwdt_kernel<NHT, NI, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error("lstm_bwd(tc): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
 #endif
-    B200RL_LAUNCH((lstm_bwdt_kernel<NHT, NI>), ntiles < sms ? ntiles : sms, btk::nthreads(NI), smem, stream, dhead, W_head, W_hh, W_ih, gates, c, cx0, dx, B, T, NH, fz);
+    B200RL_LAUNCH((lstm_bwdt_kernel<NHT, NI, TB>), ntiles < sms ? ntiles : sms, btk::nthreads(NI, TB), smem, stream, dhead, W_head, W_hh, W_ih, gates, c, cx0, dx, B, T, NH, fz);
     return check_launch("lstm_bwd(tc)");
 }
 
 template <int NHT>
 static int launch_bwdt(const float* dhead, const float* W_head, const float* W_hh, const float* W_ih, float* gates,
                        const float* c, const float* cx0, float* dx, int B, int T, int NH, BwdFuse fz, int sms, void* stream) {
-    if (NHT > 0 && fz.torso)
-        return launch_bwdt_ni<NHT, (NHT > 0 ? B200RL_BWD_NI_TORSO : B200RL_BWD_NI)>(dhead, W_head, W_hh, W_ih, gates, c, cx0, dx, B, T, NH, fz, sms, stream);
-    return launch_bwdt_ni<NHT, B200RL_BWD_NI>(dhead, W_head, W_hh, W_ih, gates, c, cx0, dx, B, T, NH, fz, sms, stream);
+    constexpr int NIT = NHT > 0 ? B200RL_BWD_NI_TORSO : B200RL_BWD_NI;
+    // (T >= 2: a CTA writes one slab row of the fused gradients, and there are min(2 SMs, B T / 32) rows)
+    if (recurrent_tile16(B, sms) && T >= 2) {
+        if (NHT > 0 && fz.torso) return launch_bwdt_ni<NHT, NIT, 16>(dhead, W_head, W_hh, W_ih, gates, c, cx0, dx, B, T, NH, fz, sms, stream);
+        return launch_bwdt_ni<NHT, B200RL_BWD_NI, 16>(dhead, W_head, W_hh, W_ih, gates, c, cx0, dx, B, T, NH, fz, sms, stream);
+    }
+    if (NHT > 0 && fz.torso) return launch_bwdt_ni<NHT, NIT, 32>(dhead, W_head, W_hh, W_ih, gates, c, cx0, dx, B, T, NH, fz, sms, stream);
+    return launch_bwdt_ni<NHT, B200RL_BWD_NI, 32>(dhead, W_head, W_hh, W_ih, gates, c, cx0, dx, B, T, NH, fz, sms, stream);
 }
 
 // partials != nullptr: head gradients fused (NH <= 4); with dx == nullptr also the torso gradients (Fin == 4) and dx is never stored

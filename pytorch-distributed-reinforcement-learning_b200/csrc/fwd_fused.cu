@@ -27,6 +27,7 @@
 //
 // Layouts: gates (B, T, 64, 4) = post-activation (i, f, g, o) of a unit as one float4 ; c, h (B, T, 64) ; head_part
 // (B, T, 2, NH) ; everything a thread stores is a full 16-byte / 128-byte-per-warp line segment.
+#include <cstdlib>
 #include "common.cuh"
 #include "tc05.cuh"
 #include "launchers.cuh"
@@ -43,22 +44,16 @@ __device__ unsigned long long g_fwd3prof[16];
 #endif
 
 namespace ffk {
-constexpr int H = 64, TB = 32, MAXF = 8, MAXNH = 4;
-constexpr int NG = 4, RW = TB / NG, CT = RW / 2;          // sequence groups, sequences a warp reads, cells a thread owns
+constexpr int H = 64, MAXF = 8, MAXNH = 4;
+constexpr int RW = 8, CT = RW / 2;                         // sequences a warp reads from tensor memory, cells a thread owns
 #ifndef B200RL_FWD3_SEP
 #define B200RL_FWD3_SEP 1                                  // 1: separate issuer warps for the input projection (+ setmaxnreg) ; 0: the 4 recurrent issuers do both
 #endif
 constexpr int NI = 4;                                      // issuers per operand: (M tile) x (even / odd K-steps), one accumulator each
 constexpr int NIW = B200RL_FWD3_SEP ? 2 * NI : NI;         // issuer warps
-constexpr int NPW = 4;                                     // producer warps: the torso output x_t as a K-major operand, two steps ahead
-constexpr int NC = NG * 128, NT = NC + 32 * NIW + 32 * NPW;
 constexpr int TM_D = 0, TM_HH = 128, TM_IH = 256, TM_HHL = 384, TM_IHL = 448, TM_COLS = 512;
 constexpr int B_LBO = 144, B_SBO = 2304;                   // TF32 B operand: 16 core matrices (4 k) along K, 16-byte skew -> conflict-free 4-byte scatter
-constexpr int B_BYTES = (TB / 8) * B_SBO;                  // 9216 per hi / lo
 constexpr int C_LBO = 144, C_SBO = 1152;                   // bf16 B operand: 8 core matrices (8 k) along K
-constexpr int C_BYTES = (TB / 8) * C_SBO;                  // 4608
-constexpr int OP_BYTES = 2 * B_BYTES + C_BYTES;            // one operand set: hi | lo | bf16(hi)
-constexpr int EXF = 2 * NG * 2 * RW * 32;                  // swap buffer [pair][direction][slot][lane] floats
 constexpr int NBAR = 10;                                   // b_full, acc_done, acc_free, x_done, x_full[2], x_free[2], h_full, h_free
 #ifndef B200RL_FWD_HEADS_PROD
 #define B200RL_FWD_HEADS_PROD 0                            // 0: heads by the cell warps (shuffle fold + partial heads) ; 1: by the producer warps from the h operand in shared
@@ -69,14 +64,25 @@ constexpr bool HP = B200RL_FWD_HEADS_PROD != 0;
 constexpr int HLAG = 3;                                    // the producers run ~3 steps ahead of the cell phase with x: the heads of step i - 3 precede x of step i
 static_assert(15 * B_LBO + 128 <= B_SBO && 7 * C_LBO + 128 <= C_SBO, "core matrices of one 8-row group must fit below SBO");
 static_assert(RW == 8 && CT == 4, "cell phase layout");
+// Everything that depends on the tile width TB (sequences per CTA = the N of every MMA): 32 for full batches, 16 when the
+// batch has too few 32-sequence tiles to fill half the SMs (B = 2048: 128 CTAs of 16 sequences instead of 64 of 32 -- the
+// kernel is bound by the per-step chain, and half the cells per CTA shorten the cell phase of every step)
+template <int TB>
+struct Tile {
+    static_assert(TB == 32 || TB == 16, "tile width");
+    static constexpr int NG = TB / RW;                      // sequence groups = cell warps per TMEM lane quarter
+    static constexpr int NPW = TB / 8;                      // producer warps: the torso output x_t as a K-major operand, two steps ahead (thread = unit x 16 sequences)
+    static constexpr int NC = NG * 128, NT = NC + 32 * NIW + 32 * NPW;
+    static constexpr int B_BYTES = (TB / 8) * B_SBO;        // 9216 per hi / lo at TB = 32
+    static constexpr int C_BYTES = (TB / 8) * C_SBO;        // 4608
+    static constexpr int OP_BYTES = 2 * B_BYTES + C_BYTES;  // one operand set: hi | lo | bf16(hi)
+    static constexpr int EXF = 2 * NG * 2 * RW * 32;        // swap buffer [pair][direction][slot][lane] floats
+    static constexpr size_t smem_bytes() { return 3 * (size_t)OP_BYTES + sizeof(float) * (EXF + H * 4 + H * MAXF + H + H * 4) + 8 * NBAR + 64; }
+};
 }  // namespace ffk
 
-static inline size_t fwd_fused_smem_bytes() {
-    return 3 * (size_t)ffk::OP_BYTES + sizeof(float) * (ffk::EXF + ffk::H * 4 + ffk::H * ffk::MAXF + ffk::H + ffk::H * 4) + 8 * ffk::NBAR + 64;
-}
-
-template <bool F4>
-__global__ void __launch_bounds__(ffk::NT, 1)
+template <bool F4, int TB>
+__global__ void __launch_bounds__(ffk::Tile<TB>::NT, 1)
 lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0, const float* __restrict__ cx0,
                       const float* __restrict__ Wt, const float* __restrict__ bt, const float* __restrict__ W_ih,
                       const float* __restrict__ W_hh, const float* __restrict__ b_ih, const float* __restrict__ b_hh,
@@ -84,6 +90,8 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
                       float* __restrict__ h_out, float* __restrict__ head_part, const float* __restrict__ b_head,
                       float* __restrict__ head_out, int B, int T, int Fin, int NH) {
     using namespace ffk;
+    using TL = Tile<TB>;
+    constexpr int NPW = TL::NPW, NC = TL::NC, NT = TL::NT, B_BYTES = TL::B_BYTES, OP_BYTES = TL::OP_BYTES, EXF = TL::EXF;
     B200RL_DYN_SMEM(unsigned char, smem);
     unsigned char* OPH = smem;                              // h_{t-1}: hi | lo | bf16
     unsigned char* OPX = smem + OP_BYTES;                   // x_t: two sets
@@ -172,7 +180,8 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
 
     if (producer) {
 #ifndef B200RL_EMUL
-        if (F4) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");      // (generic torso widths keep the 72 registers of the launch: the 8192 the cell warps gain are exactly what the issuers give back)
+        if constexpr (F4 && TB == 32) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");   // (generic torso widths keep the 72 registers of the launch: the 8192 the cell warps gain are exactly what
+                                                                                            // the issuers give back ; the 576 threads of a 16-sequence tile start with 96 each: nothing to move)
 #endif
         // x[r][j] = ReLU(bt[j] + Wt[j] . obs[r, t]) for the tile's 32 sequences: thread = (unit j, 16 of the sequences), element
         // (r, j) of operand set t & 1 as TF32 hi / lo and bf16(hi)
@@ -265,7 +274,7 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
         if (HP && heads) while (hn < nsteps) do_head();         // the last HLAG steps
     } else if (!compute) {
 #if !defined(B200RL_EMUL)
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if constexpr (TB == 32) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
 #endif
         if (lane == 0) {
             const int iw = warp - NC / 32;
@@ -325,7 +334,7 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
         }
     } else {
 #if !defined(B200RL_EMUL)
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+        if constexpr (TB == 32) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
 #endif
         const int q = warp & 3, ch = warp >> 2;                // TMEM lane quarter, sequence group
         const bool fo = q >= 2;                                // false: gates (i, g) ; true: gates (f, o)
@@ -469,6 +478,31 @@ lstm_fwd_fused_kernel(const float* __restrict__ u, const float* __restrict__ hx0
     }
 }
 
+template <bool F4, int TB>
+static int launch_fwd_fused_t(const float* u, const float* hx0, const float* cx0, const float* Wt, const float* bt, const float* W_ih,
+                              const float* W_hh, const float* b_ih, const float* b_hh, const float* W_head, const float* b_head,
+                              float* gates, float* c, float* h, float* head_part, float* head_out,
+                              int B, int T, int Fin, int NH, int sms, void* stream) {
+    const int ntiles = (B + TB - 1) / TB;
+    const size_t smem = ffk::Tile<TB>::smem_bytes();
+    const int grid = ntiles < sms ? ntiles : sms;
+#ifndef B200RL_EMUL
+    cudaError_t e = cudaFuncSetAttribute(lstm_fwd_fused_kernel<F4, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error("lstm_fwd_fused: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
+#endif
+    B200RL_LAUNCH((lstm_fwd_fused_kernel<F4, TB>), grid, ffk::Tile<TB>::NT, smem, stream, u, hx0, cx0, Wt, bt, W_ih, W_hh, b_ih, b_hh, W_head,
+                  gates, c, h, head_part, b_head, head_out, B, T, Fin, NH);
+    return check_launch("lstm_fwd_fused");
+}
+
+// 16-sequence tiles when the batch would leave more than half of the SMs without a 32-sequence tile
+bool recurrent_tile16(int B, int sms) {
+    static const int mode = [] { const char* e = getenv("B200RL_TILE16"); return e ? atoi(e) : -1; }();    // 0: never, 1: always (A/B), unset: by batch size
+    if (mode == 0) return false;
+    if (mode == 1) return true;
+    return (B + 31) / 32 <= sms / 2;
+}
+
 int launch_fwd_fused(const float* u, const float* hx0, const float* cx0, const float* Wt, const float* bt, const float* W_ih,
                      const float* W_hh, const float* b_ih, const float* b_hh, const float* W_head, const float* b_head,
                      float* gates, float* c, float* h, float* head_part, float* head_out,
@@ -476,25 +510,10 @@ int launch_fwd_fused(const float* u, const float* hx0, const float* cx0, const f
     B200RL_REQUIRE((long long)B * T < (1LL << 31), "lstm_fwd_fused: B*T must be below 2^31");
     B200RL_REQUIRE(Fin >= 1 && Fin <= ffk::MAXF, "lstm_fwd_fused: Fin=%d out of range [1,%d]", Fin, ffk::MAXF);
     B200RL_REQUIRE(head_part == nullptr || (NH >= 1 && NH <= ffk::MAXNH && head_out != nullptr), "lstm_fwd_fused: fused heads need 1 <= NH <= %d", ffk::MAXNH);
-    const int ntiles = (B + ffk::TB - 1) / ffk::TB;
-    const size_t smem = fwd_fused_smem_bytes();
-    const int grid = ntiles < sms ? ntiles : sms;
-    if (Fin == 4) {
-#ifndef B200RL_EMUL
-        cudaError_t e = cudaFuncSetAttribute(lstm_fwd_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return set_error("lstm_fwd_fused: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
-#endif
-        B200RL_LAUNCH(lstm_fwd_fused_kernel<true>, grid, ffk::NT, smem, stream, u, hx0, cx0, Wt, bt, W_ih, W_hh, b_ih, b_hh, W_head,
-                      gates, c, h, head_part, b_head, head_out, B, T, Fin, NH);
-    } else {
-#ifndef B200RL_EMUL
-        cudaError_t e = cudaFuncSetAttribute(lstm_fwd_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return set_error("lstm_fwd_fused: cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e));
-#endif
-        B200RL_LAUNCH(lstm_fwd_fused_kernel<false>, grid, ffk::NT, smem, stream, u, hx0, cx0, Wt, bt, W_ih, W_hh, b_ih, b_hh, W_head,
-                      gates, c, h, head_part, b_head, head_out, B, T, Fin, NH);
-    }
-    return check_launch("lstm_fwd_fused");
+#define B200RL_FF_ARGS u, hx0, cx0, Wt, bt, W_ih, W_hh, b_ih, b_hh, W_head, b_head, gates, c, h, head_part, head_out, B, T, Fin, NH, sms, stream
+    if (recurrent_tile16(B, sms)) return Fin == 4 ? launch_fwd_fused_t<true, 16>(B200RL_FF_ARGS) : launch_fwd_fused_t<false, 16>(B200RL_FF_ARGS);
+    return Fin == 4 ? launch_fwd_fused_t<true, 32>(B200RL_FF_ARGS) : launch_fwd_fused_t<false, 32>(B200RL_FF_ARGS);
+#undef B200RL_FF_ARGS
 }
 
 }  // namespace b200rl

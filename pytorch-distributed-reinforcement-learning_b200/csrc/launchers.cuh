@@ -22,6 +22,8 @@ int launch_fwd_fused(const float* u, const float* hx0, const float* cx0, const f
                      const float* W_hh, const float* b_ih, const float* b_hh, const float* W_head, const float* b_head,
                      float* gates, float* c, float* h, float* head_part, float* head_out,
                      int B, int T, int Fin, int NH, int sms, void* stream);
+// fwd_fused.cu: the recurrent kernels (fwd_fused, bwd_tc) run 16-sequence tiles when 32-sequence tiles would leave more than half of the SMs idle
+bool recurrent_tile16(int B, int sms);
 // dx_tc.cu: torso gradients from a stored dx (written by bwd_tc.cu) + head gradients
 int launch_torso_from_dx(const float* dx, const float* u, const float* Wt, const float* bt,
                          const float* h, const float* dhead, float* partials, int nparts, long long P,
