@@ -622,8 +622,9 @@ def main():
             timed.barrier()
             out["strong_scaling"] = {"global_batch_sequences": B, "sequences_per_gpu": Bs, "ms_per_step": ms_s,
                                      "value": B * T / (ms_s * 1e-3), "unit": UNIT,
-                                     "note": "the recurrent kernels are bound by 128 dependent timesteps per sequence tile, not by "
-                                             "the number of tiles: below one 32-sequence tile per SM the step time stops shrinking"}
+                                     "note": "the recurrent kernels are bound by 128 dependent timesteps per sequence tile; shards that leave more "
+                                             "than half of the SMs without a 32-sequence tile run 16-sequence tiles (half the cell phase per "
+                                             "step); below one 16-sequence tile per SM the step time stops shrinking"}
 
     if rank == 0:
         # ---- per-kernel device times (alone, CUDA events) and the roofline of the dominant one
@@ -677,7 +678,7 @@ def main():
         out["roofline"] = {
             "kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
             "traffic": load_traffic(dom), "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes[dom],
-            "limited_by": "latency: persistent recurrent kernel, 128 dependent timesteps per 32-sequence tile (tcgen05 issue -> "
+            "limited_by": "latency: persistent recurrent kernel, 128 dependent timesteps per 32-sequence tile (80 small tcgen05 MMAs -> "
                           "accumulator hand-over -> TMEM load -> MUFU cell phase -> operand rewrite); neither the HBM nor the "
                           "tensor roofline is reached -- `frac` is the HBM-roofline fraction the metric asks for",
             "tensor_pipe": {"kernels": sorted(algo_flop), "model_tflops": sum(algo_flop.values()) / (gemm_ms * 1e-3) / 1e12,
