@@ -5,14 +5,16 @@ body does (`agents/learner_module/{ppo,impala}/learning.py:36-106`): forward ove
 (B, T) window, GAE / V-trace, loss, backward, clip_grad_norm_, RMSprop step -- with no
 Python loop over T, no autograd graph and no host sync:
 
-    lstm_fwd -> head_fwd -> {ppo,impala}_head -> lstm_bwd -> lstm_wgrad
-             -> reduce_partials -> [NCCL all-reduce of the flat gradient] -> clip_rmsprop
+    fused forward (torso + input projection + recurrence + heads) -> {ppo,impala}_head (scan + loss + d/d heads)
+      -> BPTT (+ head / torso gradients) -> weight gradients -> reduce_partials
+      -> peer step (gradient exchange over NVLink peer memory + global-norm clip + RMSprop, ONE kernel at every world size)
 
 Multi-GPU: sequences are independent, every loss is a mean over
 B*(T-1) elements, so B shards evenly across ranks; each rank computes the gradient of
-its shard mean, ONE all-reduce(sum) of the flat gradient (+ the 8 loss scalars riding
-in a second tiny buffer) and a 1/world scale inside the optimizer kernel reproduce the
-full-batch gradient; the global-norm clip comes after the reduction.
+its shard mean, ONE exchange (sum) of the flat gradient (+ the 8 loss scalars riding
+along) and a 1/world scale inside the step kernel reproduce the full-batch gradient; the
+global-norm clip comes after the reduction.  Communicators without peer memory (gloo tests,
+`B200RL_PEER=0`) fall back to an all-reduce + the single-CTA clip / optimizer kernels.
 """
 import math
 import os

@@ -13,17 +13,20 @@
 //     accumulators 4 x 32 columns -- exactly the 512 columns of an SM.
 //   * split precision as in the backward kernel: A_hi . B_hi + A_hi . B_lo in kind::tf32, the third term A_lo . B_hi (2^-11 of
 //     the result) in kind::f16 (bf16, K = 16): 20 MMAs per (tile, operand) instead of 24.
-//   * x_t is produced by the cell warps themselves, TWO steps ahead and off the critical path (4 FMAs per element from the
+//   * x_t is produced by dedicated producer warps, TWO steps ahead and off the critical path (4 FMAs per element from the
 //     Fin-wide observation), as a K-major B operand (hi / lo / bf16) in a double-buffered shared-memory slot; dedicated issuer
 //     warps run the input-projection MMAs of step t+1 into the accumulators WHILE the cell phase of step t runs (they only
 //     wait for the accumulators to have been read), so the recurrent MMAs of step t+1 -- the only ones on the serial chain --
 //     accumulate on top as soon as h_t is written.  The serial chain carries 40 MMAs per step instead of 48.
 //   * the heads: after a thread has handed h_t to the tensor core it multiplies its 4 cells by the head rows of its unit and the
 //     warp folds the 16 (sequence, output) sums with 16 shuffles; each unit-half warp stores its partial head (12.6 MB per
-//     update instead of re-reading 134 MB of h); head_combine_kernel adds the two halves and the bias.
+//     update instead of re-reading 134 MB of h); after its last step the CTA adds the two halves and the bias of its own sequences.
+//   * the tile width (sequences per CTA = N of the MMAs) is a template parameter: 32, or 16 for batches that would leave more
+//     than half of the SMs without a tile (`recurrent_tile16`): twice the CTAs, half the cell warps, a shorter cell phase per step.
 //
-// Register budget: 16 cell warps + 8 issuer warps = 768 threads = 80 registers each at launch; the issuer warp-groups give
-// theirs back (setmaxnreg.dec 40) and the cell warp-groups grow to 96 (setmaxnreg.inc); ptxas allocates per region.
+// Register budget (32-sequence tiles): 16 cell + 8 issuer + 4 producer warps = 896 threads = 72 registers each at launch; the
+// issuer warp-groups give theirs back (setmaxnreg.dec 40), the producers keep 64 and the cell warp-groups grow to 88
+// (setmaxnreg.inc); ptxas allocates per region.  16-sequence tiles: 576 threads with 96 registers each, nothing to move.
 //
 // Layouts: gates (B, T, 64, 4) = post-activation (i, f, g, o) of a unit as one float4 ; c, h (B, T, 64) ; head_part
 // (B, T, 2, NH) ; everything a thread stores is a full 16-byte / 128-byte-per-warp line segment.
