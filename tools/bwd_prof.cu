@@ -8,6 +8,7 @@
 namespace b200rl {
 int set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vfprintf(stderr, fmt, ap); va_end(ap); fputc('\n', stderr); return 1; }
 int check_launch(const char* what) { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) return set_error("%s: %s", what, cudaGetErrorString(e)); return 0; }
+bool recurrent_tile16(int B, int sms) { const char* e = getenv("B200RL_TILE16"); return e ? atoi(e) != 0 : (B + 31) / 32 <= sms / 2; }   // (the library's lives in fwd_fused.cu)
 }
 #include "bwd_tc.cu"
 using namespace b200rl;
